@@ -1,0 +1,13 @@
+"""B200-native (sm_100a) point-set hot path of HyperPocket (gmum/3d-point-clouds-autocomplete).
+
+The directory name is not a Python identifier; import it with
+``importlib.import_module("3d-point-clouds-autocomplete_b200")`` or through the ``hp_b200``
+shim at the repository root.  ``dropin/`` mirrors the reference's import paths
+(``losses.champfer_loss``, ``utils.pytorch_structural_losses.*``, ``model.target_network``,
+``utils.metrics``) for use on ``sys.path`` ahead of the reference tree.
+"""
+from . import _native  # noqa: F401
+from .chamfer import (ChamferLoss, NNDistance, NNDistanceFunction, NNDistanceGrad, chamfer_backward,  # noqa: F401
+                      chamfer_forward, nn_distance)
+
+__version__ = "0.1.0"

@@ -1,0 +1,77 @@
+"""ctypes binding of libhp_b200.so (include/hp_b200.h).
+
+Host-side plumbing only: torch supplies device memory and the current stream, every
+computation happens in the sm_100a kernels behind the C ABI.  There is NO fallback: if the
+shared library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "lib", "libhp_b200.so")
+
+HP_OK = 0
+HP_ERR_INVALID_ARGUMENT, HP_ERR_CUDA, HP_ERR_UNSUPPORTED, HP_ERR_WORKSPACE = 1, 2, 3, 4
+
+_lib = None
+_lock = threading.Lock()
+
+_vp = ctypes.c_void_p
+_int = ctypes.c_int
+_sz = ctypes.c_size_t
+_ll = ctypes.c_longlong
+
+# name -> (restype, argtypes).  Must list every function include/hp_b200.h declares
+# (tests/test_abi_symbols.py cross-checks this table against the header).
+SIGNATURES = {
+    "hp_version": (_int, []),
+    "hp_error_string": (ctypes.c_char_p, [_int]),
+    "hp_last_error_message": (ctypes.c_char_p, []),
+    "hp_nndistance": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hp_nndistancegrad": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hp_chamfer_workspace_bytes": (_sz, [_int, _int, _int]),
+    "hp_chamfer_forward": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hp_chamfer_backward": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hp_measure_peak": (_int, [_int, _int, ctypes.POINTER(ctypes.c_double), _vp]),
+}
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load libhp_b200.so; raise loudly if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NativeLibraryMissing(
+                    f"{LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    f"or `python {os.path.join(_PKG_DIR, 'build.py')}`. There is no CPU or PyTorch fallback.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)  # AttributeError if the library is stale: loud by design
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != HP_OK:
+        lib = load()
+        msg = lib.hp_last_error_message().decode(errors="replace")
+        kind = lib.hp_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed: {kind} (code {rc}): {msg}")
+
+
+def measure_peak(kind: int, iters: int = 4096, stream: int = 0) -> float:
+    out = ctypes.c_double(0.0)
+    check(load().hp_measure_peak(kind, iters, ctypes.byref(out), stream), "hp_measure_peak")
+    return out.value

@@ -1,0 +1,478 @@
+// chamfer.cu -- nearest-neighbour (Chamfer) forward / backward for sm_100a.
+//
+// Replaces NmDistanceKernel / NmDistanceGradKernel of the reference
+// (utils/pytorch_structural_losses/nndistance.cu:8-160) behind hp_nndistance,
+// hp_nndistancegrad, hp_chamfer_forward, hp_chamfer_backward (include/hp_b200.h).
+//
+// Forward design (one launch, both directions):
+//   * a CTA owns THREADS*RQ query points of one cloud and one direction; every thread keeps
+//     RQ queries in registers (each coordinate duplicated into an fp32x2 pair);
+//   * the candidate cloud is brought into shared memory with ONE 1-D bulk-TMA copy per
+//     chunk (cp.async.bulk, mbarrier completion), then re-laid out SoA so that an LDS.128
+//     delivers the same coordinate of 4 consecutive candidates = two ready-made fp32x2 pairs;
+//   * the K=3 contraction stays on the FP32 pipe: FADD2/FMUL2/FFMA2 evaluate two candidates
+//     per instruction with the reference's exact association, FMNMX3 folds two distances
+//     into the running minimum per instruction;
+//   * only the minimum VALUE is tracked in the hot loop; the sub-chunk (16 candidates) in
+//     which the running minimum last strictly improved is remembered, and the argmin is
+//     recovered afterwards by re-evaluating that one sub-chunk and taking the lowest index
+//     with d == min (bit-exact same arithmetic) -> identical to the reference's
+//     "strict <, lowest index wins" rule (nndistance.cu:32-64,117-125);
+//   * optional fused loss: per-CTA partial sums in fixed order, last CTA folds them.
+#include "common.cuh"
+
+namespace hp {
+
+constexpr int NN_CH = 16;  // candidates per index-tracking sub-chunk
+
+struct NNArgs {
+    const float *set[2];  // set[0] = xyz1 [b,n,3], set[1] = xyz2 [b,m,3]
+    float *dist[2];
+    int *idx[2];
+    int npts[2];
+    int tiles[2];  // query tiles per cloud, per direction
+    int b;
+    float *loss;            // nullptr -> no fused loss
+    float *partial;         // [gridDim.x]
+    unsigned int *counter;  // zero on entry, zero on exit
+};
+
+template <int THREADS, int RQ, int MC>
+__global__ void __launch_bounds__(THREADS) nn_fwd_kernel(const NNArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *stage = reinterpret_cast<float *>(smem_raw);  // [MC*3] AoS landing zone of the bulk copy
+    float *xs = stage + MC * 3;                          // [MC] each, SoA
+    float *ys = xs + MC;
+    float *zs = ys + MC;
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ float warp_part[THREADS / 32];
+    __shared__ int last_flag;
+
+    const int tid = threadIdx.x;
+    const int tiles0 = a.b * a.tiles[0];
+    const int dir = (int)blockIdx.x >= tiles0 ? 1 : 0;
+    const int t = dir ? (int)blockIdx.x - tiles0 : (int)blockIdx.x;
+    const int tiles_d = dir ? a.tiles[1] : a.tiles[0];
+    const int cloud = t / tiles_d;
+    const int qtile = t - cloud * tiles_d;
+    const int nq = dir ? a.npts[1] : a.npts[0], nc = dir ? a.npts[0] : a.npts[1];
+    const float *__restrict__ Q = (dir ? a.set[1] : a.set[0]) + (size_t)cloud * nq * 3;
+    const float *__restrict__ C = (dir ? a.set[0] : a.set[1]) + (size_t)cloud * nc * 3;
+    float *__restrict__ out_d = (dir ? a.dist[1] : a.dist[0]) + (size_t)cloud * nq;
+    int *__restrict__ out_i = (dir ? a.idx[1] : a.idx[0]) + (size_t)cloud * nq;
+
+    if (tid == 0) mbar_init(&mbar, 1);
+
+    // queries -> registers
+    f32x2 qx[RQ], qy[RQ], qz[RQ];
+    float qxs[RQ], qys[RQ], qzs[RQ];
+    float best[RQ];
+    int bsub[RQ];
+#pragma unroll
+    for (int r = 0; r < RQ; ++r) {
+        int q = qtile * (THREADS * RQ) + r * THREADS + tid;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (q < nq) {
+            x = __ldg(Q + (size_t)q * 3 + 0);
+            y = __ldg(Q + (size_t)q * 3 + 1);
+            z = __ldg(Q + (size_t)q * 3 + 2);
+        }
+        qxs[r] = x, qys[r] = y, qzs[r] = z;
+        qx[r] = pack2(x, x), qy[r] = pack2(y, y), qz[r] = pack2(z, z);
+        best[r] = __int_as_float(0x7f800000);
+        bsub[r] = 0;
+    }
+    __syncthreads();  // mbarrier init visible
+
+    uint32_t phase = 0;
+    for (int c0 = 0; c0 < nc; c0 += MC) {
+        const int cnt = min(MC, nc - c0);
+        const float *src = C + (size_t)c0 * 3;
+        const bool tma_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+        const uint32_t bulk_bytes = tma_ok ? ((uint32_t)(cnt * 12) & ~15u) : 0u;
+        if (bulk_bytes) {
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&mbar, bulk_bytes);
+                bulk_g2s(stage, src, bulk_bytes, &mbar);
+            }
+        }
+        // tail (or everything, when the source is not 16-byte aligned): plain coalesced loads
+        for (int i = (int)(bulk_bytes / 4) + tid; i < cnt * 3; i += THREADS) stage[i] = __ldg(src + i);
+        if (bulk_bytes) {
+            mbar_wait(&mbar, phase);
+            phase ^= 1;
+        }
+        __syncthreads();
+        // AoS -> SoA; pad the last sub-chunk with +inf coordinates (distance +inf, never a minimum)
+        const int padded = (cnt + NN_CH - 1) / NN_CH * NN_CH;
+        for (int i = tid; i < padded; i += THREADS) {
+            float x = __int_as_float(0x7f800000), y = x, z = x;
+            if (i < cnt) x = stage[i * 3 + 0], y = stage[i * 3 + 1], z = stage[i * 3 + 2];
+            xs[i] = x, ys[i] = y, zs[i] = z;
+        }
+        __syncthreads();
+
+        const int nsub = padded / NN_CH;
+        const int sub0 = c0 / NN_CH;
+        for (int s = 0; s < nsub; ++s) {
+            const ulonglong2 *x4 = reinterpret_cast<const ulonglong2 *>(xs + s * NN_CH);
+            const ulonglong2 *y4 = reinterpret_cast<const ulonglong2 *>(ys + s * NN_CH);
+            const ulonglong2 *z4 = reinterpret_cast<const ulonglong2 *>(zs + s * NN_CH);
+            float cur[RQ];
+#pragma unroll
+            for (int r = 0; r < RQ; ++r) cur[r] = best[r];
+#pragma unroll
+            for (int v = 0; v < NN_CH / 4; ++v) {
+                const ulonglong2 cx = x4[v], cy = y4[v], cz = z4[v];
+#pragma unroll
+                for (int r = 0; r < RQ; ++r) {
+                    f32x2 d01 = sqdist_exact2(qx[r], qy[r], qz[r], cx.x, cy.x, cz.x);
+                    f32x2 d23 = sqdist_exact2(qx[r], qy[r], qz[r], cx.y, cy.y, cz.y);
+                    float d0, d1, d2, d3;
+                    unpack2(d01, d0, d1);
+                    unpack2(d23, d2, d3);
+                    cur[r] = min3(cur[r], d0, d1);
+                    cur[r] = min3(cur[r], d2, d3);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RQ; ++r) {
+                if (cur[r] < best[r]) {  // strict: an equal minimum in a later sub-chunk never wins
+                    best[r] = cur[r];
+                    bsub[r] = sub0 + s;
+                }
+            }
+        }
+        __syncthreads();  // everyone done with xs/ys/zs and stage before the next chunk lands
+    }
+
+    // argmin recovery + store
+    float lsum = 0.f;
+#pragma unroll
+    for (int r = 0; r < RQ; ++r) {
+        int q = qtile * (THREADS * RQ) + r * THREADS + tid;
+        if (q < nq) {
+            int base = bsub[r] * NN_CH;
+            int found = base;
+#pragma unroll 4
+            for (int k = NN_CH - 1; k >= 0; --k) {
+                int c = base + k;
+                if (c < nc) {
+                    float d = sqdist_exact(qxs[r], qys[r], qzs[r], __ldg(C + (size_t)c * 3 + 0),
+                                           __ldg(C + (size_t)c * 3 + 1), __ldg(C + (size_t)c * 3 + 2));
+                    if (d == best[r]) found = c;
+                }
+            }
+            out_d[q] = best[r];
+            out_i[q] = found;
+            lsum += best[r];
+        }
+    }
+
+    if (a.loss != nullptr) {
+        // deterministic: fixed shuffle tree, warps in ascending order, tiles in ascending order
+        float w = warp_sum(lsum);
+        if ((tid & 31) == 0) warp_part[tid >> 5] = w;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < THREADS / 32; ++i) s += warp_part[i];
+            a.partial[blockIdx.x] = s;
+            __threadfence();
+            unsigned int prev = atomicAdd(a.counter, 1u);
+            last_flag = (prev == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (last_flag) {
+            __threadfence();
+            float s = 0.f;
+            for (int i = tid; i < (int)gridDim.x; i += THREADS) s += __ldcg(a.partial + i);
+            s = warp_sum(s);
+            if ((tid & 31) == 0) warp_part[tid >> 5] = s;
+            __syncthreads();
+            if (tid == 0) {
+                float tot = 0.f;
+#pragma unroll
+                for (int i = 0; i < THREADS / 32; ++i) tot += warp_part[i];
+                a.loss[0] = tot;
+                *a.counter = 0u;  // restore the workspace invariant
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward.  One CTA per (cloud, side).  "own" = the set whose gradient this CTA writes,
+// "other" = the opposite set.
+//   grad_own[i] = 2 g_own[i] (P_i - O_{idx_own[i]})  +  sum_{k : idx_other[k]==i} -(2 g_other[k] (O_k - P_i))
+// (nndistance.cu:143-151).  The second term needs the inverse of idx_other: a stable counting
+// sort of k by key idx_other[k] in shared memory (integer atomics for the histogram only,
+// one warp places the entries in ascending k with __match_any_sync ranks), then each thread
+// gathers its bucket in ascending k -> no float atomics, bitwise reproducible.
+// ------------------------------------------------------------------------------------------
+struct NNGradArgs {
+    const float *set[2];
+    const int *idx[2];
+    const float *gdist[2];  // per-point upstream grads, or (scalar_grad) one device float each
+    float *grad[2];
+    int npts[2];
+    int b;
+    int scalar_grad;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) nn_grad_kernel(const NNGradArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int side = blockIdx.x & 1;
+    const int cloud = blockIdx.x >> 1;
+    const int np = side ? a.npts[1] : a.npts[0], no = side ? a.npts[0] : a.npts[1];
+    int *start = reinterpret_cast<int *>(smem_raw);  // [np+1] bucket starts (exclusive scan of counts)
+    int *cursor = start + (np + 1);                  // [np]   running fill position
+    int *perm = cursor + np;                         // [no]   k sorted by key, stable
+    __shared__ int scan_part[THREADS];
+    __shared__ int scan_total;
+
+    const float *__restrict__ P = (side ? a.set[1] : a.set[0]) + (size_t)cloud * np * 3;
+    const float *__restrict__ O = (side ? a.set[0] : a.set[1]) + (size_t)cloud * no * 3;
+    const int *__restrict__ idx_own = (side ? a.idx[1] : a.idx[0]) + (size_t)cloud * np;
+    const int *__restrict__ idx_oth = (side ? a.idx[0] : a.idx[1]) + (size_t)cloud * no;
+    const float *__restrict__ g_own = (side ? a.gdist[1] : a.gdist[0]) + (a.scalar_grad ? 0 : (size_t)cloud * np);
+    const float *__restrict__ g_oth = (side ? a.gdist[0] : a.gdist[1]) + (a.scalar_grad ? 0 : (size_t)cloud * no);
+    float *__restrict__ G = (side ? a.grad[1] : a.grad[0]) + (size_t)cloud * np * 3;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < np; i += THREADS) cursor[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < no; k += THREADS) {
+        int key = __ldg(idx_oth + k);
+        if ((unsigned)key < (unsigned)np) atomicAdd(&cursor[key], 1);
+    }
+    __syncthreads();
+    // exclusive scan of cursor[0..np) -> start; contiguous slice per thread
+    const int per = (np + THREADS - 1) / THREADS;
+    const int lo = min(np, tid * per), hi = min(np, lo + per);
+    int local = 0;
+    for (int i = lo; i < hi; ++i) local += cursor[i];
+    scan_part[tid] = local;
+    __syncthreads();
+    if (tid < 32) {  // one warp scans the THREADS partials
+        int carry = 0;
+        for (int base = 0; base < THREADS; base += 32) {
+            int v = scan_part[base + tid];
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= o) inc += n;
+            }
+            scan_part[base + tid] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (tid == 0) scan_total = carry;
+    }
+    __syncthreads();
+    {
+        int run = scan_part[tid];
+        for (int i = lo; i < hi; ++i) {
+            int c = cursor[i];
+            start[i] = run;
+            cursor[i] = run;
+            run += c;
+        }
+    }
+    if (tid == 0) start[np] = scan_total;
+    __syncthreads();
+    if (tid < 32) {  // stable placement: ascending k, 32 at a time
+        for (int k0 = 0; k0 < no; k0 += 32) {
+            int k = k0 + tid;
+            int key = (k < no) ? __ldg(idx_oth + k) : -1;
+            bool ok = (unsigned)key < (unsigned)np;
+            unsigned act = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                unsigned peers = __match_any_sync(act, key);
+                int rank = __popc(peers & ((1u << tid) - 1u));
+                int basep = cursor[key];
+                __syncwarp(act);
+                perm[basep + rank] = k;
+                if (rank == __popc(peers) - 1) cursor[key] = basep + rank + 1;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    const float gs_own = a.scalar_grad ? __ldg(g_own) : 0.f;
+    const float gs_oth = a.scalar_grad ? __ldg(g_oth) : 0.f;
+    for (int i = tid; i < np; i += THREADS) {
+        float px = __ldg(P + (size_t)i * 3 + 0), py = __ldg(P + (size_t)i * 3 + 1), pz = __ldg(P + (size_t)i * 3 + 2);
+        int j2 = min(max(__ldg(idx_own + i), 0), no - 1);
+        float g = (a.scalar_grad ? gs_own : __ldg(g_own + i)) * 2.f;
+        float ox = __ldg(O + (size_t)j2 * 3 + 0), oy = __ldg(O + (size_t)j2 * 3 + 1), oz = __ldg(O + (size_t)j2 * 3 + 2);
+        float ax = g * (px - ox), ay = g * (py - oy), az = g * (pz - oz);
+        const int e = start[i + 1];
+        for (int p = start[i]; p < e; ++p) {
+            int k = perm[p];
+            float gk = (a.scalar_grad ? gs_oth : __ldg(g_oth + k)) * 2.f;
+            float kx = __ldg(O + (size_t)k * 3 + 0), ky = __ldg(O + (size_t)k * 3 + 1), kz = __ldg(O + (size_t)k * 3 + 2);
+            ax += -(gk * (kx - px));
+            ay += -(gk * (ky - py));
+            az += -(gk * (kz - pz));
+        }
+        G[(size_t)i * 3 + 0] = ax;
+        G[(size_t)i * 3 + 1] = ay;
+        G[(size_t)i * 3 + 2] = az;
+    }
+}
+
+// Large-cloud fallback (n+m > HP_NNGRAD_SMEM_POINTS): float atomics like the reference.
+__global__ void nn_grad_atomic_kernel(int b, int n, const float *__restrict__ xyz1, int m,
+                                      const float *__restrict__ xyz2, const float *__restrict__ gd,
+                                      int scalar_grad, const int *__restrict__ idx1, float *grad1, float *grad2) {
+    size_t total = (size_t)b * n;
+    for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+        size_t i = o / n;
+        int j2 = idx1[o];
+        size_t o2 = i * m + j2;
+        float g = (scalar_grad ? gd[0] : gd[o]) * 2.f;
+        float dx = xyz1[o * 3 + 0] - xyz2[o2 * 3 + 0];
+        float dy = xyz1[o * 3 + 1] - xyz2[o2 * 3 + 1];
+        float dz = xyz1[o * 3 + 2] - xyz2[o2 * 3 + 2];
+        atomicAdd(grad1 + o * 3 + 0, g * dx);
+        atomicAdd(grad1 + o * 3 + 1, g * dy);
+        atomicAdd(grad1 + o * 3 + 2, g * dz);
+        atomicAdd(grad2 + o2 * 3 + 0, -(g * dx));
+        atomicAdd(grad2 + o2 * 3 + 1, -(g * dy));
+        atomicAdd(grad2 + o2 * 3 + 2, -(g * dz));
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+constexpr int FWD_THREADS = 128;
+constexpr int FWD_RQ = 2;
+constexpr int FWD_MC = 2048;
+constexpr int GRAD_THREADS = 256;
+
+static size_t fwd_smem_bytes() { return (size_t)FWD_MC * 6 * sizeof(float); }
+
+static int nn_forward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1,
+                             float *dist2, int *idx2, float *loss, void *workspace, cudaStream_t stream) {
+    NNArgs a;
+    a.set[0] = xyz1, a.set[1] = xyz2;
+    a.dist[0] = dist1, a.dist[1] = dist2;
+    a.idx[0] = idx1, a.idx[1] = idx2;
+    a.npts[0] = n, a.npts[1] = m;
+    const int QT = FWD_THREADS * FWD_RQ;
+    a.tiles[0] = (n + QT - 1) / QT;
+    a.tiles[1] = (m + QT - 1) / QT;
+    a.b = b;
+    long long grid = (long long)b * (a.tiles[0] + a.tiles[1]);
+    HP_REQUIRE(grid <= 0x7fffffffLL, "hp_nndistance: grid too large (%lld tiles)", grid);
+    a.loss = loss;
+    a.counter = reinterpret_cast<unsigned int *>(workspace);
+    a.partial = workspace ? reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(workspace) + 8) : nullptr;
+    auto kern = nn_fwd_kernel<FWD_THREADS, FWD_RQ, FWD_MC>;
+    static SmemAttrCache fwd_attr;
+    HP_CUDA(ensure_dynamic_smem(kern, fwd_smem_bytes(), fwd_attr));
+    kern<<<(unsigned)grid, FWD_THREADS, fwd_smem_bytes(), stream>>>(a);
+    HP_LAUNCH_CHECK("nn_fwd_kernel");
+    return HP_OK;
+}
+
+static int nn_backward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const float *g1, const int *idx1,
+                              const float *g2, const int *idx2, float *grad1, float *grad2, int scalar_grad,
+                              cudaStream_t stream) {
+    if ((long long)n + m <= HP_NNGRAD_SMEM_POINTS) {
+        NNGradArgs a;
+        a.set[0] = xyz1, a.set[1] = xyz2;
+        a.idx[0] = idx1, a.idx[1] = idx2;
+        a.gdist[0] = g1, a.gdist[1] = g2;
+        a.grad[0] = grad1, a.grad[1] = grad2;
+        a.npts[0] = n, a.npts[1] = m;
+        a.b = b;
+        a.scalar_grad = scalar_grad;
+        // side 0: start[n+1] cursor[n] perm[m]; side 1: start[m+1] cursor[m] perm[n]
+        const size_t big = (size_t)(n > m ? n : m), small = (size_t)(n > m ? m : n);
+        const size_t smem = (2 * big + 1 + small) * sizeof(int);
+        auto kern = nn_grad_kernel<GRAD_THREADS>;
+        static SmemAttrCache grad_attr;
+        if (smem > 48 * 1024) HP_CUDA(ensure_dynamic_smem(kern, smem, grad_attr));
+        kern<<<2 * b, GRAD_THREADS, smem, stream>>>(a);
+        HP_LAUNCH_CHECK("nn_grad_kernel");
+        return HP_OK;
+    }
+    HP_CUDA(cudaMemsetAsync(grad1, 0, (size_t)b * n * 3 * sizeof(float), stream));
+    HP_CUDA(cudaMemsetAsync(grad2, 0, (size_t)b * m * 3 * sizeof(float), stream));
+    int blocks = sm_count() * 8;
+    nn_grad_atomic_kernel<<<blocks, 256, 0, stream>>>(b, n, xyz1, m, xyz2, g1, scalar_grad, idx1, grad1, grad2);
+    HP_LAUNCH_CHECK("nn_grad_atomic_kernel(1)");
+    nn_grad_atomic_kernel<<<blocks, 256, 0, stream>>>(b, m, xyz2, n, xyz1, g2, scalar_grad, idx2, grad2, grad1);
+    HP_LAUNCH_CHECK("nn_grad_atomic_kernel(2)");
+    return HP_OK;
+}
+
+}  // namespace hp
+
+using namespace hp;
+
+extern "C" int hp_nndistance(int b, int n, const float *xyz, int m, const float *xyz2, float *result, int *result_i,
+                             float *result2, int *result2_i, void *stream) {
+    HP_REQUIRE(b >= 0 && n >= 0 && m >= 0, "hp_nndistance: negative size (b=%d n=%d m=%d)", b, n, m);
+    if (b == 0 || (n == 0 && m == 0)) return HP_OK;
+    HP_REQUIRE(n > 0 && m > 0, "hp_nndistance: one point set is empty (n=%d m=%d): nearest neighbour undefined", n, m);
+    HP_REQUIRE(xyz && xyz2 && result && result_i && result2 && result2_i, "hp_nndistance: null pointer");
+    return nn_forward_launch(b, n, xyz, m, xyz2, result, result_i, result2, result2_i, nullptr, nullptr,
+                             (cudaStream_t)stream);
+}
+
+extern "C" size_t hp_chamfer_workspace_bytes(int b, int n, int m) {
+    if (b <= 0 || n <= 0 || m <= 0) return 16;
+    const int QT = FWD_THREADS * FWD_RQ;
+    size_t tiles = (size_t)b * ((n + QT - 1) / QT + (m + QT - 1) / QT);
+    return 8 + tiles * sizeof(float) + 8;
+}
+
+extern "C" int hp_chamfer_forward(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1,
+                                  float *dist2, int *idx2, float *loss, void *workspace, size_t workspace_bytes,
+                                  void *stream) {
+    HP_REQUIRE(b >= 0 && n >= 0 && m >= 0, "hp_chamfer_forward: negative size (b=%d n=%d m=%d)", b, n, m);
+    HP_REQUIRE(loss != nullptr, "hp_chamfer_forward: loss pointer is null");
+    if (b == 0 || (n == 0 && m == 0)) {
+        HP_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+        return HP_OK;
+    }
+    HP_REQUIRE(n > 0 && m > 0, "hp_chamfer_forward: one point set is empty (n=%d m=%d)", n, m);
+    HP_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, "hp_chamfer_forward: null pointer");
+    HP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0,
+               "hp_chamfer_forward: workspace null or not 8-byte aligned");
+    if (workspace_bytes < hp_chamfer_workspace_bytes(b, n, m)) {
+        set_error("hp_chamfer_forward: workspace %zu < required %zu bytes", workspace_bytes,
+                  hp_chamfer_workspace_bytes(b, n, m));
+        return HP_ERR_WORKSPACE;
+    }
+    return nn_forward_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int hp_nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,
+                                 const int *idx1, const float *grad_dist2, const int *idx2, float *grad_xyz1,
+                                 float *grad_xyz2, void *stream) {
+    HP_REQUIRE(b >= 0 && n >= 0 && m >= 0, "hp_nndistancegrad: negative size (b=%d n=%d m=%d)", b, n, m);
+    if (b == 0 || (n == 0 && m == 0)) return HP_OK;
+    HP_REQUIRE(n > 0 && m > 0, "hp_nndistancegrad: one point set is empty (n=%d m=%d)", n, m);
+    HP_REQUIRE(xyz1 && xyz2 && grad_dist1 && idx1 && grad_dist2 && idx2 && grad_xyz1 && grad_xyz2,
+               "hp_nndistancegrad: null pointer");
+    return nn_backward_launch(b, n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, 0,
+                              (cudaStream_t)stream);
+}
+
+extern "C" int hp_chamfer_backward(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1,
+                                   const int *idx2, const float *grad_loss, float *grad_xyz1, float *grad_xyz2,
+                                   void *stream) {
+    HP_REQUIRE(b >= 0 && n >= 0 && m >= 0, "hp_chamfer_backward: negative size (b=%d n=%d m=%d)", b, n, m);
+    if (b == 0 || (n == 0 && m == 0)) return HP_OK;
+    HP_REQUIRE(n > 0 && m > 0, "hp_chamfer_backward: one point set is empty (n=%d m=%d)", n, m);
+    HP_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && grad_loss && grad_xyz1 && grad_xyz2, "hp_chamfer_backward: null pointer");
+    return nn_backward_launch(b, n, xyz1, m, xyz2, grad_loss, idx1, grad_loss, idx2, grad_xyz1, grad_xyz2, 1,
+                              (cudaStream_t)stream);
+}

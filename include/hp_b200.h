@@ -1,0 +1,111 @@
+/*
+ * hp_b200.h -- C ABI of the B200-native (sm_100a) point-set hot path of HyperPocket
+ * (gmum/3d-point-clouds-autocomplete).  Shared library: libhp_b200.so.
+ *
+ * This is the drop-in boundary.  Everything is `extern "C"`, plain device
+ * pointers and sizes, no torch types.  Conventions shared by every entry point:
+ *   - all pointers are DEVICE pointers on the current CUDA device unless a name ends in
+ *     `_host`; all tensors are dense, row-major, fp32 (indices int32);
+ *   - `stream` is a `cudaStream_t` passed as `void*`; work is enqueued on it and the call
+ *     returns without synchronising (fully stream-ordered, no legacy-stream memset --
+ *     the reference's nndistancegrad() issues cudaMemset on the legacy stream,
+ *     nndistance.cu:156-157; that hazard is not reproduced);
+ *   - the library never allocates device memory: outputs and workspaces are caller-owned
+ *     (the reference's glue allocates outputs with torch::empty, structural_loss.cpp:32-33,
+ *     49,64-65,90-93,111-112; our Python glue does the same);
+ *   - return value: HP_OK (0) or an HP_ERR_* code; the reference's launchers return void and
+ *     throw std::runtime_error on launch failure (approxmatch.cu:334-337) or do not check at
+ *     all (nndistance.cu:131-134).  hp_last_error_message() gives the detail string.
+ *
+ * The first five functions have exactly the argument lists of the reference's internal
+ * launchers declared at utils/pytorch_structural_losses/structural_loss.cpp:11-15, which is
+ * what a maintainer would bind.
+ */
+#ifndef HP_B200_H_
+#define HP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HP_B200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define HP_API __attribute__((visibility("default")))
+#else
+#define HP_API
+#endif
+
+enum {
+    HP_OK = 0,
+    HP_ERR_INVALID_ARGUMENT = 1, /* negative size, null pointer, misaligned workspace ... */
+    HP_ERR_CUDA = 2,             /* a CUDA runtime call or kernel launch failed */
+    HP_ERR_UNSUPPORTED = 3,      /* shape outside what the kernels support (documented per call) */
+    HP_ERR_WORKSPACE = 4         /* workspace_bytes smaller than hp_*_workspace_bytes() */
+};
+
+HP_API int hp_version(void);
+HP_API const char *hp_error_string(int code);
+/* Thread-local detail of the last failing call on this thread ("" if none). */
+HP_API const char *hp_last_error_message(void);
+
+/* ------------------------------------------------------------------------------------
+ * (a) Chamfer / nearest-neighbour distance
+ * ---------------------------------------------------------------------------------- */
+
+/* Replaces `void nndistance(int b,int n,const float*xyz,int m,const float*xyz2,float*result,
+ * int*result_i,float*result2,int*result2_i,cudaStream_t)`  (structural_loss.cpp:14,
+ * nndistance.cu:131-134).
+ *   result [b,n]  = min_k |xyz[b,j]-xyz2[b,k]|^2,  result_i = argmin (lowest index on ties)
+ *   result2[b,m], result2_i: the reverse direction.
+ * d = fma(dz,dz,fma(dx,dx,dy*dy)) in fp32, bit-identical to the reference build.
+ * One launch covers both directions.  n==0 or m==0 with b>0 -> HP_ERR_INVALID_ARGUMENT
+ * (the reference leaves the outputs uninitialised).  Inputs must be finite. */
+HP_API int hp_nndistance(int b, int n, const float *xyz, int m, const float *xyz2, float *result,
+                  int *result_i, float *result2, int *result2_i, void *stream);
+
+/* Replaces `void nndistancegrad(int b,int n,const float*xyz1,int m,const float*xyz2,
+ * const float*grad_dist1,const int*idx1,const float*grad_dist2,const int*idx2,
+ * float*grad_xyz1,float*grad_xyz2,cudaStream_t)`  (structural_loss.cpp:15,
+ * nndistance.cu:155-160).
+ *   grad_xyz1[b,j] = 2 g1[j] (a_j - b_idx1[j]) + sum_{k: idx2[k]==j} 2 g2[k] (a_j - b_k)
+ *   grad_xyz2 symmetric.  Outputs are fully overwritten (no memset needed).
+ * Atomic-free and deterministic (per-cloud stable counting sort of the index map in shared
+ * memory, then a fixed-order gather) when n+m <= HP_NNGRAD_SMEM_POINTS; above that an
+ * atomicAdd kernel like the reference's is used (non-deterministic summation order). */
+HP_API int hp_nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2,
+                      const float *grad_dist1, const int *idx1, const float *grad_dist2,
+                      const int *idx2, float *grad_xyz1, float *grad_xyz2, void *stream);
+#define HP_NNGRAD_SMEM_POINTS 49152
+
+/* Fused ChamferLoss forward (losses/champfer_loss.py:11-17 semantics, direct-form distances):
+ * hp_nndistance plus loss[0] = sum(result) + sum(result2), reduced deterministically inside
+ * the same launch.  `workspace` must hold hp_chamfer_workspace_bytes(b,n,m) bytes, be
+ * 8-byte aligned and ZERO-FILLED once when allocated (the kernel restores that state, so it
+ * can be reused across calls on one stream). */
+HP_API size_t hp_chamfer_workspace_bytes(int b, int n, int m);
+HP_API int hp_chamfer_forward(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1,
+                       int *idx1, float *dist2, int *idx2, float *loss, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* Backward of the fused loss: like hp_nndistancegrad with grad_dist1 == grad_dist2 ==
+ * grad_loss[0] (a single device scalar, read by the kernel -- no host sync). */
+HP_API int hp_chamfer_backward(int b, int n, const float *xyz1, int m, const float *xyz2,
+                        const int *idx1, const int *idx2, const float *grad_loss,
+                        float *grad_xyz1, float *grad_xyz2, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Measurement helpers (used by bench.py for the roofline denominators; not on the path)
+ * ---------------------------------------------------------------------------------- */
+/* Runs a register-resident FFMA (kind 0), packed FFMA2 (kind 1) or MUFU.EX2 (kind 2) chain
+ * on every SM and returns the achieved rate in *rate (FLOP/s for kinds 0-1, ex2/s for kind 2),
+ * timed with CUDA events on `stream` (synchronises). */
+HP_API int hp_measure_peak(int kind, int iters, double *rate_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HP_B200_H_ */

@@ -1,0 +1,76 @@
+import importlib
+import os
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _has_cuda() -> bool:
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_cuda():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def hp():
+    """The product package, with libhp_b200.so built (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as entry
+
+    entry.build_native()
+    return importlib.import_module("3d-point-clouds-autocomplete_b200")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+
+    O.build()
+    return O
+
+
+@pytest.fixture(scope="session")
+def golden_cpu():
+    import numpy as np
+
+    return np.load(os.path.join(REPO, "tests", "golden", "cpu_reference.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_gpu():
+    import numpy as np
+
+    p = os.path.join(REPO, "tests", "golden", "gpu_reference_ext.npz")
+    if not os.path.exists(p):
+        pytest.skip("tests/golden/gpu_reference_ext.npz not generated yet")
+    return np.load(p)
+
+
+@pytest.fixture(scope="session")
+def ref_ext():
+    """The reference's own CUDA extension (oracle/_ref), or skip."""
+    from oracle import oracle as O
+
+    m = O.load_reference_ext()
+    if m is None:
+        pytest.skip("oracle/_ref not built")
+    return m

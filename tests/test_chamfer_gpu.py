@@ -1,0 +1,211 @@
+"""GPU parity tests for the Chamfer / nearest-neighbour path, through the C ABI
+(ctypes -> libhp_b200.so).  Bars: indices and distances BIT-EXACT vs the oracle and vs the
+reference's own CUDA extension; gradients and losses within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _clouds(shape_a, shape_b, kind, seed):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "uniform":
+        a = torch.rand(*shape_a, generator=g) - 0.5
+        b = torch.rand(*shape_b, generator=g) - 0.5
+    elif kind == "lattice":  # coarse lattice: many exact ties
+        a = torch.randint(-4, 5, shape_a, generator=g).float() / 8
+        b = torch.randint(-4, 5, shape_b, generator=g).float() / 8
+    else:  # "same": identical clouds -> dist 0, idx = first duplicate
+        a = torch.rand(*shape_a, generator=g) - 0.5
+        b = a.clone()
+    return a.contiguous(), b.contiguous()
+
+
+SHAPES = [(1, 1, 1), (2, 1, 5), (2, 5, 1), (3, 300, 257), (2, 17, 33), (2, 700, 1100), (1, 2049, 4100), (5, 256, 256)]
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lattice"])
+@pytest.mark.parametrize("b,n,m", SHAPES)
+def test_nndistance_bit_exact_vs_oracle(hp, oracle, b, n, m, kind):
+    a, c = _clouds((b, n, 3), (b, m, 3), kind, seed=b * 1000 + n + m)
+    d1, i1, d2, i2 = hp.NNDistance(a.to(DEV), c.to(DEV))
+    od1, oi1, od2, oi2 = oracle.nn_distance(a.numpy(), c.numpy())
+    assert d1.dtype == torch.float32 and i1.dtype == torch.int32 and tuple(d2.shape) == (b, m)
+    assert np.array_equal(i1.cpu().numpy(), oi1)
+    assert np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy().view(np.uint32), od1.view(np.uint32))
+    assert np.array_equal(d2.cpu().numpy().view(np.uint32), od2.view(np.uint32))
+
+
+def test_identical_clouds(hp):
+    a, _ = _clouds((2, 513, 3), (2, 513, 3), "same", 1)
+    a[0, 100] = a[0, 7]  # a duplicate point: the lower index must win
+    d1, i1, d2, i2 = hp.NNDistance(a.to(DEV), a.to(DEV))
+    assert (d1 == 0).all() and (d2 == 0).all()
+    exp = torch.arange(513, dtype=torch.int32).repeat(2, 1)
+    exp[0, 100] = 7
+    assert torch.equal(i1.cpu(), exp) and torch.equal(i2.cpu(), exp)
+
+
+def test_full_size_c2_bit_exact_and_symmetric(hp, oracle):
+    """BASELINE config C2: B=32, N=M=2048."""
+    a, c = _clouds((32, 2048, 3), (32, 2048, 3), "uniform", 0)
+    ad, cd = a.to(DEV), c.to(DEV)
+    d1, i1, d2, i2 = hp.NNDistance(ad, cd)
+    od1, oi1, od2, oi2 = oracle.nn_distance(a.numpy(), c.numpy())
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+    # size-independent properties: role swap, and each reported distance is the distance to its index
+    e2, j2, e1, j1 = hp.NNDistance(cd, ad)
+    assert torch.equal(e1, d1) and torch.equal(j1, i1) and torch.equal(e2, d2) and torch.equal(j2, i2)
+    nearest = torch.gather(cd, 1, i1.long().unsqueeze(-1).expand(-1, -1, 3))
+    recomputed = ((ad.double() - nearest.double()) ** 2).sum(-1)
+    torch.testing.assert_close(d1.double(), recomputed, rtol=1e-6, atol=1e-12)
+    # idempotence / determinism
+    f1, k1, f2, k2 = hp.NNDistance(ad, cd)
+    assert torch.equal(f1, d1) and torch.equal(k1, i1) and torch.equal(f2, d2) and torch.equal(k2, i2)
+
+
+def test_vs_reference_extension_live(hp, ref_ext):
+    """Differential test against the UNMODIFIED reference CUDA extension (oracle/_ref)."""
+    for (b, n, m, kind) in [(4, 2048, 2048, "uniform"), (3, 1000, 1500, "lattice"), (2, 333, 77, "uniform")]:
+        a, c = _clouds((b, n, 3), (b, m, 3), kind, seed=n)
+        ad, cd = a.to(DEV), c.to(DEV)
+        d1, i1, d2, i2 = hp.NNDistance(ad, cd)
+        r1, j1, r2, j2 = ref_ext.NNDistance(ad, cd)
+        assert torch.equal(i1, j1) and torch.equal(i2, j2), "NN indices differ from the reference extension"
+        assert torch.equal(d1, r1) and torch.equal(d2, r2), "NN distances differ from the reference extension"
+        g = torch.Generator().manual_seed(5)
+        g1, g2 = torch.randn(b, n, generator=g).to(DEV), torch.randn(b, m, generator=g).to(DEV)
+        ga, gb = hp.NNDistanceGrad(ad, cd, i1, i2, g1, g2)
+        ra, rb = ref_ext.NNDistanceGrad(ad, cd, j1, j2, g1, g2)
+        torch.cuda.synchronize()  # the reference memsets on the legacy stream (nndistance.cu:156-157)
+        torch.testing.assert_close(ga, ra, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(gb, rb, rtol=1e-5, atol=1e-6)
+
+
+def test_vs_reference_extension_golden(hp, golden_gpu):
+    g = golden_gpu
+    for pre in ("nn_uni", "nn_lat", "nn_one"):
+        a, c = torch.from_numpy(g[pre + "_a"]).to(DEV), torch.from_numpy(g[pre + "_b"]).to(DEV)
+        d1, i1, d2, i2 = hp.NNDistance(a, c)
+        assert np.array_equal(i1.cpu().numpy(), g[pre + "_i1"]) and np.array_equal(i2.cpu().numpy(), g[pre + "_i2"])
+        assert np.array_equal(d1.cpu().numpy(), g[pre + "_d1"]) and np.array_equal(d2.cpu().numpy(), g[pre + "_d2"])
+        ga, gb = hp.NNDistanceGrad(a, c, i1, i2, torch.from_numpy(g[pre + "_g1"]).to(DEV),
+                                   torch.from_numpy(g[pre + "_g2"]).to(DEV))
+        np.testing.assert_allclose(ga.cpu().numpy(), g[pre + "_ga"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(gb.cpu().numpy(), g[pre + "_gb"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("b,n,m", [(3, 300, 257), (2, 700, 1100), (1, 1, 9), (2, 2048, 2048)])
+def test_nndistance_grad_vs_oracle_and_deterministic(hp, oracle, b, n, m):
+    a, c = _clouds((b, n, 3), (b, m, 3), "lattice" if n == 700 else "uniform", seed=n * 3 + m)
+    g = torch.Generator().manual_seed(11)
+    g1, g2 = torch.randn(b, n, generator=g), torch.randn(b, m, generator=g)
+    ad, cd = a.to(DEV), c.to(DEV)
+    d1, i1, d2, i2 = hp.NNDistance(ad, cd)
+    ga, gb = hp.NNDistanceGrad(ad, cd, i1, i2, g1.to(DEV), g2.to(DEV))
+    oga, ogb = oracle.nn_distance_grad(a.numpy(), c.numpy(), i1.cpu().numpy(), i2.cpu().numpy(), g1.numpy(), g2.numpy())
+    np.testing.assert_allclose(ga.cpu().numpy(), oga, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gb.cpu().numpy(), ogb, rtol=1e-5, atol=1e-6)
+    ga2, gb2 = hp.NNDistanceGrad(ad, cd, i1, i2, g1.to(DEV), g2.to(DEV))
+    assert torch.equal(ga, ga2) and torch.equal(gb, gb2), "backward must be bitwise reproducible (no float atomics)"
+
+
+def test_degenerate_all_points_identical_backward(hp, oracle):
+    """Every query maps to candidate 0: one bucket holds all points (worst case for the scatter)."""
+    a = torch.zeros(2, 1024, 3)
+    c = torch.rand(2, 1024, 3, generator=torch.Generator().manual_seed(2))
+    ad, cd = a.to(DEV), c.to(DEV)
+    d1, i1, d2, i2 = hp.NNDistance(ad, cd)
+    assert (i2 == 0).all()
+    ones1, ones2 = torch.ones(2, 1024, device=DEV), torch.ones(2, 1024, device=DEV)
+    ga, gb = hp.NNDistanceGrad(ad, cd, i1, i2, ones1, ones2)
+    oga, ogb = oracle.nn_distance_grad(a.numpy(), c.numpy(), i1.cpu().numpy(), i2.cpu().numpy(),
+                                       np.ones((2, 1024), np.float32), np.ones((2, 1024), np.float32))
+    np.testing.assert_allclose(ga.cpu().numpy(), oga, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(gb.cpu().numpy(), ogb, rtol=1e-5, atol=1e-6)
+
+
+def test_autograd_op_and_batch_quirk(hp):
+    a, c = _clouds((1, 128, 3), (4, 128, 3), "uniform", 9)
+    ad = a.to(DEV).requires_grad_(True)
+    cd = c.to(DEV).requires_grad_(True)
+    d1, d2 = hp.nn_distance(ad, cd)  # reference quirk Q3: batch of the first argument only
+    assert tuple(d1.shape) == (1, 128) and tuple(d2.shape) == (1, 128)
+    (d1.mean() + d2.mean()).backward()
+    assert ad.grad.shape == ad.shape and cd.grad.shape == cd.shape
+    assert (cd.grad[1:] == 0).all() and cd.grad[0].abs().sum() > 0
+    with pytest.raises(RuntimeError, match="batch"):
+        hp.nn_distance(cd.detach(), ad.detach())  # second set has fewer clouds: out of bounds in the reference
+
+
+def test_input_validation(hp):
+    a = torch.zeros(2, 8, 3, device=DEV)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        hp.NNDistance(torch.zeros(2, 3, 8, device=DEV).transpose(1, 2), a)
+    with pytest.raises(RuntimeError, match="float32"):
+        hp.NNDistance(a.double(), a)
+    with pytest.raises(RuntimeError, match="shape"):
+        hp.NNDistance(torch.zeros(2, 8, 4, device=DEV), a)
+    with pytest.raises(RuntimeError, match="empty"):
+        hp.NNDistance(torch.zeros(2, 0, 3, device=DEV), a)
+    d1, i1, d2, i2 = hp.NNDistance(torch.zeros(0, 8, 3, device=DEV), torch.zeros(0, 8, 3, device=DEV))
+    assert d1.numel() == 0 and i2.numel() == 0
+
+
+@pytest.mark.parametrize("pre", ["lat", "uni"])
+def test_chamfer_loss_module_vs_reference_pure_torch(hp, golden_cpu, pre):
+    """ChamferLoss drop-in vs the reference's pure-torch module (golden, generated on CPU)."""
+    g = golden_cpu
+    a = torch.from_numpy(g[f"{pre}_a"]).to(DEV).requires_grad_(True)
+    c = torch.from_numpy(g[f"{pre}_b"]).to(DEV).requires_grad_(True)
+    loss = hp.ChamferLoss()(c, a)  # forward(preds, gts)
+    assert loss.dim() == 0
+    assert float(loss) == pytest.approx(float(g[f"{pre}_loss"]), rel=1e-5)
+    loss.backward()
+    # near-ties may pick a different (equally near) neighbour than the expansion form on uniform data
+    tol = dict(rtol=1e-4, atol=2e-6) if pre == "lat" else dict(rtol=1e-3, atol=5e-4)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), g[f"{pre}_grad_a"], **tol)
+    np.testing.assert_allclose(c.grad.cpu().numpy(), g[f"{pre}_grad_b"], **tol)
+
+
+def test_chamfer_loss_fused_equals_sum_of_parts_and_noncontiguous(hp, oracle):
+    a, c = _clouds((6, 2048, 3), (6, 1024, 3), "uniform", 21)
+    ad, cd = a.to(DEV), c.to(DEV)
+    loss, d1, i1, d2, i2 = hp.chamfer_forward(ad, cd)
+    e1, j1, e2, j2 = hp.NNDistance(ad, cd)
+    assert torch.equal(d1, e1) and torch.equal(i1, j1) and torch.equal(d2, e2) and torch.equal(i2, j2)
+    ref = d1.double().sum() + d2.double().sum()
+    assert float(loss) == pytest.approx(float(ref), rel=1e-6)
+    loss2 = hp.chamfer_forward(ad, cd)[0]
+    assert torch.equal(loss, loss2), "fused loss reduction must be deterministic"
+    # the trainer hands ChamferLoss a permuted [B,3,N] -> [B,N,3] view (core/epoch_loops.py:26)
+    soa = cd.transpose(1, 2).contiguous().requires_grad_(True)  # [B,3,N] storage
+    l3 = hp.ChamferLoss()(ad, soa.permute(0, 2, 1))
+    assert float(l3) == pytest.approx(float(loss), rel=1e-6)
+    l3.backward()
+    assert soa.grad.shape == soa.shape
+    # gradient of the fused loss == per-point op with all-ones upstream
+    ga, gb = hp.NNDistanceGrad(ad, cd, i1, i2, torch.ones_like(d1), torch.ones_like(d2))
+    # ChamferLoss()(preds=ad, gts=soa-view) runs the kernels as (gts, preds): soa is the first set there
+    e1, j1, e2, j2 = hp.NNDistance(cd, ad)
+    gfirst, _gsecond = hp.NNDistanceGrad(cd, ad, j1, j2, torch.ones_like(e1), torch.ones_like(e2))
+    assert torch.equal(soa.grad.permute(0, 2, 1), gfirst)
+
+
+def test_large_cloud_fallback_backward(hp, oracle):
+    """n+m above HP_NNGRAD_SMEM_POINTS: the atomic fallback (documented non-deterministic order)."""
+    a, c = _clouds((1, 30000, 3), (1, 25000, 3), "uniform", 4)
+    ad, cd = a.to(DEV), c.to(DEV)
+    d1, i1, d2, i2 = hp.NNDistance(ad, cd)
+    od1, oi1, od2, oi2 = oracle.nn_distance(a.numpy(), c.numpy())
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
+    g1, g2 = torch.ones_like(d1), torch.ones_like(d2)
+    ga, gb = hp.NNDistanceGrad(ad, cd, i1, i2, g1, g2)
+    oga, ogb = oracle.nn_distance_grad(a.numpy(), c.numpy(), oi1, oi2, g1.cpu().numpy(), g2.cpu().numpy())
+    np.testing.assert_allclose(ga.cpu().numpy(), oga, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(gb.cpu().numpy(), ogb, rtol=1e-4, atol=1e-6)
