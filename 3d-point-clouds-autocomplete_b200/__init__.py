@@ -10,4 +10,7 @@ from . import _native  # noqa: F401
 from .chamfer import (ChamferLoss, NNDistance, NNDistanceFunction, NNDistanceGrad, chamfer_backward,  # noqa: F401
                       chamfer_forward, nn_distance)
 
+from .emd import (ApproxMatch, MatchCost, MatchCostFunction, MatchCostGrad, approx_match, emd_cost_pairs,  # noqa: F401
+                  match_cost)
+
 __version__ = "0.1.0"

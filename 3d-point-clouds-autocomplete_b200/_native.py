@@ -35,6 +35,11 @@ SIGNATURES = {
     "hp_chamfer_workspace_bytes": (_sz, [_int, _int, _int]),
     "hp_chamfer_forward": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hp_chamfer_backward": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hp_approxmatch": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "hp_matchcost": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "hp_matchcostgrad": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hp_emd_cost_workspace_bytes": (_sz, [_int, _int, _int]),
+    "hp_emd_cost_pairs": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hp_measure_peak": (_int, [_int, _int, ctypes.POINTER(ctypes.c_double), _vp]),
 }
 

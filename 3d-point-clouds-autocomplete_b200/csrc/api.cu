@@ -37,9 +37,9 @@ int sm_count() {
 // kind 0: scalar FFMA, 16 independent chains/thread            -> 2 FLOP per FFMA
 // kind 1: packed FFMA2 (fma.rn.f32x2), 8 independent chains    -> 4 FLOP per FFMA2
 // kind 2: MUFU.EX2 (ex2.approx.ftz.f32), 8 independent chains  -> 1 ex2 each
-// kind 3: the Chamfer inner-loop mix without memory: per candidate PAIR 3 FADD2 + FMUL2 +
-//         2 FFMA2 + 1 FMNMX3                                    -> 16 "algorithmic" FLOP per pair of evals
-// kind 4: the same mix in scalar form: per candidate 3 FADD + FMUL + 2 FFMA + 1 FMNMX -> 8 FLOP
+// kind 3/5: the Chamfer inner loop (candidates from a shared-memory SoA table, 2 / 4 queries per
+//         thread): per candidate PAIR 3 FADD2 + FMUL2 + 2 FFMA2 + 1 FMNMX3 -> 8 algorithmic FLOP per eval
+// kind 4: the same loop in scalar form: per candidate 3 FADD + FMUL + 2 FFMA + 1 FMNMX
 template <int KIND>
 __global__ void __launch_bounds__(256) peak_kernel(int iters, float seed, float *sink) {
     const float x = seed * 0.999f, y = seed * 1e-3f;
@@ -84,44 +84,54 @@ __global__ void __launch_bounds__(256) peak_kernel(int iters, float seed, float 
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += acc[i];
         if (s == 123.456f) sink[0] = s;
-    } else if (KIND == 3) {
-        f32x2 qx[2], qy[2], qz[2];
-        float best[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            qx[r] = pack2(seed + r, seed + r), qy[r] = pack2(seed - r, seed - r), qz[r] = pack2(seed * r, seed * r);
-            best[r] = 3.0e38f;
-        }
-        f32x2 cx = pack2(threadIdx.x * 0.01f, seed), cy = pack2(seed, threadIdx.x * 0.02f), cz = pack2(0.5f, 0.25f);
-        const f32x2 step = pack2(1e-3f, 2e-3f);
-        for (int it = 0; it < iters; ++it) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    f32x2 d = sqdist_exact2(qx[r], qy[r], qz[r], cx, cy, cz);
-                    float d0, d1;
-                    unpack2(d, d0, d1);
-                    best[r] = min3(best[r], d0, d1);
-                }
-                cx = sub2(cx, step);  // keeps the compiler from hoisting; 1 extra FADD2 per 2 pair-evals*2
-            }
-        }
-        if (best[0] + best[1] == 123.456f) sink[0] = best[0];
     } else {
-        float qx[4], qy[4], qz[4], best[4];
+        // KIND 3 / 5: the Chamfer inner loop (packed) with 2 / 4 queries per thread; KIND 4: scalar, 4 queries.
+        // Candidates come from a 1024-entry SoA table in shared memory exactly like the real kernel.
+        __shared__ __align__(16) float tx[1024], ty[1024], tz[1024];
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+            tx[i] = seed * 0.001f * i, ty[i] = seed * 0.002f * (i ^ 5), tz[i] = seed * 0.003f * (i ^ 9);
+        }
+        __syncthreads();
+        constexpr int RQ = (KIND == 3) ? 2 : 4;
+        float qx[RQ], qy[RQ], qz[RQ], best[RQ];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) qx[r] = seed + r, qy[r] = seed - r, qz[r] = seed * r, best[r] = 3.0e38f;
-        float cx = threadIdx.x * 0.01f, cy = seed, cz = 0.5f;
+        for (int r = 0; r < RQ; ++r) {
+            qx[r] = seed + r + threadIdx.x * 0.01f, qy[r] = seed - r, qz[r] = seed * r, best[r] = 3.0e38f;
+        }
         for (int it = 0; it < iters; ++it) {
+#pragma unroll 4
+            for (int c = 0; c < 1024; c += 4) {
+                if (KIND == 4) {
+                    const float4 cx = *reinterpret_cast<const float4 *>(tx + c);
+                    const float4 cy = *reinterpret_cast<const float4 *>(ty + c);
+                    const float4 cz = *reinterpret_cast<const float4 *>(tz + c);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+                    for (int r = 0; r < RQ; ++r) {
+                        best[r] = fminf(best[r], sqdist_exact(qx[r], qy[r], qz[r], cx.x, cy.x, cz.x));
+                        best[r] = fminf(best[r], sqdist_exact(qx[r], qy[r], qz[r], cx.y, cy.y, cz.y));
+                        best[r] = fminf(best[r], sqdist_exact(qx[r], qy[r], qz[r], cx.z, cy.z, cz.z));
+                        best[r] = fminf(best[r], sqdist_exact(qx[r], qy[r], qz[r], cx.w, cy.w, cz.w));
+                    }
+                } else {
+                    const ulonglong2 cx = *reinterpret_cast<const ulonglong2 *>(tx + c);
+                    const ulonglong2 cy = *reinterpret_cast<const ulonglong2 *>(ty + c);
+                    const ulonglong2 cz = *reinterpret_cast<const ulonglong2 *>(tz + c);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) best[r] = fminf(best[r], sqdist_exact(qx[r], qy[r], qz[r], cx, cy, cz));
-                cx = __fsub_rn(cx, 1e-3f);
+                    for (int r = 0; r < RQ; ++r) {
+                        const f32x2 px = pack2(qx[r], qx[r]), py = pack2(qy[r], qy[r]), pz = pack2(qz[r], qz[r]);
+                        float d0, d1, d2, d3;
+                        unpack2(sqdist_exact2(px, py, pz, cx.x, cy.x, cz.x), d0, d1);
+                        unpack2(sqdist_exact2(px, py, pz, cx.y, cy.y, cz.y), d2, d3);
+                        best[r] = min3(best[r], d0, d1);
+                        best[r] = min3(best[r], d2, d3);
+                    }
+                }
             }
         }
-        if (best[0] + best[1] + best[2] + best[3] == 123.456f) sink[0] = best[0];
+        float s = 0;
+#pragma unroll
+        for (int r = 0; r < RQ; ++r) s += best[r];
+        if (s == 123.456f) sink[0] = s;
     }
 }
 
@@ -146,7 +156,7 @@ extern "C" const char *hp_last_error_message(void) { return g_err; }
 
 extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *stream_v) {
     HP_REQUIRE(rate_host != nullptr, "hp_measure_peak: null result pointer");
-    HP_REQUIRE(kind >= 0 && kind <= 4 && iters > 0, "hp_measure_peak: bad kind/iters (%d, %d)", kind, iters);
+    HP_REQUIRE(kind >= 0 && kind <= 5 && iters > 0, "hp_measure_peak: bad kind/iters (%d, %d)", kind, iters);
     cudaStream_t stream = (cudaStream_t)stream_v;
     float *sink = nullptr;
     HP_CUDA(cudaMalloc(&sink, sizeof(float)));  // measurement helper only: not on the product path
@@ -162,7 +172,8 @@ extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *str
             case 1: peak_kernel<1><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
             case 2: peak_kernel<2><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
             case 3: peak_kernel<3><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
-            default: peak_kernel<4><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
+            case 4: peak_kernel<4><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
+            default: peak_kernel<5><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
         }
         HP_CUDA(cudaEventRecord(e1, stream));
         HP_CUDA(cudaEventSynchronize(e1));
@@ -180,8 +191,8 @@ extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *str
         case 0: per_thread_iter = 16 * 2.0; break;         // FLOP
         case 1: per_thread_iter = 8 * 4.0; break;          // FLOP
         case 2: per_thread_iter = 8.0; break;              // ex2
-        case 3: per_thread_iter = 4 * 2 * 2 * 8.0; break;  // 4 steps x 2 queries x 2 candidates x 8 FLOP
-        default: per_thread_iter = 4 * 4 * 8.0; break;     // 4 steps x 4 queries x 8 FLOP
+        case 3: per_thread_iter = 1024 * 2 * 8.0; break;   // 1024 candidates x 2 queries x 8 algorithmic FLOP
+        default: per_thread_iter = 1024 * 4 * 8.0; break;  // 1024 candidates x 4 queries x 8 algorithmic FLOP
     }
     *rate_host = threads_total * per_thread_iter * (double)iters / ((double)best_ms * 1e-3);
     return HP_OK;

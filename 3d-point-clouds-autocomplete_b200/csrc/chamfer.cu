@@ -19,6 +19,8 @@
 //     with d == min (bit-exact same arithmetic) -> identical to the reference's
 //     "strict <, lowest index wins" rule (nndistance.cu:32-64,117-125);
 //   * optional fused loss: per-CTA partial sums in fixed order, last CTA folds them.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hp {
@@ -40,10 +42,14 @@ struct NNArgs {
 template <int THREADS, int RQ, int MC>
 __global__ void __launch_bounds__(THREADS) nn_fwd_kernel(const NNArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *stage = reinterpret_cast<float *>(smem_raw);  // [MC*3] AoS landing zone of the bulk copy
-    float *xs = stage + MC * 3;                          // [MC] each, SoA
+    // One [MC*3] buffer: the bulk copy lands the chunk AoS (xyzxyz...), then it is transposed IN PLACE
+    // (through registers) to SoA xs|ys|zs so that an LDS.128 yields two ready-made fp32x2 candidate pairs.
+    float *stage = reinterpret_cast<float *>(smem_raw);
+    float *xs = stage;
     float *ys = xs + MC;
     float *zs = ys + MC;
+    constexpr int PER = MC / THREADS;  // candidates per thread in the transposition
+    static_assert(MC % THREADS == 0 && MC % NN_CH == 0, "chunk must tile evenly");
     __shared__ __align__(8) uint64_t mbar;
     __shared__ float warp_part[THREADS / 32];
     __shared__ int last_flag;
@@ -104,12 +110,23 @@ __global__ void __launch_bounds__(THREADS) nn_fwd_kernel(const NNArgs a) {
             phase ^= 1;
         }
         __syncthreads();
-        // AoS -> SoA; pad the last sub-chunk with +inf coordinates (distance +inf, never a minimum)
+        // AoS -> SoA in place; pad the last sub-chunk with +inf coordinates (distance +inf, never a minimum)
         const int padded = (cnt + NN_CH - 1) / NN_CH * NN_CH;
-        for (int i = tid; i < padded; i += THREADS) {
-            float x = __int_as_float(0x7f800000), y = x, z = x;
-            if (i < cnt) x = stage[i * 3 + 0], y = stage[i * 3 + 1], z = stage[i * 3 + 2];
-            xs[i] = x, ys[i] = y, zs[i] = z;
+        {
+            float tx[PER], ty[PER], tz[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int i = tid + j * THREADS;
+                float x = __int_as_float(0x7f800000), y = x, z = x;
+                if (i < cnt) x = stage[i * 3 + 0], y = stage[i * 3 + 1], z = stage[i * 3 + 2];
+                tx[j] = x, ty[j] = y, tz[j] = z;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int i = tid + j * THREADS;
+                if (i < padded) xs[i] = tx[j], ys[i] = ty[j], zs[i] = tz[j];
+            }
         }
         __syncthreads();
 
@@ -223,14 +240,15 @@ struct NNGradArgs {
 };
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) nn_grad_kernel(const NNGradArgs a) {
+__global__ void __launch_bounds__(THREADS) nn_grad_kernel(const NNGradArgs a, const int nseg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int side = blockIdx.x & 1;
     const int cloud = blockIdx.x >> 1;
     const int np = side ? a.npts[1] : a.npts[0], no = side ? a.npts[0] : a.npts[1];
-    int *start = reinterpret_cast<int *>(smem_raw);  // [np+1] bucket starts (exclusive scan of counts)
-    int *cursor = start + (np + 1);                  // [np]   running fill position
-    int *perm = cursor + np;                         // [no]   k sorted by key, stable
+    int *keys = reinterpret_cast<int *>(smem_raw);  // [no]  idx_other staged (one coalesced pass over HBM/L2)
+    int *perm = keys + no;                           // [no]  k sorted by key, stable
+    int *start = perm + no;                          // [np+1] bucket starts
+    int *cnt = start + (np + 1);                     // [nseg][np] per-segment counts -> per-segment cursors
     __shared__ int scan_part[THREADS];
     __shared__ int scan_total;
 
@@ -242,22 +260,55 @@ __global__ void __launch_bounds__(THREADS) nn_grad_kernel(const NNGradArgs a) {
     const float *__restrict__ g_oth = (side ? a.gdist[0] : a.gdist[1]) + (a.scalar_grad ? 0 : (size_t)cloud * no);
     float *__restrict__ G = (side ? a.grad[1] : a.grad[0]) + (size_t)cloud * np * 3;
     const int tid = threadIdx.x;
+    // k-range of placement segment s: [s*seg, min(no,(s+1)*seg)), seg a multiple of 32
+    const int seg = ((no + nseg - 1) / nseg + 31) & ~31;
 
-    for (int i = tid; i < np; i += THREADS) cursor[i] = 0;
-    __syncthreads();
+    // Issue the loads of the "own" term first: their latency hides behind the sort phases below.
+    constexpr int PRE = 2;  // points per thread kept in registers (covers np <= PRE*THREADS)
+    const float gs_own = a.scalar_grad ? __ldg(g_own) : 0.f;
+    const float gs_oth = a.scalar_grad ? __ldg(g_oth) : 0.f;
+    float pre_p[PRE][3], pre_o[PRE][3], pre_g[PRE];
+#pragma unroll
+    for (int u = 0; u < PRE; ++u) {
+        const int i = tid + u * THREADS;
+        if (i < np) {
+            const int j2 = min(max(__ldg(idx_own + i), 0), no - 1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) pre_p[u][c] = __ldg(P + (size_t)i * 3 + c), pre_o[u][c] = __ldg(O + (size_t)j2 * 3 + c);
+            pre_g[u] = (a.scalar_grad ? gs_own : __ldg(g_own + i)) * 2.f;
+        }
+    }
+
+    for (int i = tid; i < nseg * np; i += THREADS) cnt[i] = 0;
     for (int k = tid; k < no; k += THREADS) {
         int key = __ldg(idx_oth + k);
-        if ((unsigned)key < (unsigned)np) atomicAdd(&cursor[key], 1);
+        keys[k] = ((unsigned)key < (unsigned)np) ? key : -1;
     }
     __syncthreads();
-    // exclusive scan of cursor[0..np) -> start; contiguous slice per thread
+    for (int k = tid; k < no; k += THREADS) {
+        int key = keys[k];
+        if (key >= 0) atomicAdd(&cnt[(k / seg) * np + key], 1);  // integer atomics: order-independent result
+    }
+    __syncthreads();
+    // per key: exclusive prefix over segments (in place) and the bucket size (into start[])
+    for (int i = tid; i < np; i += THREADS) {
+        int run = 0;
+        for (int s = 0; s < nseg; ++s) {
+            int c = cnt[s * np + i];
+            cnt[s * np + i] = run;
+            run += c;
+        }
+        start[i] = run;
+    }
+    __syncthreads();
+    // exclusive scan of start[0..np): contiguous slice per thread + one-warp scan of the partials
     const int per = (np + THREADS - 1) / THREADS;
     const int lo = min(np, tid * per), hi = min(np, lo + per);
     int local = 0;
-    for (int i = lo; i < hi; ++i) local += cursor[i];
+    for (int i = lo; i < hi; ++i) local += start[i];
     scan_part[tid] = local;
     __syncthreads();
-    if (tid < 32) {  // one warp scans the THREADS partials
+    if (tid < 32) {
         int carry = 0;
         for (int base = 0; base < THREADS; base += 32) {
             int v = scan_part[base + tid];
@@ -276,43 +327,40 @@ __global__ void __launch_bounds__(THREADS) nn_grad_kernel(const NNGradArgs a) {
     {
         int run = scan_part[tid];
         for (int i = lo; i < hi; ++i) {
-            int c = cursor[i];
+            int c = start[i];
             start[i] = run;
-            cursor[i] = run;
             run += c;
         }
     }
     if (tid == 0) start[np] = scan_total;
     __syncthreads();
-    if (tid < 32) {  // stable placement: ascending k, 32 at a time
-        for (int k0 = 0; k0 < no; k0 += 32) {
-            int k = k0 + tid;
-            int key = (k < no) ? __ldg(idx_oth + k) : -1;
-            bool ok = (unsigned)key < (unsigned)np;
+    // stable placement: warp w owns segment w and walks it in ascending k, 32 at a time
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < nseg) {
+        int *cur = cnt + warp * np;
+        const int k_end = min(no, (warp + 1) * seg);
+        for (int k0 = warp * seg; k0 < k_end; k0 += 32) {
+            int k = k0 + lane;
+            int key = (k < k_end) ? keys[k] : -1;
+            bool ok = key >= 0;
             unsigned act = __ballot_sync(0xffffffffu, ok);
             if (ok) {
                 unsigned peers = __match_any_sync(act, key);
-                int rank = __popc(peers & ((1u << tid) - 1u));
-                int basep = cursor[key];
+                int rank = __popc(peers & ((1u << lane) - 1u));
+                int basep = cur[key];
                 __syncwarp(act);
-                perm[basep + rank] = k;
-                if (rank == __popc(peers) - 1) cursor[key] = basep + rank + 1;
+                perm[start[key] + basep + rank] = k;
+                if (rank == __popc(peers) - 1) cur[key] = basep + rank + 1;
             }
             __syncwarp();
         }
     }
     __syncthreads();
 
-    const float gs_own = a.scalar_grad ? __ldg(g_own) : 0.f;
-    const float gs_oth = a.scalar_grad ? __ldg(g_oth) : 0.f;
-    for (int i = tid; i < np; i += THREADS) {
-        float px = __ldg(P + (size_t)i * 3 + 0), py = __ldg(P + (size_t)i * 3 + 1), pz = __ldg(P + (size_t)i * 3 + 2);
-        int j2 = min(max(__ldg(idx_own + i), 0), no - 1);
-        float g = (a.scalar_grad ? gs_own : __ldg(g_own + i)) * 2.f;
-        float ox = __ldg(O + (size_t)j2 * 3 + 0), oy = __ldg(O + (size_t)j2 * 3 + 1), oz = __ldg(O + (size_t)j2 * 3 + 2);
+    auto finish = [&](int i, float px, float py, float pz, float ox, float oy, float oz, float g) {
         float ax = g * (px - ox), ay = g * (py - oy), az = g * (pz - oz);
         const int e = start[i + 1];
-        for (int p = start[i]; p < e; ++p) {
+        for (int p = start[i]; p < e; ++p) {  // ascending k: fixed summation order
             int k = perm[p];
             float gk = (a.scalar_grad ? gs_oth : __ldg(g_oth + k)) * 2.f;
             float kx = __ldg(O + (size_t)k * 3 + 0), ky = __ldg(O + (size_t)k * 3 + 1), kz = __ldg(O + (size_t)k * 3 + 2);
@@ -323,6 +371,17 @@ __global__ void __launch_bounds__(THREADS) nn_grad_kernel(const NNGradArgs a) {
         G[(size_t)i * 3 + 0] = ax;
         G[(size_t)i * 3 + 1] = ay;
         G[(size_t)i * 3 + 2] = az;
+    };
+#pragma unroll
+    for (int u = 0; u < PRE; ++u) {
+        const int i = tid + u * THREADS;
+        if (i < np) finish(i, pre_p[u][0], pre_p[u][1], pre_p[u][2], pre_o[u][0], pre_o[u][1], pre_o[u][2], pre_g[u]);
+    }
+    for (int i = tid + PRE * THREADS; i < np; i += THREADS) {
+        const int j2 = min(max(__ldg(idx_own + i), 0), no - 1);
+        finish(i, __ldg(P + (size_t)i * 3 + 0), __ldg(P + (size_t)i * 3 + 1), __ldg(P + (size_t)i * 3 + 2),
+               __ldg(O + (size_t)j2 * 3 + 0), __ldg(O + (size_t)j2 * 3 + 1), __ldg(O + (size_t)j2 * 3 + 2),
+               (a.scalar_grad ? gs_own : __ldg(g_own + i)) * 2.f);
     }
 }
 
@@ -349,12 +408,36 @@ __global__ void nn_grad_atomic_kernel(int b, int n, const float *__restrict__ xy
 }
 
 // ---- host side ---------------------------------------------------------------------------
-constexpr int FWD_THREADS = 128;
-constexpr int FWD_RQ = 2;
-constexpr int FWD_MC = 2048;
-constexpr int GRAD_THREADS = 256;
+constexpr int FWD_MIN_QT = 32;  // smallest query tile of any variant (sizes the loss workspace)
+constexpr int GRAD_THREADS = 1024;
 
-static size_t fwd_smem_bytes() { return (size_t)FWD_MC * 6 * sizeof(float); }
+// Forward tile variants (threads per CTA, queries per thread).  HP_NN_VARIANT selects one at run time for
+// tuning; the default is the best measured on B200 at B=32, N=M=2048.
+static int fwd_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HP_NN_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 8) v = 0;
+    }
+    return v;
+}
+
+template <int THREADS, int RQ, int MC>
+static int nn_forward_launch_t(NNArgs a, cudaStream_t stream) {
+    const int QT = THREADS * RQ;
+    a.tiles[0] = (a.npts[0] + QT - 1) / QT;
+    a.tiles[1] = (a.npts[1] + QT - 1) / QT;
+    long long grid = (long long)a.b * (a.tiles[0] + a.tiles[1]);
+    HP_REQUIRE(grid <= 0x7fffffffLL, "hp_nndistance: grid too large (%lld tiles)", grid);
+    auto kern = nn_fwd_kernel<THREADS, RQ, MC>;
+    const size_t smem = (size_t)MC * 3 * sizeof(float);
+    static SmemAttrCache fwd_attr;
+    HP_CUDA(ensure_dynamic_smem(kern, smem, fwd_attr));
+    kern<<<(unsigned)grid, THREADS, smem, stream>>>(a);
+    HP_LAUNCH_CHECK("nn_fwd_kernel");
+    return HP_OK;
+}
 
 static int nn_forward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1,
                              float *dist2, int *idx2, float *loss, void *workspace, cudaStream_t stream) {
@@ -363,21 +446,21 @@ static int nn_forward_launch(int b, int n, const float *xyz1, int m, const float
     a.dist[0] = dist1, a.dist[1] = dist2;
     a.idx[0] = idx1, a.idx[1] = idx2;
     a.npts[0] = n, a.npts[1] = m;
-    const int QT = FWD_THREADS * FWD_RQ;
-    a.tiles[0] = (n + QT - 1) / QT;
-    a.tiles[1] = (m + QT - 1) / QT;
     a.b = b;
-    long long grid = (long long)b * (a.tiles[0] + a.tiles[1]);
-    HP_REQUIRE(grid <= 0x7fffffffLL, "hp_nndistance: grid too large (%lld tiles)", grid);
     a.loss = loss;
     a.counter = reinterpret_cast<unsigned int *>(workspace);
     a.partial = workspace ? reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(workspace) + 8) : nullptr;
-    auto kern = nn_fwd_kernel<FWD_THREADS, FWD_RQ, FWD_MC>;
-    static SmemAttrCache fwd_attr;
-    HP_CUDA(ensure_dynamic_smem(kern, fwd_smem_bytes(), fwd_attr));
-    kern<<<(unsigned)grid, FWD_THREADS, fwd_smem_bytes(), stream>>>(a);
-    HP_LAUNCH_CHECK("nn_fwd_kernel");
-    return HP_OK;
+    switch (fwd_variant()) {
+        case 1: return nn_forward_launch_t<128, 2, 2048>(a, stream);
+        case 2: return nn_forward_launch_t<64, 2, 1024>(a, stream);
+        case 3: return nn_forward_launch_t<256, 1, 2048>(a, stream);
+        case 4: return nn_forward_launch_t<64, 1, 1024>(a, stream);
+        case 5: return nn_forward_launch_t<64, 4, 1024>(a, stream);
+        case 6: return nn_forward_launch_t<128, 4, 2048>(a, stream);
+        case 7: return nn_forward_launch_t<32, 4, 512>(a, stream);
+        case 8: return nn_forward_launch_t<32, 8, 512>(a, stream);
+        default: return nn_forward_launch_t<128, 1, 2048>(a, stream);
+    }
 }
 
 static int nn_backward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const float *g1, const int *idx1,
@@ -392,13 +475,17 @@ static int nn_backward_launch(int b, int n, const float *xyz1, int m, const floa
         a.npts[0] = n, a.npts[1] = m;
         a.b = b;
         a.scalar_grad = scalar_grad;
-        // side 0: start[n+1] cursor[n] perm[m]; side 1: start[m+1] cursor[m] perm[n]
-        const size_t big = (size_t)(n > m ? n : m), small = (size_t)(n > m ? m : n);
-        const size_t smem = (2 * big + 1 + small) * sizeof(int);
+        // shared memory (ints): keys[no] perm[no] start[np+1] cnt[nseg][np]; nseg placement warps as it fits
+        const size_t big = (size_t)(n > m ? n : m);
+        const size_t fixed = (size_t)2 * big + big + 1;
+        const size_t budget = (size_t)200 * 1024 / sizeof(int);
+        int nseg = (int)((budget - fixed) / big);
+        nseg = nseg > GRAD_THREADS / 32 ? GRAD_THREADS / 32 : (nseg < 1 ? 1 : nseg);
+        const size_t smem = (fixed + (size_t)nseg * big) * sizeof(int);
         auto kern = nn_grad_kernel<GRAD_THREADS>;
         static SmemAttrCache grad_attr;
         if (smem > 48 * 1024) HP_CUDA(ensure_dynamic_smem(kern, smem, grad_attr));
-        kern<<<2 * b, GRAD_THREADS, smem, stream>>>(a);
+        kern<<<2 * b, GRAD_THREADS, smem, stream>>>(a, nseg);
         HP_LAUNCH_CHECK("nn_grad_kernel");
         return HP_OK;
     }
@@ -428,7 +515,7 @@ extern "C" int hp_nndistance(int b, int n, const float *xyz, int m, const float 
 
 extern "C" size_t hp_chamfer_workspace_bytes(int b, int n, int m) {
     if (b <= 0 || n <= 0 || m <= 0) return 16;
-    const int QT = FWD_THREADS * FWD_RQ;
+    const int QT = FWD_MIN_QT;
     size_t tiles = (size_t)b * ((n + QT - 1) / QT + (m + QT - 1) / QT);
     return 8 + tiles * sizeof(float) + 8;
 }

@@ -1,0 +1,525 @@
+// emd.cu -- approximate earth mover's distance (soft auction) for sm_100a.
+//
+// Replaces approxmatchkernel / matchcostkernel / matchcostgrad{1,2}kernel of the reference
+// (utils/pytorch_structural_losses/approxmatch.cu:34-357) behind hp_approxmatch, hp_matchcost,
+// hp_matchcostgrad and adds the match-free hp_emd_cost_pairs used by the metrics path.
+//
+// The auction runs 9 annealing levels (level = -4^j, j = 7..-1, approxmatch.cu:55-59); each level
+// is three all-pairs passes that each need a COMPLETE reduction of the previous one:
+//   P1  ratioL[k] = remainL[k] / (1e-9 + sum_l e(k,l) remainR[l])                 (approxmatch.cu:60-93)
+//   P2  sumr = remainR[l] * sum_k e(k,l) ratioL[k];  ratioR[l] = min(remainR/(sumr+1e-9),1) remainR[l];
+//       remainR[l] = max(0, remainR[l]-sumr)                                       (approxmatch.cu:109-142)
+//   P3  w = e(k,l) ratioL[k] ratioR[l];  match[l][k] += w;  remainL[k] = max(0, remainL[k]-sum_l w)
+//                                                                                  (approxmatch.cu:161-194)
+// with e(k,l) = __expf(level * |x1_k - x2_l|^2).  The reference runs ONE CTA per cloud pair (32 SMs busy
+// at B=32).  Here every pass is one launch over ALL cloud pairs: a CTA owns THREADS*RQ rows of one pair
+// (and, when a workspace is available, one slice of the columns, so small batches still fill 148 SMs);
+// columns are staged SoA in shared memory so one LDS.128 feeds two fp32x2 candidate pairs; the
+// distance and the two exponent scalings run as FADD2/FMUL2/FFMA2, the exponential on MUFU.EX2.
+// Bound: MUFU (16 ex2/clk/SM) and the FP32 pipe are within ~10% of each other for this mix.
+//
+// Numerics kept from the reference build (verified in its sm_100 SASS):
+//   d = fma(dz,dz,fma(dx,dx,dy*dy));  arg = (d * level) * 1.4426950216f;  e = ex2.approx(arg)
+//   P1/P2: acc = fma(e, w, acc) in ascending column order;  P3: t = ratioL*e; acc = fma(t, ratioR, acc),
+//   match = fma(t, ratioR, match);  IEEE division; level = -powf(4.0f, j) evaluated on the device.
+// Deviation: ex2.approx.ftz (results below 2^-126 flush to 0 instead of going denormal): |delta| < 1.2e-38
+// per term, below the resolution of every sum it enters.
+#include "common.cuh"
+
+namespace hp {
+
+constexpr int EMD_CC = 256;  // columns staged per shared-memory chunk
+
+struct EmdArgs {
+    const float *first, *second;  // clouds: first [*, n, 3] (xyz1 role), second [*, m, 3] (xyz2 role)
+    const int *ia, *ib;           // per-pair cloud index into first / second (nullptr = pair index)
+    float *state;                 // [pairs][2(n+m)] = remainL[n] remainR[m] ratioL[n] ratioR[m]
+    float *partial;               // [pairs][S][rstride] row partial sums (column-split mode) or nullptr
+    float *match;                 // [pairs][m][n] or nullptr
+    float *costpart;              // [pairs][cp_stride] per-CTA cost partials or nullptr
+    int n, m, pairs;
+    int S, span;                  // column split: slice s covers columns [s*span, min(nc,(s+1)*span))
+    int row_tiles, rstride;
+    int j;                        // level exponent: level = -4^j
+    int level_index;              // 0..8
+    int first_level;              // P3: match = w instead of match += w
+    int cp_stride;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <int MODE>
+__device__ __forceinline__ void emd_row_epilogue(float acc, float *st, int n, int m, int r) {
+    float *remainL = st, *remainR = st + n, *ratioL = st + n + m, *ratioR = st + n + m + n;
+    if (MODE == 1) {
+        ratioL[r] = remainL[r] / acc;  // acc already includes the 1e-9 start (approxmatch.cu:68,92)
+    } else if (MODE == 2) {
+        const float rem = remainR[r];
+        const float sumr = acc * rem;                                   // approxmatch.cu:137
+        const float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);    // :138
+        ratioR[r] = consumption * rem;                                  // :139
+        remainR[r] = fmaxf(0.0f, rem - sumr);                           // :140
+    } else {
+        remainL[r] = fmaxf(0.0f, remainL[r] - acc);                     // :193
+    }
+}
+
+// MODE 1/3: rows = xyz1 (n), columns = xyz2 (m).  MODE 2: rows = xyz2 (m), columns = xyz1 (n).
+template <int MODE, int RQ, int THREADS, bool SPLIT, bool MATCH, bool COST>
+__global__ void __launch_bounds__(THREADS) emd_pass_kernel(const EmdArgs a) {
+    __shared__ __align__(16) float xs[EMD_CC], ys[EMD_CC], zs[EMD_CC], ws[EMD_CC];
+    __shared__ float warp_part[THREADS / 32];
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int s = bid % a.S;
+    bid /= a.S;
+    const int rt = bid % a.row_tiles;
+    const int pair = bid / a.row_tiles;
+    const int n = a.n, m = a.m;
+    const int nr = (MODE == 2) ? m : n, nc = (MODE == 2) ? n : m;
+    const size_t c1 = a.ia ? (size_t)a.ia[pair] : (size_t)pair, c2 = a.ib ? (size_t)a.ib[pair] : (size_t)pair;
+    const float *__restrict__ X1 = a.first + c1 * n * 3;
+    const float *__restrict__ X2 = a.second + c2 * m * 3;
+    const float *__restrict__ R = (MODE == 2) ? X2 : X1;
+    const float *__restrict__ C = (MODE == 2) ? X1 : X2;
+    float *st = a.state + (size_t)pair * 2 * (n + m);
+    const float *colw = (MODE == 1) ? st + n : (MODE == 2) ? st + n + m : st + n + m + n;  // remainR | ratioL | ratioR
+    const float level = -powf(4.0f, (float)a.j);  // approxmatch.cu:56, evaluated on the device like the reference
+    const f32x2 level2 = pack2(level, level);
+    const f32x2 log2e2 = pack2(1.4426950216293334961f, 1.4426950216293334961f);
+
+    f32x2 qx[RQ], qy[RQ], qz[RQ];
+    float acc[RQ], rl[RQ], cost[RQ];
+    int row[RQ];
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+        row[q] = rt * (THREADS * RQ) + q * THREADS + tid;
+        float x = 0.f, y = 0.f, z = 0.f;
+        rl[q] = 0.f;
+        if (row[q] < nr) {
+            x = __ldg(R + (size_t)row[q] * 3 + 0), y = __ldg(R + (size_t)row[q] * 3 + 1), z = __ldg(R + (size_t)row[q] * 3 + 2);
+            if (MODE == 3) rl[q] = st[n + m + row[q]];  // ratioL[k]
+        }
+        qx[q] = pack2(x, x), qy[q] = pack2(y, y), qz[q] = pack2(z, z);
+        acc[q] = (MODE == 1 && s == 0) ? 1e-9f : 0.f;  // approxmatch.cu:68 (P1) / :117,169 (P2, P3)
+        cost[q] = 0.f;
+    }
+
+    const int c_begin = s * a.span, c_end = min(nc, c_begin + a.span);
+    for (int c0 = c_begin; c0 < c_end; c0 += EMD_CC) {
+        for (int i = tid; i < EMD_CC; i += THREADS) {
+            const int c = c0 + i;
+            float x = 0.f, y = 0.f, z = 0.f, w = 0.f;  // zero weight: padded columns add exactly nothing
+            if (c < c_end) x = __ldg(C + (size_t)c * 3 + 0), y = __ldg(C + (size_t)c * 3 + 1), z = __ldg(C + (size_t)c * 3 + 2), w = colw[c];
+            xs[i] = x, ys[i] = y, zs[i] = z, ws[i] = w;
+        }
+        __syncthreads();
+        const int cnt = min(EMD_CC, c_end - c0);
+        const int cnt4 = (cnt + 3) & ~3;
+#pragma unroll 2
+        for (int c = 0; c < cnt4; c += 4) {
+            const ulonglong2 cx = *reinterpret_cast<const ulonglong2 *>(xs + c);
+            const ulonglong2 cy = *reinterpret_cast<const ulonglong2 *>(ys + c);
+            const ulonglong2 cz = *reinterpret_cast<const ulonglong2 *>(zs + c);
+            const float4 w = *reinterpret_cast<const float4 *>(ws + c);
+#pragma unroll
+            for (int q = 0; q < RQ; ++q) {
+                const f32x2 d01 = sqdist_exact2(qx[q], qy[q], qz[q], cx.x, cy.x, cz.x);
+                const f32x2 d23 = sqdist_exact2(qx[q], qy[q], qz[q], cx.y, cy.y, cz.y);
+                float t0, t1, t2, t3;
+                unpack2(mul2(mul2(d01, level2), log2e2), t0, t1);  // (d*level)*log2e, two roundings like the reference
+                unpack2(mul2(mul2(d23, level2), log2e2), t2, t3);
+                const float e0 = ex2_approx(t0), e1 = ex2_approx(t1), e2 = ex2_approx(t2), e3 = ex2_approx(t3);
+                if (MODE != 3) {
+                    acc[q] = __fmaf_rn(e0, w.x, acc[q]);
+                    acc[q] = __fmaf_rn(e1, w.y, acc[q]);
+                    acc[q] = __fmaf_rn(e2, w.z, acc[q]);
+                    acc[q] = __fmaf_rn(e3, w.w, acc[q]);
+                } else {
+                    const float u0 = __fmul_rn(rl[q], e0), u1 = __fmul_rn(rl[q], e1), u2 = __fmul_rn(rl[q], e2), u3 = __fmul_rn(rl[q], e3);
+                    acc[q] = __fmaf_rn(u0, w.x, acc[q]);
+                    acc[q] = __fmaf_rn(u1, w.y, acc[q]);
+                    acc[q] = __fmaf_rn(u2, w.z, acc[q]);
+                    acc[q] = __fmaf_rn(u3, w.w, acc[q]);
+                    if (MATCH) {
+                        if (row[q] < nr) {
+                            float *mp = a.match + (size_t)pair * n * m + (size_t)(c0 + c) * n + row[q];
+                            const float uu[4] = {u0, u1, u2, u3};
+                            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) {
+                                if (c + v < cnt) {
+                                    const float old = a.first_level ? 0.f : mp[(size_t)v * n];
+                                    mp[(size_t)v * n] = __fmaf_rn(uu[v], wv[v], old);
+                                }
+                            }
+                        }
+                    }
+                    if (COST) {
+                        float d0, d1, d2, d3;
+                        unpack2(d01, d0, d1);
+                        unpack2(d23, d2, d3);
+                        cost[q] = __fmaf_rn(__fmul_rn(u0, w.x), sqrt_approx(d0), cost[q]);
+                        cost[q] = __fmaf_rn(__fmul_rn(u1, w.y), sqrt_approx(d1), cost[q]);
+                        cost[q] = __fmaf_rn(__fmul_rn(u2, w.z), sqrt_approx(d2), cost[q]);
+                        cost[q] = __fmaf_rn(__fmul_rn(u3, w.w), sqrt_approx(d3), cost[q]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+        if (row[q] < nr) {
+            if (SPLIT) a.partial[((size_t)pair * a.S + s) * a.rstride + row[q]] = acc[q];
+            else emd_row_epilogue<MODE>(acc[q], st, n, m, row[q]);
+        }
+    }
+    if (COST) {
+        float c = 0.f;
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) c += (row[q] < nr) ? cost[q] : 0.f;
+        c = warp_sum(c);
+        if ((tid & 31) == 0) warp_part[tid >> 5] = c;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < THREADS / 32; ++i) t += warp_part[i];
+            a.costpart[(size_t)pair * a.cp_stride + ((size_t)a.level_index * a.row_tiles + rt) * a.S + s] = t;
+        }
+    }
+}
+
+// Column-split mode: fold the S slices in ascending order, then the row epilogue.
+template <int MODE>
+__global__ void emd_combine_kernel(const EmdArgs a) {
+    const int nr = (MODE == 2) ? a.m : a.n;
+    const size_t total = (size_t)a.pairs * nr;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int pair = (int)(i / nr), r = (int)(i % nr);
+        const float *p = a.partial + (size_t)pair * a.S * a.rstride + r;
+        float acc = p[0];
+        for (int s = 1; s < a.S; ++s) acc += p[(size_t)s * a.rstride];
+        emd_row_epilogue<MODE>(acc, a.state + (size_t)pair * 2 * (a.n + a.m), a.n, a.m, r);
+    }
+}
+
+// remainL = multiL, remainR = multiR with the reference's INTEGER division (approxmatch.cu:36-43,49-52)
+__global__ void emd_init_kernel(float *state, int pairs, int n, int m) {
+    float multiL, multiR;
+    if (n >= m) multiL = 1, multiR = (float)(n / m);
+    else multiL = (float)(m / n), multiR = 1;
+    const size_t per = (size_t)2 * (n + m), total = (size_t)pairs * (n + m);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pair = i / (n + m), r = i % (n + m);
+        state[pair * per + r] = (r < (size_t)n) ? multiL : multiR;
+    }
+}
+
+__global__ void emd_cost_finish_kernel(const float *costpart, int cp_stride, int pairs, float *cost) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pairs) return;
+    float t = 0.f;
+    for (int i = 0; i < cp_stride; ++i) t += costpart[(size_t)p * cp_stride + i];  // fixed order
+    cost[p] = t;
+}
+
+// ---- MatchCost (approxmatch.cu:215-255): HBM-bound read of match; an 8-CTA cluster per cloud pair, the
+// per-CTA partials are folded in rank order through distributed shared memory (deterministic, no scratch).
+constexpr int MC_CLUSTER = 8;
+constexpr int MC_THREADS = 256;
+
+__global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS)
+    matchcost_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                     const float *__restrict__ match, float *__restrict__ out) {
+    __shared__ float warp_part[MC_THREADS / 32];
+    __shared__ float cluster_part[MC_CLUSTER];
+    unsigned rank;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int pair = blockIdx.x / MC_CLUSTER;
+    const int tid = threadIdx.x;
+    const int l_begin = (int)(((long long)m * rank) / MC_CLUSTER), l_end = (int)(((long long)m * (rank + 1)) / MC_CLUSTER);
+    const float *X1 = xyz1 + (size_t)pair * n * 3, *X2 = xyz2 + (size_t)pair * m * 3;
+    const float *M = match + (size_t)pair * n * m;
+    float sum = 0.f;
+    for (int k = tid; k < n; k += MC_THREADS) {
+        const float x1 = __ldg(X1 + (size_t)k * 3 + 0), y1 = __ldg(X1 + (size_t)k * 3 + 1), z1 = __ldg(X1 + (size_t)k * 3 + 2);
+#pragma unroll 8
+        for (int l = l_begin; l < l_end; ++l) {
+            const float d = sqdist_exact(x1, y1, z1, __ldg(X2 + (size_t)l * 3 + 0), __ldg(X2 + (size_t)l * 3 + 1), __ldg(X2 + (size_t)l * 3 + 2));
+            sum = __fmaf_rn(__ldg(M + (size_t)l * n + k), sqrtf(d), sum);  // approxmatch.cu:238-239 (IEEE sqrtf)
+        }
+    }
+    sum = warp_sum(sum);
+    if ((tid & 31) == 0) warp_part[tid >> 5] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < MC_THREADS / 32; ++i) t += warp_part[i];
+        // write my partial into rank 0's cluster_part[rank]
+        uint32_t local = smem_u32(&cluster_part[rank]), remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(t) : "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (rank == 0 && tid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < MC_CLUSTER; ++i) t += cluster_part[i];
+        out[pair] = t;
+    }
+}
+
+// ---- MatchCostGrad (approxmatch.cu:260-322) ----------------------------------------------------------
+// grad1[k] = sum_l match[l][k] (x1_k - x2_l) rsqrt(max(d,1e-20)): thread per k, ascending l (the reference's order)
+__global__ void matchcostgrad1_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                                      const float *__restrict__ match, float *__restrict__ grad1) {
+    extern __shared__ __align__(16) float sh[];  // xyz2 tile [LT*3]
+    constexpr int LT = 512;
+    const int pair = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const float *X2 = xyz2 + (size_t)pair * m * 3;
+    const float *M = match + (size_t)pair * n * m;
+    float x1 = 0.f, y1 = 0.f, z1 = 0.f;
+    if (k < n) {
+        const float *p = xyz1 + ((size_t)pair * n + k) * 3;
+        x1 = __ldg(p), y1 = __ldg(p + 1), z1 = __ldg(p + 2);
+    }
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int l0 = 0; l0 < m; l0 += LT) {
+        const int cnt = min(LT, m - l0);
+        for (int i = threadIdx.x; i < cnt * 3; i += blockDim.x) sh[i] = __ldg(X2 + (size_t)l0 * 3 + i);
+        __syncthreads();
+        if (k < n) {
+#pragma unroll 8
+            for (int l = 0; l < cnt; ++l) {
+                const float ex = x1 - sh[l * 3 + 0], ey = y1 - sh[l * 3 + 1], ez = z1 - sh[l * 3 + 2];
+                const float s2 = __fmaf_rn(ez, ez, __fmaf_rn(ex, ex, __fmul_rn(ey, ey)));
+                const float d = __ldg(M + (size_t)(l0 + l) * n + k) * rsqrtf(fmaxf(s2, 1e-20f));
+                gx = __fmaf_rn(ex, d, gx), gy = __fmaf_rn(ey, d, gy), gz = __fmaf_rn(ez, d, gz);
+            }
+        }
+        __syncthreads();
+    }
+    if (k < n) {
+        float *g = grad1 + ((size_t)pair * n + k) * 3;
+        g[0] = gx, g[1] = gy, g[2] = gz;
+    }
+}
+
+// grad2[l] = sum_k match[l][k] (x2_l - x1_k) rsqrt(max(d,1e-20)): one warp per l, lanes stride k, fixed shuffle tree
+__global__ void matchcostgrad2_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                                      const float *__restrict__ match, float *__restrict__ grad2) {
+    const int pair = blockIdx.y;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= m) return;
+    const int l = warp;
+    const float *X1 = xyz1 + (size_t)pair * n * 3;
+    const float *p2 = xyz2 + ((size_t)pair * m + l) * 3;
+    const float x2 = __ldg(p2), y2 = __ldg(p2 + 1), z2 = __ldg(p2 + 2);
+    const float *M = match + (size_t)pair * n * m + (size_t)l * n;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll 4
+    for (int k = lane; k < n; k += 32) {
+        const float ex = x2 - __ldg(X1 + (size_t)k * 3 + 0), ey = y2 - __ldg(X1 + (size_t)k * 3 + 1), ez = z2 - __ldg(X1 + (size_t)k * 3 + 2);
+        const float s2 = __fmaf_rn(ez, ez, __fmaf_rn(ex, ex, __fmul_rn(ey, ey)));
+        const float d = __ldg(M + k) * rsqrtf(fmaxf(s2, 1e-20f));
+        gx = __fmaf_rn(ex, d, gx), gy = __fmaf_rn(ey, d, gy), gz = __fmaf_rn(ez, d, gz);
+    }
+    gx = warp_sum(gx), gy = warp_sum(gy), gz = warp_sum(gz);
+    if (lane == 0) {
+        float *g = grad2 + ((size_t)pair * m + l) * 3;
+        g[0] = gx, g[1] = gy, g[2] = gz;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+template <int MODE, int RQ, int THREADS, bool SPLIT, bool MATCH, bool COST>
+static int launch_pass(EmdArgs a, cudaStream_t stream) {
+    const int nr = (MODE == 2) ? a.m : a.n;
+    a.row_tiles = (nr + THREADS * RQ - 1) / (THREADS * RQ);
+    const long long grid = (long long)a.pairs * a.row_tiles * a.S;
+    HP_REQUIRE(grid <= 0x7fffffffLL, "emd: grid too large (%lld CTAs); split the batch", grid);
+    emd_pass_kernel<MODE, RQ, THREADS, SPLIT, MATCH, COST><<<(unsigned)grid, THREADS, 0, stream>>>(a);
+    HP_LAUNCH_CHECK("emd_pass_kernel");
+    return HP_OK;
+}
+
+// Tile shape by available row parallelism: big tiles (RQ=8: shared-memory traffic per ex2 is lowest) when
+// the batch alone fills the GPU, smaller ones otherwise.
+template <int MODE, bool SPLIT, bool MATCH, bool COST>
+static int launch_pass_auto(const EmdArgs &a, cudaStream_t stream) {
+    const int nr = (MODE == 2) ? a.m : a.n;
+    const long long want = (long long)sm_count() * 4;  // CTAs
+    auto ctas = [&](int tile) { return (long long)a.pairs * ((nr + tile - 1) / tile) * a.S; };
+    if (ctas(128 * 8) >= want) return launch_pass<MODE, 8, 128, SPLIT, MATCH, COST>(a, stream);
+    if (ctas(128 * 4) >= want) return launch_pass<MODE, 4, 128, SPLIT, MATCH, COST>(a, stream);
+    if (ctas(64 * 4) >= want) return launch_pass<MODE, 4, 64, SPLIT, MATCH, COST>(a, stream);
+    return launch_pass<MODE, 2, 64, SPLIT, MATCH, COST>(a, stream);
+}
+
+static int row_tiles_auto(int pairs, int nr, int S) {
+    const long long want = (long long)sm_count() * 4;
+    auto ctas = [&](int tile) { return (long long)pairs * ((nr + tile - 1) / tile) * S; };
+    int tile = 64 * 2;
+    if (ctas(128 * 8) >= want) tile = 128 * 8;
+    else if (ctas(128 * 4) >= want) tile = 128 * 4;
+    else if (ctas(64 * 4) >= want) tile = 64 * 4;
+    return (nr + tile - 1) / tile;
+}
+
+template <bool SPLIT, bool MATCH, bool COST>
+static int run_auction(EmdArgs a, cudaStream_t stream) {
+    const int blocks = sm_count() * 4;
+    emd_init_kernel<<<blocks, 256, 0, stream>>>(a.state, a.pairs, a.n, a.m);
+    HP_LAUNCH_CHECK("emd_init_kernel");
+    const int span_rows_n = a.S > 1 ? ((a.n + a.S - 1) / a.S + EMD_CC - 1) / EMD_CC * EMD_CC : a.n;  // columns = xyz1 (P2)
+    const int span_rows_m = a.S > 1 ? ((a.m + a.S - 1) / a.S + EMD_CC - 1) / EMD_CC * EMD_CC : a.m;  // columns = xyz2 (P1, P3)
+    int li = 0;
+    for (int j = 7; j > -2; --j, ++li) {  // approxmatch.cu:55
+        a.j = j;
+        a.level_index = li;
+        a.first_level = (li == 0);
+        int rc;
+        a.span = span_rows_m;
+        if ((rc = launch_pass_auto<1, SPLIT, false, false>(a, stream)) != HP_OK) return rc;
+        if (SPLIT) {
+            emd_combine_kernel<1><<<blocks, 256, 0, stream>>>(a);
+            HP_LAUNCH_CHECK("emd_combine_kernel<1>");
+        }
+        a.span = span_rows_n;
+        if ((rc = launch_pass_auto<2, SPLIT, false, false>(a, stream)) != HP_OK) return rc;
+        if (SPLIT) {
+            emd_combine_kernel<2><<<blocks, 256, 0, stream>>>(a);
+            HP_LAUNCH_CHECK("emd_combine_kernel<2>");
+        }
+        a.span = span_rows_m;
+        if ((rc = launch_pass_auto<3, SPLIT, MATCH, COST>(a, stream)) != HP_OK) return rc;
+        if (SPLIT) {
+            emd_combine_kernel<3><<<blocks, 256, 0, stream>>>(a);
+            HP_LAUNCH_CHECK("emd_combine_kernel<3>");
+        }
+    }
+    return HP_OK;
+}
+
+// column split for the workspace-backed path: enough CTAs to fill the GPU even for a single cloud pair
+static int choose_split(int pairs, int n, int m) {
+    const long long want = (long long)sm_count() * 8;
+    const int big = n > m ? n : m, small_ = n > m ? m : n;
+    long long base = (long long)pairs * ((small_ + 255) / 256);  // CTAs at the smallest useful row tile (64x4)
+    int S = (int)((want + base - 1) / base);
+    const int maxS = (big + EMD_CC - 1) / EMD_CC;
+    if (S > maxS) S = maxS;
+    if (S < 1) S = 1;
+    return S;
+}
+
+}  // namespace hp
+
+using namespace hp;
+
+extern "C" int hp_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *temp,
+                              void *stream) {
+    HP_REQUIRE(b >= 0 && n >= 0 && m >= 0, "hp_approxmatch: negative size (b=%d n=%d m=%d)", b, n, m);
+    if (b == 0 || (n == 0 && m == 0)) return HP_OK;
+    HP_REQUIRE(n > 0 && m > 0, "hp_approxmatch: one point set is empty (n=%d m=%d): the reference divides n/m", n, m);
+    HP_REQUIRE(xyz1 && xyz2 && match && temp, "hp_approxmatch: null pointer");
+    EmdArgs a = {};
+    a.first = xyz1, a.second = xyz2, a.ia = nullptr, a.ib = nullptr;
+    a.state = temp, a.partial = nullptr, a.match = match, a.costpart = nullptr;
+    a.n = n, a.m = m, a.pairs = b, a.S = 1, a.rstride = 0, a.cp_stride = 0;
+    return run_auction<false, true, false>(a, (cudaStream_t)stream);
+}
+
+extern "C" size_t hp_emd_cost_workspace_bytes(int pairs, int n, int m) {
+    if (pairs <= 0 || n <= 0 || m <= 0) return 16;
+    const int S = choose_split(pairs, n, m);
+    const size_t big = (size_t)(n > m ? n : m);
+    const size_t state = (size_t)pairs * 2 * ((size_t)n + m);
+    const size_t partial = S > 1 ? (size_t)pairs * S * big : 0;
+    const int rt_max = (n + 127) / 128;  // upper bound: the smallest row tile is 64 threads x 2 rows
+    const size_t costpart = (size_t)pairs * 9 * rt_max * S;
+    return (state + partial + costpart) * sizeof(float) + 64;
+}
+
+extern "C" int hp_emd_cost_pairs(int pairs, int n, int m, const float *first, const int *ia, const float *second,
+                                 const int *ib, float *cost, void *workspace, size_t workspace_bytes, void *stream_v) {
+    HP_REQUIRE(pairs >= 0 && n >= 0 && m >= 0, "hp_emd_cost_pairs: negative size (pairs=%d n=%d m=%d)", pairs, n, m);
+    if (pairs == 0) return HP_OK;
+    HP_REQUIRE(n > 0 && m > 0, "hp_emd_cost_pairs: empty point set (n=%d m=%d)", n, m);
+    HP_REQUIRE(first && second && cost && workspace, "hp_emd_cost_pairs: null pointer");
+    HP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "hp_emd_cost_pairs: workspace must be 16-byte aligned");
+    if (workspace_bytes < hp_emd_cost_workspace_bytes(pairs, n, m)) {
+        set_error("hp_emd_cost_pairs: workspace %zu < required %zu bytes", workspace_bytes, hp_emd_cost_workspace_bytes(pairs, n, m));
+        return HP_ERR_WORKSPACE;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const int S = choose_split(pairs, n, m);
+    const size_t big = (size_t)(n > m ? n : m);
+    float *ws = reinterpret_cast<float *>(workspace);
+    EmdArgs a = {};
+    a.first = first, a.second = second, a.ia = ia, a.ib = ib;
+    a.state = ws;
+    ws += (size_t)pairs * 2 * ((size_t)n + m);
+    a.partial = S > 1 ? ws : nullptr;
+    ws += S > 1 ? (size_t)pairs * S * big : 0;
+    a.costpart = ws;
+    a.match = nullptr;
+    a.n = n, a.m = m, a.pairs = pairs, a.S = S, a.rstride = (int)big;
+    const int rt3 = row_tiles_auto(pairs, n, S);  // the row tiling P3 will use (same rule as launch_pass_auto<3>)
+    a.cp_stride = 9 * rt3 * S;
+    int rc = (S > 1) ? run_auction<true, false, true>(a, stream) : run_auction<false, false, true>(a, stream);
+    if (rc != HP_OK) return rc;
+    emd_cost_finish_kernel<<<(pairs + 127) / 128, 128, 0, stream>>>(a.costpart, a.cp_stride, pairs, cost);
+    HP_LAUNCH_CHECK("emd_cost_finish_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *out,
+                            void *stream) {
+    HP_REQUIRE(b >= 0 && n >= 0 && m >= 0, "hp_matchcost: negative size (b=%d n=%d m=%d)", b, n, m);
+    if (b == 0) return HP_OK;
+    HP_REQUIRE(out != nullptr, "hp_matchcost: null output");
+    if (n == 0 || m == 0) {
+        HP_CUDA(cudaMemsetAsync(out, 0, (size_t)b * sizeof(float), (cudaStream_t)stream));
+        return HP_OK;
+    }
+    HP_REQUIRE(xyz1 && xyz2 && match, "hp_matchcost: null pointer");
+    matchcost_kernel<<<b * MC_CLUSTER, MC_THREADS, 0, (cudaStream_t)stream>>>(b, n, m, xyz1, xyz2, match, out);
+    HP_LAUNCH_CHECK("matchcost_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match,
+                                float *grad1, float *grad2, void *stream_v) {
+    HP_REQUIRE(b >= 0 && n >= 0 && m >= 0, "hp_matchcostgrad: negative size (b=%d n=%d m=%d)", b, n, m);
+    if (b == 0 || (n == 0 && m == 0)) return HP_OK;
+    HP_REQUIRE(b <= 65535, "hp_matchcostgrad: batch %d > 65535; split the batch", b);
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    HP_REQUIRE(grad1 && grad2, "hp_matchcostgrad: null output");
+    if (n == 0 || m == 0) {
+        if (n) HP_CUDA(cudaMemsetAsync(grad1, 0, (size_t)b * n * 3 * sizeof(float), stream));
+        if (m) HP_CUDA(cudaMemsetAsync(grad2, 0, (size_t)b * m * 3 * sizeof(float), stream));
+        return HP_OK;
+    }
+    HP_REQUIRE(xyz1 && xyz2 && match, "hp_matchcostgrad: null pointer");
+    matchcostgrad1_kernel<<<dim3((n + 127) / 128, b), 128, 512 * 3 * sizeof(float), stream>>>(b, n, m, xyz1, xyz2, match, grad1);
+    HP_LAUNCH_CHECK("matchcostgrad1_kernel");
+    matchcostgrad2_kernel<<<dim3((m * 32 + 255) / 256, b), 256, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad2);
+    HP_LAUNCH_CHECK("matchcostgrad2_kernel");
+    return HP_OK;
+}

@@ -4,3 +4,6 @@ from _pkg import pkg as _hp
 
 NNDistance = _hp.NNDistance
 NNDistanceGrad = _hp.NNDistanceGrad
+ApproxMatch = _hp.ApproxMatch
+MatchCost = _hp.MatchCost
+MatchCostGrad = _hp.MatchCostGrad

@@ -79,7 +79,7 @@ HP_API int hp_nndistance(int b, int n, const float *xyz, int m, const float *xyz
 HP_API int hp_nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2,
                       const float *grad_dist1, const int *idx1, const float *grad_dist2,
                       const int *idx2, float *grad_xyz1, float *grad_xyz2, void *stream);
-#define HP_NNGRAD_SMEM_POINTS 49152
+#define HP_NNGRAD_SMEM_POINTS 24576
 
 /* Fused ChamferLoss forward (losses/champfer_loss.py:11-17 semantics, direct-form distances):
  * hp_nndistance plus loss[0] = sum(result) + sum(result2), reduced deterministically inside
@@ -96,6 +96,36 @@ HP_API int hp_chamfer_forward(int b, int n, const float *xyz1, int m, const floa
 HP_API int hp_chamfer_backward(int b, int n, const float *xyz1, int m, const float *xyz2,
                         const int *idx1, const int *idx2, const float *grad_loss,
                         float *grad_xyz1, float *grad_xyz2, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * (b) Approximate EMD (soft auction)
+ * ---------------------------------------------------------------------------------- */
+
+/* Replaces `void approxmatch(int b,int n,int m,const float*xyz1,const float*xyz2,float*match,
+ * float*temp,cudaStream_t)` (structural_loss.cpp:11, approxmatch.cu:330-338).
+ *   match [b,m,n] (match[b,l,k]: l indexes xyz2, k indexes xyz1), temp [b,2(n+m)] scratch
+ *   (remainL,remainR,ratioL,ratioR per cloud; returned like the reference does). */
+HP_API int hp_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match,
+                   float *temp, void *stream);
+
+/* Replaces `void matchcost(...)` (structural_loss.cpp:12, approxmatch.cu:340-347):
+ *   out[b] = sum_{l,k} match[b,l,k] * |xyz1[b,k]-xyz2[b,l]|. */
+HP_API int hp_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match,
+                 float *out, void *stream);
+
+/* Replaces `void matchcostgrad(...)` (structural_loss.cpp:13, approxmatch.cu:349-357):
+ *   grad1[b,k] = sum_l match (x1-x2)/max(|x1-x2|,1e-10), grad2[b,l] the reverse. */
+HP_API int hp_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2,
+                     const float *match, float *grad1, float *grad2, void *stream);
+
+/* Fused, match-free EMD cost for the metrics path (utils/metrics.py:71-76,147: match_cost is
+ * only ever used forward-only there): cost[p] = match_cost(first[ia[p]], second[ib[p]]) for
+ * `pairs` cloud pairs addressed through index lists (ia/ib may be NULL = identity).
+ *   first [na, npts, 3], second [nb, npts, 3].  workspace: hp_emd_cost_workspace_bytes(). */
+HP_API size_t hp_emd_cost_workspace_bytes(int pairs, int n, int m);
+HP_API int hp_emd_cost_pairs(int pairs, int n, int m, const float *first, const int *ia,
+                      const float *second, const int *ib, float *cost, void *workspace,
+                      size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Measurement helpers (used by bench.py for the roofline denominators; not on the path)

@@ -194,9 +194,10 @@ HP_EXPORT void hp_oracle_approxmatch(int b, int n, int m, const float *xyz1, con
                 for (int l = 0; l < m; ++l) {
                     float d = level * sqdist3(p1[k * 3], p1[k * 3 + 1], p1[k * 3 + 2],
                                               p2[l * 3], p2[l * 3 + 1], p2[l * 3 + 2]);
-                    float w = fast_expf(d) * rl * ratioR[l];
-                    mt[(size_t)l * n + k] += w;
-                    suml += w;
+                    /* as compiled (sm_100 SASS of the reference): t = rl*e, then BOTH updates are fma(t, ratioR, .) */
+                    float t = rl * fast_expf(d);
+                    mt[(size_t)l * n + k] = fmaf(t, ratioR[l], mt[(size_t)l * n + k]);
+                    suml = fmaf(t, ratioR[l], suml);
                 }
                 remainL[k] = fmaxf(0.0f, remainL[k] - suml);
             }

@@ -1,0 +1,151 @@
+"""GPU parity tests for approximate EMD (approx_match / match_cost), through the C ABI.
+Bar (north star): EMD costs and gradients within 1e-5 relative of the reference's CUDA extension."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _clouds(b, n, m, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    a = ((torch.rand(b, n, 3, generator=g) - 0.5) * scale).contiguous()
+    c = ((torch.rand(b, m, 3, generator=g) - 0.5) * scale).contiguous()
+    return a, c
+
+
+def _rel(x, y):
+    x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+    return np.abs(x - y).max() / max(np.abs(y).max(), 1e-30)
+
+
+@pytest.mark.parametrize("pre", ["emd_eq", "emd_nm", "emd_mn"])
+def test_vs_reference_extension_golden(hp, golden_gpu, pre):
+    g = golden_gpu
+    a, c = torch.from_numpy(g[pre + "_a"]).to(DEV), torch.from_numpy(g[pre + "_b"]).to(DEV)
+    match, temp = hp.ApproxMatch(a, c)
+    assert tuple(match.shape) == g[pre + "_match"].shape and tuple(temp.shape) == (a.size(0), 2 * (a.size(1) + c.size(1)))
+    np.testing.assert_allclose(match.cpu().numpy(), g[pre + "_match"], rtol=2e-4, atol=2e-6)
+    cost = hp.MatchCost(a, c, match)
+    np.testing.assert_allclose(cost.cpu().numpy(), g[pre + "_cost"], rtol=1e-5)
+    # MatchCost / MatchCostGrad fed with the REFERENCE's match: isolates those kernels
+    mref = torch.from_numpy(g[pre + "_match"]).to(DEV)
+    np.testing.assert_allclose(hp.MatchCost(a, c, mref).cpu().numpy(), g[pre + "_cost"], rtol=1e-5)
+    g1, g2 = hp.MatchCostGrad(a, c, mref)
+    assert _rel(g1.cpu().numpy(), g[pre + "_g1"]) < 1e-5 and _rel(g2.cpu().numpy(), g[pre + "_g2"]) < 1e-5
+    # fused match-free cost
+    fused = hp.emd_cost_pairs(a, c)
+    np.testing.assert_allclose(fused.cpu().numpy(), g[pre + "_cost"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("b,n,m", [(4, 1024, 1024), (2, 2048, 2048), (33, 256, 256), (3, 500, 250), (2, 100, 333), (1, 1, 1), (2, 5, 1)])
+def test_vs_reference_extension_live(hp, ref_ext, b, n, m):
+    a, c = _clouds(b, n, m, seed=n + m)
+    ad, cd = a.to(DEV), c.to(DEV)
+    rmatch, _rtemp = ref_ext.ApproxMatch(ad, cd)
+    rcost = ref_ext.MatchCost(ad, cd, rmatch)
+    rg1, rg2 = ref_ext.MatchCostGrad(ad, cd, rmatch)
+    match, _ = hp.ApproxMatch(ad, cd)
+    cost = hp.MatchCost(ad, cd, match)
+    g1, g2 = hp.MatchCostGrad(ad, cd, match)
+    fused = hp.emd_cost_pairs(ad, cd)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(cost, rcost, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(fused, rcost, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(match, rmatch, rtol=5e-4, atol=2e-6)
+    assert _rel(g1.cpu().numpy(), rg1.cpu().numpy()) < 2e-5 and _rel(g2.cpu().numpy(), rg2.cpu().numpy()) < 2e-5
+
+
+def test_vs_cpu_oracle(hp, oracle):
+    a, c = _clouds(2, 192, 160, seed=3)
+    match, temp = hp.ApproxMatch(a.to(DEV), c.to(DEV))
+    omatch, _ = oracle.approx_match(a.numpy(), c.numpy())
+    ocost = oracle.match_cost_from_match(a.numpy(), c.numpy(), omatch)
+    cost = hp.MatchCost(a.to(DEV), c.to(DEV), match)
+    # the CPU oracle uses exp2f for MUFU.EX2 and 1/sqrtf for MUFU.RSQ: agreement ~1e-5, not bit-level
+    np.testing.assert_allclose(cost.cpu().numpy(), ocost, rtol=5e-5)
+    np.testing.assert_allclose(match.cpu().numpy(), omatch, rtol=1e-3, atol=5e-6)
+    og1, og2 = oracle.match_cost_grad(a.numpy(), c.numpy(), omatch)
+    g1, g2 = hp.MatchCostGrad(a.to(DEV), c.to(DEV), torch.from_numpy(omatch).to(DEV))
+    assert _rel(g1.cpu().numpy(), og1) < 1e-5 and _rel(g2.cpu().numpy(), og2) < 1e-5
+
+
+def test_fused_cost_pair_lists_and_split_paths(hp):
+    """hp_emd_cost_pairs with index lists; column-split (few pairs) and unsplit (many pairs) give the same costs."""
+    first, second = _clouds(6, 512, 512, seed=8)
+    fd, sd = first.to(DEV), second.to(DEV)
+    ia = torch.tensor([0, 0, 3, 5, 5, 2, 1], dtype=torch.int32, device=DEV)
+    ib = torch.tensor([0, 4, 3, 0, 5, 2, 1], dtype=torch.int32, device=DEV)
+    few = hp.emd_cost_pairs(fd, sd, ia, ib)  # 7 pairs -> column split S > 1
+    ref = torch.stack([hp.MatchCost(fd[i:i + 1], sd[j:j + 1], hp.ApproxMatch(fd[i:i + 1], sd[j:j + 1])[0])[0]
+                       for i, j in zip(ia.tolist(), ib.tolist())])
+    torch.testing.assert_close(few, ref, rtol=1e-5, atol=1e-7)
+    # many pairs -> no split: all 6x6 combinations, 40 times over
+    I, J = torch.meshgrid(torch.arange(6), torch.arange(6), indexing="ij")
+    ia2 = I.reshape(-1).repeat(40).to(torch.int32).to(DEV)
+    ib2 = J.reshape(-1).repeat(40).to(torch.int32).to(DEV)
+    many = hp.emd_cost_pairs(fd, sd, ia2, ib2)
+    assert torch.equal(many[:36], many[36:72]), "same pair must give bit-identical cost (deterministic reductions)"
+    sel = [ (ia2[:36] == i) & (ib2[:36] == j) for i, j in zip(ia.tolist(), ib.tolist())]
+    picked = torch.stack([many[:36][s][0] for s in sel])
+    torch.testing.assert_close(picked, few, rtol=1e-5, atol=1e-7)
+    again = hp.emd_cost_pairs(fd, sd, ia, ib)
+    assert torch.equal(again, few)
+
+
+def test_match_cost_autograd(hp, ref_ext):
+    a, c = _clouds(3, 300, 300, seed=12)
+    ad = a.to(DEV).requires_grad_(True)
+    cd = c.to(DEV).requires_grad_(True)
+    cost = hp.match_cost(ad, cd)
+    w = torch.tensor([1.0, -2.0, 0.5], device=DEV)
+    (cost * w).sum().backward()
+    rmatch, _ = ref_ext.ApproxMatch(ad.detach(), cd.detach())
+    rg1, rg2 = ref_ext.MatchCostGrad(ad.detach(), cd.detach(), rmatch)
+    rcost = ref_ext.MatchCost(ad.detach(), cd.detach(), rmatch)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(cost.detach(), rcost, rtol=1e-5, atol=1e-7)
+    assert _rel(ad.grad.cpu().numpy(), (rg1 * w.view(-1, 1, 1)).cpu().numpy()) < 2e-5
+    assert _rel(cd.grad.cpu().numpy(), (rg2 * w.view(-1, 1, 1)).cpu().numpy()) < 2e-5
+    with torch.no_grad():
+        fused = hp.match_cost(ad, cd)  # no grad -> match-free kernel
+    torch.testing.assert_close(fused, rcost, rtol=1e-5, atol=1e-7)
+    am = hp.approx_match(ad, cd)
+    assert not am.requires_grad and tuple(am.shape) == (3, 300, 300)
+
+
+def test_full_size_c3_properties(hp):
+    """BASELINE config C3 shapes (B=32, 2048x2048): size-independent properties of the auction."""
+    a, c = _clouds(32, 2048, 2048, seed=0)
+    ad, cd = a.to(DEV), c.to(DEV)
+    match, temp = hp.ApproxMatch(ad, cd)
+    assert torch.isfinite(match).all() and (match >= 0).all()
+    mass = match.sum(dim=(1, 2))
+    torch.testing.assert_close(mass, torch.full_like(mass, 2048.0), rtol=5e-3, atol=0)
+    assert (match.sum(dim=1) <= 1 + 1e-3).all() and (match.sum(dim=2) <= 1 + 1e-3).all()
+    cost = hp.MatchCost(ad, cd, match)
+    fused = hp.emd_cost_pairs(ad, cd)
+    torch.testing.assert_close(fused, cost, rtol=1e-5, atol=0)
+    # brute-force check of the cost definition on one cloud
+    d = torch.cdist(cd[0].double(), ad[0].double())  # [m, n]
+    assert float((match[0].double() * d).sum()) == pytest.approx(float(cost[0]), rel=1e-5)
+    # EMD of a cloud with itself is (near) zero compared with two different clouds
+    same = hp.emd_cost_pairs(ad[:4], ad[:4])
+    assert (same < 0.05 * cost[:4]).all()
+    # determinism
+    assert torch.equal(hp.emd_cost_pairs(ad, cd), fused)
+
+
+def test_input_validation(hp):
+    a = torch.zeros(2, 8, 3, device=DEV)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        hp.ApproxMatch(torch.zeros(2, 3, 8, device=DEV).transpose(1, 2), a)
+    with pytest.raises(RuntimeError, match="float32"):
+        hp.ApproxMatch(a.double(), a)
+    with pytest.raises(RuntimeError, match="empty"):
+        hp.ApproxMatch(torch.zeros(2, 0, 3, device=DEV), a)
+    with pytest.raises(RuntimeError, match="match must be"):
+        hp.MatchCost(a, a, torch.zeros(2, 8, 7, device=DEV))
+    m, t = hp.ApproxMatch(torch.zeros(0, 8, 3, device=DEV), torch.zeros(0, 8, 3, device=DEV))
+    assert m.numel() == 0
