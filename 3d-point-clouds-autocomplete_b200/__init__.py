@@ -13,4 +13,7 @@ from .chamfer import (ChamferLoss, NNDistance, NNDistanceFunction, NNDistanceGra
 from .emd import (ApproxMatch, MatchCost, MatchCostFunction, MatchCostGrad, approx_match, emd_cost_pairs,  # noqa: F401
                   match_cost)
 
+from . import metrics  # noqa: F401
+from .metrics import compute_all_metrics, pairwise_cd, pairwise_emd  # noqa: F401
+
 __version__ = "0.1.0"

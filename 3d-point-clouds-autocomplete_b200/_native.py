@@ -40,6 +40,7 @@ SIGNATURES = {
     "hp_matchcostgrad": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_emd_cost_workspace_bytes": (_sz, [_int, _int, _int]),
     "hp_emd_cost_pairs": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hp_pairwise_cd": (_int, [_int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "hp_measure_peak": (_int, [_int, _int, ctypes.POINTER(ctypes.c_double), _vp]),
 }
 

@@ -1,0 +1,275 @@
+"""Set-vs-set metrics (MMD-CD/EMD, COV, 1-NNA) on the B200 kernels, optionally sharded by row
+blocks over the GPUs of one box.
+
+Mirrors, for this path, the reference's ``utils/metrics.py``:
+  ``emd_approx`` (:71-76), ``dist_chamfer`` (:78-83), ``earth_mover_distance`` (:44-68),
+  ``_pairwise_EMD_CD_`` (:121-158), ``knn`` (:162-191), ``mmd_cov`` (:194-206),
+  ``compute_all_metrics`` (:209-238; its 1-NN block is dead code inside a string literal in the
+  reference, :224-237 -- revived here behind ``one_nn=True``).
+
+Work split: the cloud-distance matrices are the only heavy part; rank g of G owns the
+row block ``rows[g*ceil(Nr/G) : (g+1)*ceil(Nr/G))`` of every matrix (rows = clouds of the FIRST
+argument of ``_pairwise_EMD_CD_``), the second set is replicated.  Matrix entries are produced by the
+same kernels whatever G is, so they are bit-identical for G = 1, 2, 4, 8.  Only per-row and per-column
+(min, argmin) vectors cross NVLink (all_gather of a few KB); means and the unique-count are taken after
+the gather in a fixed order, so the final numbers are identical for every G.
+
+The epilogues below (min / argmin / mean / unique over a [Nr, Ns] matrix) are device-agnostic torch
+ops on purpose: they are O(Nr*Ns) trivia next to the O(Nr*Ns*N*M) kernels, and keeping them
+device-agnostic lets the sharding logic run under gloo on CPU in the test-suite.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _native
+from ._glue import check_points, check_same_device, on_device_of
+from .chamfer import ChamferLoss
+from .emd import emd_cost_pairs, match_cost
+
+INF = float("inf")
+
+
+# --------------------------------------------------------------------------------------
+# sharding helpers (host logic; exercised with gloo on CPU in tests/test_metrics_sharding.py)
+# --------------------------------------------------------------------------------------
+def _rank_world(group) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_rows(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Row block of `rank`: equal ceil-sized blocks (equal work: per-pair cost is data independent)."""
+    per = (n_rows + world - 1) // world
+    return min(n_rows, rank * per), min(n_rows, (rank + 1) * per)
+
+
+def _all_gather_padded(t: torch.Tensor, per: int, total: int, fill, group) -> torch.Tensor:
+    """all_gather of per-rank vectors of (at most) `per` leading entries -> first `total` entries."""
+    rank, world = _rank_world(group)
+    if world == 1:
+        return t[:total]
+    pad = torch.full((per,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat(out, dim=0)[:total]
+
+
+def row_min_gathered(block: torch.Tensor, n_rows: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(min, argmin) over columns for every row of the full matrix; each rank holds a row block."""
+    _, world = _rank_world(group)
+    per = (n_rows + world - 1) // world
+    if block.shape[0] > 0:
+        val, idx = torch.min(block, dim=1)
+    else:
+        val = block.new_empty((0,))
+        idx = torch.empty((0,), dtype=torch.long, device=block.device)
+    return (_all_gather_padded(val, per, n_rows, INF, group),
+            _all_gather_padded(idx, per, n_rows, 0, group))
+
+
+def col_min_merged(block: torch.Tensor, row_begin: int, n_rows: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(min, argmin-row) over ALL rows for every column; ties -> lowest global row index."""
+    rank, world = _rank_world(group)
+    ncols = block.shape[1]
+    if block.shape[0] > 0:
+        val, idx = torch.min(block, dim=0)  # first (lowest) row among local ties
+        idx = idx + row_begin
+    else:
+        val = torch.full((ncols,), INF, dtype=block.dtype, device=block.device)
+        idx = torch.full((ncols,), n_rows, dtype=torch.long, device=block.device)
+    if world == 1:
+        return val, idx
+    vals = [torch.empty_like(val) for _ in range(world)]
+    idxs = [torch.empty_like(idx) for _ in range(world)]
+    dist.all_gather(vals, val, group=group)
+    dist.all_gather(idxs, idx, group=group)
+    V, I = torch.stack(vals), torch.stack(idxs)  # [world, ncols]; rank order == ascending row order
+    best = torch.min(V, dim=0)
+    # lowest rank among equal minima == lowest global row index (row blocks are ordered by rank)
+    first_rank = torch.argmax((V == best.values.unsqueeze(0)).to(torch.uint8), dim=0)
+    return best.values, I.gather(0, first_rank.unsqueeze(0)).squeeze(0)
+
+
+# --------------------------------------------------------------------------------------
+# the heavy part: row blocks of the cloud-distance matrices (kernels)
+# --------------------------------------------------------------------------------------
+def pairwise_cd(first: torch.Tensor, second: torch.Tensor, row_begin: int = 0, row_end: Optional[int] = None) -> torch.Tensor:
+    """cd[r - row_begin, s] = mean_i min_j d(first_r[i], second_s[j]) + mean_j min_i d(...)."""
+    check_points(first, "first")
+    check_points(second, "second")
+    check_same_device(first, second)
+    na, nb, n, m = first.size(0), second.size(0), first.size(1), second.size(1)
+    row_end = na if row_end is None else row_end
+    out = torch.empty((max(0, row_end - row_begin), nb), dtype=torch.float32, device=first.device)
+    if out.numel() == 0:
+        return out
+    lib = _native.load()
+    max_rows = max(1, (1 << 30) // max(nb, 1))
+    with on_device_of(first) as stream:
+        for rb in range(row_begin, row_end, max_rows):
+            re_ = min(row_end, rb + max_rows)
+            rc = lib.hp_pairwise_cd(na, nb, n, m, first.data_ptr(), second.data_ptr(), rb, re_,
+                                    out[rb - row_begin:].data_ptr(), stream)
+            _native.check(rc, "hp_pairwise_cd")
+    return out
+
+
+def pairwise_emd(first: torch.Tensor, second: torch.Tensor, row_begin: int = 0, row_end: Optional[int] = None,
+                 max_pairs_per_call: int = 4096) -> torch.Tensor:
+    """emd[r - row_begin, s] = match_cost(first_r, second_s) / N  (emd_approx, utils/metrics.py:71-76)."""
+    check_points(first, "first")
+    check_points(second, "second")
+    check_same_device(first, second)
+    na, nb, n = first.size(0), second.size(0), first.size(1)
+    if n != second.size(1):
+        raise AssertionError("Not sure what would EMD do in this case")  # utils/metrics.py:73
+    row_end = na if row_end is None else row_end
+    rows = max(0, row_end - row_begin)
+    out = torch.empty((rows, nb), dtype=torch.float32, device=first.device)
+    flat = out.view(-1)
+    total = rows * nb
+    dev = first.device
+    for p0 in range(0, total, max_pairs_per_call):
+        p1 = min(total, p0 + max_pairs_per_call)
+        p = torch.arange(p0, p1, device=dev, dtype=torch.int64)
+        ia = (row_begin + p // nb).to(torch.int32).contiguous()
+        ib = (p % nb).to(torch.int32).contiguous()
+        flat[p0:p1] = emd_cost_pairs(first, second, ia, ib) / float(n)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# reference-named entry points
+# --------------------------------------------------------------------------------------
+def emd_approx(sample: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    N, N_ref = sample.size(1), ref.size(1)
+    assert N == N_ref, "Not sure what would EMD do in this case"
+    return match_cost(sample.contiguous(), ref.contiguous()) / float(N)
+
+
+def dist_chamfer(x: torch.Tensor, y: torch.Tensor, chamfer_loss=None):
+    """(min over x for every y, min over y for every x), like P.min(1)[0], P.min(2)[0] of the reference
+    (utils/metrics.py:78-83) -- from the nearest-neighbour kernel, no [B,N,M] matrix."""
+    from .chamfer import NNDistance
+
+    d_x, _ix, d_y, _iy = NNDistance(x.contiguous(), y.contiguous())
+    return d_y, d_x
+
+
+def earth_mover_distance(sample_pcs, ref_pcs, batch_size=None):
+    sample_pcs, ref_pcs = sample_pcs.contiguous(), ref_pcs.contiguous()
+    if sample_pcs.dim() == 2:
+        sample_pcs = sample_pcs.unsqueeze(0)
+    if ref_pcs.dim() == 2:
+        ref_pcs = ref_pcs.unsqueeze(0)
+    assert sample_pcs.shape[0] == ref_pcs.shape[0], f"REF:{ref_pcs.shape[0]} SMP:{sample_pcs.shape[0]}"
+    return emd_approx(sample_pcs, ref_pcs)  # one fused launch sequence; batch_size only bounded memory in the reference
+
+
+def _pairwise_EMD_CD_(sample_pcs, ref_pcs, batch_size=None, chamfer_loss=None, rows: Optional[Tuple[int, int]] = None,
+                      with_emd: bool = True):
+    """All-pairs matrices [N_first(rows), N_second]; `batch_size` and `chamfer_loss` are accepted for
+    signature compatibility (utils/metrics.py:121) and ignored: nothing is materialised per chunk."""
+    first, second = sample_pcs.contiguous(), ref_pcs.contiguous()
+    rb, re_ = rows if rows is not None else (0, first.size(0))
+    all_cd = pairwise_cd(first, second, rb, re_)
+    all_emd = pairwise_emd(first, second, rb, re_) if with_emd else None
+    return all_cd, all_emd
+
+
+def mmd_cov(all_dist: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """utils/metrics.py:194-206 on a full [N_sample, N_ref] matrix (single process)."""
+    return mmd_cov_from_block(all_dist.t().contiguous(), 0, all_dist.size(1), None)
+
+
+def mmd_cov_from_block(block_rs: torch.Tensor, row_begin: int, n_ref: int, group=None) -> Dict[str, torch.Tensor]:
+    """mmd_cov(M_rs.t()) where this rank holds rows [row_begin, row_begin+block.shape[0]) of M_rs [N_ref, N_sample].
+
+    all_dist = M_rs.t() is [N_sample, N_ref]:
+      min over dim 1 (+argmin, -> COV, mmd_smp)  == column (min, argmin-row) of M_rs   (merged across ranks)
+      min over dim 0 (-> MMD)                     == row min of M_rs                    (local, then gathered)
+    """
+    min_from_smp, min_idx = col_min_merged(block_rs, row_begin, n_ref, group)
+    min_val, _ = row_min_gathered(block_rs, n_ref, group)
+    mmd = min_val.mean()
+    mmd_smp = min_from_smp.mean()
+    cov = float(min_idx.unique().view(-1).size(0)) / float(n_ref)
+    cov = torch.tensor(cov).to(block_rs)
+    return {"mmd(Fidelity)": mmd, "cov(Coverage)": cov, "mmd_smp": mmd_smp}
+
+
+def knn(Mxx, Mxy, Myy, k, sqrt=False):
+    """1-NN two-sample test on full matrices (utils/metrics.py:162-191), k = 1."""
+    return knn_from_blocks(Mxx, Mxy, Myy, 0, 0, Mxx.size(0), Myy.size(0), k, sqrt, None)
+
+
+def knn_from_blocks(Mxx_blk, Mxy_blk, Myy_blk, x_begin: int, y_begin: int, n0: int, n1: int, k: int = 1,
+                    sqrt: bool = False, group=None):
+    """knn() when each rank holds a row block of Mxx [n0,n0], Mxy [n0,n1] (rows x_begin..) and of
+    Myy [n1,n1] (rows y_begin..).  Column c of the stacked matrix [[Mxx,Mxy],[Mxy^T,Myy]] + inf*I is
+    [Mxx[:,c]; Mxy[c,:]] for c < n0 and [Mxy[:,c-n0]; Myy[:,c-n0]] otherwise, so its top-1 needs only
+    column-minima of Mxx, Mxy, Myy (merged across ranks) and row-minima of Mxy (local)."""
+    if k != 1:
+        raise NotImplementedError("only k=1 (1-NNA) is used by the metrics")
+    f = (lambda t: t.abs().sqrt()) if sqrt else (lambda t: t)
+    Mxx_blk, Mxy_blk, Myy_blk = f(Mxx_blk).clone(), f(Mxy_blk), f(Myy_blk).clone()
+    if Mxx_blk.shape[0] > 0:
+        r = torch.arange(Mxx_blk.shape[0], device=Mxx_blk.device)
+        Mxx_blk[r, r + x_begin] = INF
+    if Myy_blk.shape[0] > 0:
+        r = torch.arange(Myy_blk.shape[0], device=Myy_blk.device)
+        Myy_blk[r, r + y_begin] = INF
+    xx_v, _ = col_min_merged(Mxx_blk, x_begin, n0, group)      # nearest other x for every x
+    xy_row_v, _ = row_min_gathered(Mxy_blk, n0, group)          # nearest y for every x
+    xy_col_v, _ = col_min_merged(Mxy_blk, x_begin, n0, group)  # nearest x for every y
+    yy_v, _ = col_min_merged(Myy_blk, y_begin, n1, group)      # nearest other y for every y
+    # stacked row order is x first, then y: on ties the lower stacked index (an x) wins
+    pred_x = (xx_v <= xy_row_v).to(Mxy_blk.dtype)   # 1 = nearest neighbour is an x (label 1)
+    pred_y = (xy_col_v <= yy_v).to(Mxy_blk.dtype)
+    pred = torch.cat((pred_x, pred_y))
+    label = torch.cat((torch.ones(n0), torch.zeros(n1))).to(Mxy_blk)
+    s = {
+        "tp": (pred * label).sum(), "fp": (pred * (1 - label)).sum(),
+        "fn": ((1 - pred) * label).sum(), "tn": ((1 - pred) * (1 - label)).sum(),
+    }
+    s.update({
+        "precision": s["tp"] / (s["tp"] + s["fp"] + 1e-10),
+        "recall": s["tp"] / (s["tp"] + s["fn"] + 1e-10),
+        "acc_t": s["tp"] / (s["tp"] + s["fn"] + 1e-10),
+        "acc_f": s["tn"] / (s["tn"] + s["fp"] + 1e-10),
+        "acc": torch.eq(label, pred).float().mean(),
+    })
+    return s
+
+
+def compute_all_metrics(sample_pcs, ref_pcs, batch_size=None, chamfer_loss=None, group=None, with_emd: bool = True,
+                        one_nn: bool = False) -> Dict[str, torch.Tensor]:
+    """utils/metrics.py:209-238 with the same result keys; values are 0-dim device tensors.
+
+    With torch.distributed initialised (one process per GPU) the rows of every matrix are sharded
+    over the ranks of `group`; every rank returns the same dict."""
+    rank, world = _rank_world(group)
+    sample_pcs, ref_pcs = sample_pcs.contiguous(), ref_pcs.contiguous()
+    n_ref, n_smp = ref_pcs.size(0), sample_pcs.size(0)
+    rb, re_ = shard_rows(n_ref, rank, world)
+    results: Dict[str, torch.Tensor] = {}
+    M_rs_cd, M_rs_emd = _pairwise_EMD_CD_(ref_pcs, sample_pcs, batch_size, chamfer_loss, rows=(rb, re_), with_emd=with_emd)
+    results.update({"%s-CD" % k: v for k, v in mmd_cov_from_block(M_rs_cd, rb, n_ref, group).items()})
+    if with_emd:
+        results.update({"%s-EMD" % k: v for k, v in mmd_cov_from_block(M_rs_emd, rb, n_ref, group).items()})
+    if one_nn:
+        sb, se = shard_rows(n_smp, rank, world)
+        M_rr_cd, M_rr_emd = _pairwise_EMD_CD_(ref_pcs, ref_pcs, batch_size, chamfer_loss, rows=(rb, re_), with_emd=with_emd)
+        M_ss_cd, M_ss_emd = _pairwise_EMD_CD_(sample_pcs, sample_pcs, batch_size, chamfer_loss, rows=(sb, se), with_emd=with_emd)
+        one = knn_from_blocks(M_rr_cd, M_rs_cd, M_ss_cd, rb, sb, n_ref, n_smp, 1, False, group)
+        results.update({"1-NN-CD-%s" % k: v for k, v in one.items() if "acc" in k})
+        if with_emd:
+            one = knn_from_blocks(M_rr_emd, M_rs_emd, M_ss_emd, rb, sb, n_ref, n_smp, 1, False, group)
+            results.update({"1-NN-EMD-%s" % k: v for k, v in one.items() if "acc" in k})
+    return results

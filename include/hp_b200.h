@@ -128,6 +128,17 @@ HP_API int hp_emd_cost_pairs(int pairs, int n, int m, const float *first, const 
                       size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * (d) Set-vs-set metrics (utils/metrics.py:121-158): one row block of the cloud-distance
+ *     matrix per call; rows are what gets sharded across GPUs.
+ * ---------------------------------------------------------------------------------- */
+
+/* cd[r - row_begin, s] = mean_i min_j d(first[r,i], second[s,j]) + mean_j min_i d(...)
+ * for r in [row_begin,row_end), s in [0,nb).  first [na,n,3], second [nb,m,3].
+ * Each unordered point pair is evaluated once and feeds both minima. */
+HP_API int hp_pairwise_cd(int na, int nb, int n, int m, const float *first, const float *second,
+                   int row_begin, int row_end, float *cd, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * Measurement helpers (used by bench.py for the roofline denominators; not on the path)
  * ---------------------------------------------------------------------------------- */
 /* Runs a register-resident FFMA (kind 0), packed FFMA2 (kind 1) or MUFU.EX2 (kind 2) chain

@@ -1,0 +1,89 @@
+"""GPU parity tests for the set-vs-set metrics path (pairwise CD/EMD matrices, MMD/COV/1-NNA)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _sets(na, nb, n, m, seed):
+    g = torch.Generator().manual_seed(seed)
+    a = (torch.rand(na, n, 3, generator=g) - 0.5).contiguous()
+    b = (torch.rand(nb, m, 3, generator=g) - 0.5).contiguous()
+    return a, b
+
+
+@pytest.mark.parametrize("na,nb,n,m", [(3, 4, 256, 256), (2, 3, 300, 129), (2, 2, 2048, 2048), (1, 2, 5000, 2500), (2, 2, 1, 7), (1, 1, 4100, 33)])
+def test_pairwise_cd_vs_oracle(hp, oracle, na, nb, n, m):
+    a, b = _sets(na, nb, n, m, seed=n + m)
+    cd = hp.pairwise_cd(a.to(DEV), b.to(DEV))
+    ocd = oracle.pairwise_cd_direct(a.numpy(), b.numpy())
+    # every min is bit-exact (same arithmetic as nn_distance); only the order of the two mean reductions differs
+    np.testing.assert_allclose(cd.cpu().numpy(), ocd, rtol=2e-6)
+    # from the nearest-neighbour kernel of this library: identical mins, so very tight
+    ad, bd = a.to(DEV), b.to(DEV)
+    for r in range(na):
+        d1, _, d2, _ = hp.NNDistance(ad[r:r + 1].expand(nb, -1, -1).contiguous(), bd)
+        ref = d1.double().mean(1) + d2.double().mean(1)
+        torch.testing.assert_close(cd[r].double(), ref, rtol=2e-6, atol=0)
+
+
+def test_pairwise_cd_row_blocks_are_bit_identical(hp):
+    a, b = _sets(7, 5, 512, 512, seed=2)
+    ad, bd = a.to(DEV), b.to(DEV)
+    full = hp.pairwise_cd(ad, bd)
+    parts = torch.cat([hp.pairwise_cd(ad, bd, 0, 3), hp.pairwise_cd(ad, bd, 3, 4), hp.pairwise_cd(ad, bd, 4, 7)])
+    assert torch.equal(full, parts)
+    assert torch.equal(full, hp.pairwise_cd(ad, bd))
+    # symmetry of the definition: cd(a_r, b_s) == cd(b_s, a_r) up to the order of the two means
+    swapped = hp.pairwise_cd(bd, ad)
+    torch.testing.assert_close(full, swapped.t(), rtol=1e-6, atol=0)
+
+
+def test_pairwise_cd_vs_reference_expansion_form(hp, oracle):
+    """vs the reference's own dist_chamfer arithmetic (expansion form, torch port): 1e-5 relative."""
+    a, b = _sets(3, 3, 1024, 1024, seed=5)
+    cd = hp.pairwise_cd(a.to(DEV), b.to(DEV)).cpu().numpy()
+    ref = oracle.pairwise_cd_expansion(a.numpy(), b.numpy(), batch_size=2)
+    np.testing.assert_allclose(cd, ref, rtol=1e-5)
+
+
+def test_pairwise_emd_vs_match_cost(hp):
+    a, b = _sets(3, 4, 256, 256, seed=6)
+    ad, bd = a.to(DEV), b.to(DEV)
+    emd = hp.pairwise_emd(ad, bd, max_pairs_per_call=5)  # forces several batched calls
+    for r in range(3):
+        row = hp.match_cost(ad[r:r + 1].expand(4, -1, -1).contiguous(), bd) / 256.0
+        torch.testing.assert_close(emd[r], row, rtol=1e-5, atol=1e-8)
+
+
+def test_compute_all_metrics_vs_oracle(hp, oracle):
+    smp, ref = _sets(6, 5, 128, 128, seed=9)
+    res = hp.compute_all_metrics(smp.to(DEV), ref.to(DEV), batch_size=3, chamfer_loss=hp.ChamferLoss(), one_nn=True)
+    ores = oracle.compute_all_metrics(smp.numpy(), ref.numpy(), with_emd=True, with_1nn=True)
+    assert set(res) == set(ores), (sorted(res), sorted(ores))
+    for k in ("mmd(Fidelity)-CD", "cov(Coverage)-CD", "mmd_smp-CD", "mmd(Fidelity)-EMD", "cov(Coverage)-EMD", "mmd_smp-EMD"):
+        assert k in res
+    for k, v in ores.items():
+        assert v == pytest.approx(float(res[k]), rel=5e-5), k
+        assert res[k].dim() == 0 and res[k].is_cuda
+
+
+def test_compute_all_metrics_reference_keys_without_1nn(hp):
+    smp, ref = _sets(4, 4, 64, 64, seed=1)
+    res = hp.compute_all_metrics(smp.to(DEV), ref.to(DEV), 2, hp.ChamferLoss())
+    assert sorted(res) == sorted(["mmd(Fidelity)-CD", "cov(Coverage)-CD", "mmd_smp-CD",
+                                  "mmd(Fidelity)-EMD", "cov(Coverage)-EMD", "mmd_smp-EMD"])
+
+
+def test_dist_chamfer_and_emd_approx(hp):
+    a, b = _sets(3, 3, 200, 150, seed=3)
+    ad, bd = a.to(DEV), b.to(DEV)
+    dl, dr = hp.metrics.dist_chamfer(ad, bd, hp.ChamferLoss())
+    P = hp.ChamferLoss().batch_pairwise_dist(ad, bd)
+    torch.testing.assert_close(dl, P.min(1)[0], rtol=0, atol=2e-6)
+    torch.testing.assert_close(dr, P.min(2)[0], rtol=0, atol=2e-6)
+    a2, b2 = _sets(2, 2, 128, 128, seed=4)
+    e = hp.metrics.emd_approx(a2.to(DEV), b2.to(DEV))
+    torch.testing.assert_close(e, hp.match_cost(a2.to(DEV), b2.to(DEV)) / 128.0)

@@ -1,0 +1,96 @@
+"""CPU: host-side logic of the sharded metrics (row-block partition, (min,argmin) merges, 1-NNA from
+blocks) against the oracle / golden vectors, single process and world_size=2 over gloo."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_mmd_cov_and_knn_match_reference_golden(hp, golden_cpu):
+    g = golden_cpu
+    r = hp.metrics.mmd_cov(torch.from_numpy(g["mc_M"]))
+    assert float(r["mmd(Fidelity)"]) == pytest.approx(float(g["mc_mmd"]), rel=1e-6)
+    assert float(r["cov(Coverage)"]) == pytest.approx(float(g["mc_cov"]), rel=1e-6)
+    assert float(r["mmd_smp"]) == pytest.approx(float(g["mc_mmd_smp"]), rel=1e-6)
+    k = hp.metrics.knn(torch.from_numpy(g["knn_Mxx"]), torch.from_numpy(g["knn_Mxy"]), torch.from_numpy(g["knn_Myy"]), 1)
+    for key in ("tp", "fp", "fn", "tn", "precision", "recall", "acc_t", "acc_f", "acc"):
+        assert float(k[key]) == pytest.approx(float(g["knn_" + key]), rel=1e-6), key
+
+
+def test_knn_and_mmd_cov_match_oracle_on_random_matrices_with_ties(hp, oracle):
+    gen = torch.Generator().manual_seed(4)
+    for n0, n1 in [(5, 7), (16, 16), (1, 3)]:
+        Mxx = torch.randint(0, 6, (n0, n0), generator=gen).float()
+        Myy = torch.randint(0, 6, (n1, n1), generator=gen).float()
+        Mxy = torch.randint(0, 6, (n0, n1), generator=gen).float()
+        k = hp.metrics.knn(Mxx, Mxy, Myy, 1)
+        ok = oracle.knn(Mxx.numpy(), Mxy.numpy(), Myy.numpy(), 1)
+        for key in ("tp", "fp", "fn", "tn", "acc"):
+            assert float(k[key]) == pytest.approx(ok[key], rel=1e-6), (n0, n1, key)
+        r = hp.metrics.mmd_cov(Mxy.t().contiguous())
+        o = oracle.mmd_cov(Mxy.t().numpy())
+        for key in o:
+            assert float(r[key]) == pytest.approx(float(o[key]), rel=1e-6)
+
+
+def test_shard_rows_partition(hp):
+    for n in (0, 1, 7, 1000):
+        for world in (1, 2, 3, 8):
+            blocks = [hp.metrics.shard_rows(n, r, world) for r in range(world)]
+            covered = [i for b, e in blocks for i in range(b, e)]
+            assert covered == list(range(n))
+            assert max(e - b for b, e in blocks) <= (n + world - 1) // world
+
+
+def _worker(rank, world, port, path, n_ref, n_smp):
+    sys.path.insert(0, REPO)
+    import importlib
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    hp = importlib.import_module("3d-point-clouds-autocomplete_b200")
+    M = hp.metrics
+    d = torch.load(path)
+    rb, re_ = M.shard_rows(n_ref, rank, world)
+    sb, se = M.shard_rows(n_smp, rank, world)
+    res = M.mmd_cov_from_block(d["M_rs"][rb:re_].contiguous(), rb, n_ref, None)
+    one = M.knn_from_blocks(d["M_rr"][rb:re_].contiguous(), d["M_rs"][rb:re_].contiguous(), d["M_ss"][sb:se].contiguous(),
+                            rb, sb, n_ref, n_smp, 1, False, None)
+    out = {k: float(v) for k, v in res.items()}
+    out.update({"knn_" + k: float(v) for k, v in one.items()})
+    torch.save(out, f"{path}.rank{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_ref,n_smp", [(9, 6), (4, 4)])
+def test_world_size_2_gloo_equals_single_process(hp, tmp_path, n_ref, n_smp):
+    gen = torch.Generator().manual_seed(n_ref)
+    # small integers -> plenty of ties, so the lowest-index merge rule is exercised across ranks
+    d = {"M_rs": torch.randint(0, 5, (n_ref, n_smp), generator=gen).float(),
+         "M_rr": torch.randint(0, 5, (n_ref, n_ref), generator=gen).float(),
+         "M_ss": torch.randint(0, 5, (n_smp, n_smp), generator=gen).float()}
+    path = str(tmp_path / "mats.pt")
+    torch.save(d, path)
+    single = {k: float(v) for k, v in hp.metrics.mmd_cov_from_block(d["M_rs"], 0, n_ref, None).items()}
+    single.update({"knn_" + k: float(v) for k, v in hp.metrics.knn(d["M_rr"], d["M_rs"], d["M_ss"], 1).items()})
+    mp.spawn(_worker, args=(2, _free_port(), path, n_ref, n_smp), nprocs=2, join=True)
+    for rank in range(2):
+        got = torch.load(f"{path}.rank{rank}")
+        assert got == single, (rank, got, single)
