@@ -31,6 +31,7 @@ SIGNATURES = {
     "hp_error_string": (ctypes.c_char_p, [_int]),
     "hp_last_error_message": (ctypes.c_char_p, []),
     "hp_nndistance": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hp_nndistance_ws": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hp_nndistancegrad": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_chamfer_workspace_bytes": (_sz, [_int, _int, _int]),
     "hp_chamfer_forward": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -40,6 +41,11 @@ SIGNATURES = {
     "hp_matchcostgrad": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_emd_cost_workspace_bytes": (_sz, [_int, _int, _int]),
     "hp_emd_cost_pairs": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hp_target_network_num_weights": (_ll, [_int, ctypes.POINTER(_int), _int]),
+    "hp_target_network_forward": (_int, [_int, _int, _int, ctypes.POINTER(_int), _int, _vp, _vp, _ll, _vp, _int, _vp]),
+    "hp_target_network_backward_workspace_bytes": (_sz, [_int, _int, _int, ctypes.POINTER(_int), _int]),
+    "hp_target_network_backward": (_int, [_int, _int, _int, ctypes.POINTER(_int), _int, _vp, _vp, _ll, _vp, _int, _vp, _vp,
+                                          _vp, _sz, _vp]),
     "hp_pairwise_cd": (_int, [_int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "hp_measure_peak": (_int, [_int, _int, ctypes.POINTER(ctypes.c_double), _vp]),
 }

@@ -42,10 +42,13 @@ def NNDistance(set_d: torch.Tensor, set_q: torch.Tensor):
     idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
     dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
     idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+    lib = _native.load()
     with on_device_of(set_d) as stream:
-        rc = _native.load().hp_nndistance(b, n, set_d.data_ptr(), m, set_q.data_ptr(), dist1.data_ptr(),
-                                          idx1.data_ptr(), dist2.data_ptr(), idx2.data_ptr(), stream)
-    _native.check(rc, "hp_nndistance")
+        nbytes = lib.hp_chamfer_workspace_bytes(b, n, m)
+        ws = zeroed_workspace(dev, stream, nbytes, "chamfer")
+        rc = lib.hp_nndistance_ws(b, n, set_d.data_ptr(), m, set_q.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
+                                  dist2.data_ptr(), idx2.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+    _native.check(rc, "hp_nndistance_ws")
     return [dist1, idx1, dist2, idx2]
 
 

@@ -407,6 +407,22 @@ __global__ void nn_grad_atomic_kernel(int b, int n, const float *__restrict__ xy
     }
 }
 
+// warp-ring forward (chamfer_ring.cu): every unordered pair once, both directions
+size_t nn_ring_workspace_bytes(int b, int n, int m);
+int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
+                           int *idx2, float *loss, void *workspace, cudaStream_t stream);
+
+// HP_NN_RING=0 selects the first-generation ordered-pair kernel (kept for A/B measurements and as the
+// workspace-free path of hp_nndistance).
+static bool use_ring() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HP_NN_RING");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // ---- host side ---------------------------------------------------------------------------
 constexpr int FWD_MIN_QT = 32;  // smallest query tile of any variant (sizes the loss workspace)
 constexpr int GRAD_THREADS = 1024;
@@ -517,7 +533,26 @@ extern "C" size_t hp_chamfer_workspace_bytes(int b, int n, int m) {
     if (b <= 0 || n <= 0 || m <= 0) return 16;
     const int QT = FWD_MIN_QT;
     size_t tiles = (size_t)b * ((n + QT - 1) / QT + (m + QT - 1) / QT);
-    return 8 + tiles * sizeof(float) + 8;
+    const size_t ordered = 8 + tiles * sizeof(float) + 8, ring = nn_ring_workspace_bytes(b, n, m);
+    return ordered > ring ? ordered : ring;
+}
+
+extern "C" int hp_nndistance_ws(int b, int n, const float *xyz, int m, const float *xyz2, float *result, int *result_i,
+                                float *result2, int *result2_i, void *workspace, size_t workspace_bytes, void *stream) {
+    HP_REQUIRE(b >= 0 && n >= 0 && m >= 0, "hp_nndistance_ws: negative size (b=%d n=%d m=%d)", b, n, m);
+    if (b == 0 || (n == 0 && m == 0)) return HP_OK;
+    HP_REQUIRE(n > 0 && m > 0, "hp_nndistance_ws: one point set is empty (n=%d m=%d): nearest neighbour undefined", n, m);
+    HP_REQUIRE(xyz && xyz2 && result && result_i && result2 && result2_i, "hp_nndistance_ws: null pointer");
+    HP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+               "hp_nndistance_ws: workspace null or not 16-byte aligned");
+    if (workspace_bytes < hp_chamfer_workspace_bytes(b, n, m)) {
+        set_error("hp_nndistance_ws: workspace %zu < required %zu bytes", workspace_bytes, hp_chamfer_workspace_bytes(b, n, m));
+        return HP_ERR_WORKSPACE;
+    }
+    if (use_ring())
+        return nn_ring_forward_launch(b, n, xyz, m, xyz2, result, result_i, result2, result2_i, nullptr, workspace,
+                                      (cudaStream_t)stream);
+    return nn_forward_launch(b, n, xyz, m, xyz2, result, result_i, result2, result2_i, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int hp_chamfer_forward(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1,
@@ -531,13 +566,15 @@ extern "C" int hp_chamfer_forward(int b, int n, const float *xyz1, int m, const 
     }
     HP_REQUIRE(n > 0 && m > 0, "hp_chamfer_forward: one point set is empty (n=%d m=%d)", n, m);
     HP_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, "hp_chamfer_forward: null pointer");
-    HP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0,
-               "hp_chamfer_forward: workspace null or not 8-byte aligned");
+    HP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+               "hp_chamfer_forward: workspace null or not 16-byte aligned");
     if (workspace_bytes < hp_chamfer_workspace_bytes(b, n, m)) {
         set_error("hp_chamfer_forward: workspace %zu < required %zu bytes", workspace_bytes,
                   hp_chamfer_workspace_bytes(b, n, m));
         return HP_ERR_WORKSPACE;
     }
+    if (use_ring())
+        return nn_ring_forward_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, workspace, (cudaStream_t)stream);
     return nn_forward_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, workspace, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,418 @@
+// chamfer_ring.cu -- nearest-neighbour forward (values AND indices, both directions) in "warp ring" form.
+//
+// The first-generation kernel (chamfer.cu: nn_fwd_kernel) evaluates every ORDERED (query, candidate) pair:
+// 2*B*N*M distance evaluations.  d(a_i, b_j) is bit-symmetric under the library's one association
+// fma(dz,dz,fma(dx,dx,dy*dy)), so here every UNORDERED pair is evaluated once and feeds both directions:
+//
+//   * a lane keeps 8 points of set 1 ("rows") and 4 points of set 2 ("columns") in registers; 32 times per
+//     round the 8x4 distances are evaluated (FADD2/FMUL2/FFMA2, 96 packed ops), folded into the lane's 8 row
+//     minima and into the 4 column minima that TRAVEL WITH the column points, and the column registers move
+//     one lane up the warp (SHFL).  No shared-memory traffic in the hot loop; the FMA pipe is the bound.
+//   * indices: per row / per column only the ROTATION in which the minimum last improved is tracked
+//     (FSETP+SEL per row per rotation, issued in the shadow of the FMA pipe); afterwards the 4 columns
+//     (8 rows) met in that rotation are re-evaluated with bit-identical arithmetic and the lowest index with
+//     d == min is taken.
+//   * ties: the reference keeps the LOWEST index among equal distances (nndistance.cu:32-64,117-125).  A lane
+//     meets column groups in ascending index order except for ONE wrap (groups 31-L+t mod 32), so a plain
+//     "strict <" would favour the pre-wrap group.  At the wrap the running minimum is bumped by one ulp (as
+//     integer bits: d >= 0), which makes "strict <" behave like "<=" for the post-wrap (lower-index) groups
+//     only; the bump is removed afterwards if nothing replaced it.  Same for columns, which wrap when they
+//     pass from lane 31 to lane 0.  Result: bit-exact distances and reference-exact indices.
+//   * a CTA (4 warps) owns 1024 rows x R*128 columns of one cloud; per-CTA (distance,index) candidates are
+//     written as 64-bit keys (float bits << 32 | index: integer order == (distance, index) order) and folded
+//     by nn_ring_unpack_kernel, which also reduces the fused loss in a fixed order.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace hp {
+
+constexpr int RF_RQ = 8, RF_RC = 4;
+constexpr int RF_WARPS = 4;
+constexpr int RF_WROWS = 32 * RF_RQ;            // 256 rows per warp
+constexpr int RF_ROWS = RF_WARPS * RF_WROWS;    // 1024 rows per CTA
+constexpr int RF_COLS = 32 * RF_RC;             // 128 columns per round
+constexpr float RF_PAD_ROW = 1.0e18f;           // padding points: finite, farther than any real pair
+constexpr float RF_PAD_COL = -1.0e18f;
+constexpr int RF_MERGE_THREADS = 1024;
+
+typedef unsigned long long u64;
+
+struct RingNNArgs {
+    const float *set1, *set2;  // [b,n,3], [b,m,3]
+    int b, n, m;
+    int rowchunks, colchunks, R;
+    u64 *rowkey;               // [b][n]  ~key of the best candidate so far (0 = none): zero on entry, zero on exit
+    u64 *colkey;               // [b][m]
+    float *dist1, *dist2;
+    int *idx1, *idx2;
+    float *loss;               // nullptr: no fused loss
+    float *losspart;           // [2b] per-(cloud,direction) sums
+    float *grouppart;          // [ngroups]
+    unsigned int *counters;    // [1 + ngroups] tickets; zero on entry, zero on exit
+};
+
+__device__ __forceinline__ float bump_up(float v) { return __int_as_float(__float_as_int(v) + 1); }
+__device__ __forceinline__ float bump_down(float v) { return __int_as_float(__float_as_int(v) - 1); }
+
+// stage `cnt` points (AoS) from global to shared: bulk-TMA for the 16-byte aligned body, plain loads for the rest,
+// pad up to `total` points with `pad`.
+__device__ __forceinline__ void rf_stage_points(float *dst, const float *src, int cnt, int total, float pad, uint64_t *mbar,
+                                                uint32_t &phase, int tid, int nthreads) {
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    const uint32_t bulk_bytes = tma_ok ? ((uint32_t)(cnt * 12) & ~15u) : 0u;
+    if (bulk_bytes && tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(mbar, bulk_bytes);
+        bulk_g2s(dst, src, bulk_bytes, mbar);
+    }
+    for (int i = (int)(bulk_bytes / 4) + tid; i < cnt * 3; i += nthreads) dst[i] = __ldg(src + i);
+    for (int i = cnt * 3 + tid; i < total * 3; i += nthreads) dst[i] = pad;
+    if (bulk_bytes) {
+        mbar_wait(mbar, phase);
+        phase ^= 1;
+    }
+}
+
+// A column group = 4 consecutive columns stored as 12 floats [x0 x1 y0 y1 | z0 z1 x2 x3 | y2 y3 z2 z3]: three LDS.128
+// deliver the six fp32x2 operands of the packed distance evaluation in aligned register pairs, no moves.
+struct RFGroup {
+    f32x2 x01, y01, z01, x23, y23, z23;
+};
+__device__ __forceinline__ RFGroup rf_load_group(const float *cols_p, int g) {
+    const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(cols_p + g * 12);
+    const ulonglong2 a = p[0], b = p[1], c = p[2];
+    RFGroup r;
+    r.x01 = a.x, r.y01 = a.y, r.z01 = b.x, r.x23 = b.y, r.y23 = c.x, r.z23 = c.y;
+    return r;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const RingNNArgs a) {
+    __shared__ __align__(128) float rows_s[RF_ROWS * 3];
+    __shared__ __align__(128) float cols_raw[RF_COLS * 3];
+    __shared__ __align__(128) float cols_p[RF_COLS * 3];
+    __shared__ __align__(16) float wmn_s[RF_WARPS][RF_COLS];  // per warp: running column minima ...
+    __shared__ __align__(16) int wrot_s[RF_WARPS][RF_COLS];   // ... and the rotation that last improved them
+    __shared__ __align__(8) u64 colkey[RF_COLS];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int bid = blockIdx.x;
+    const int cc = bid % a.colchunks;
+    bid /= a.colchunks;
+    const int rc = bid % a.rowchunks;
+    const int cloud = bid / a.rowchunks;
+    const int n = a.n, m = a.m;
+    const float *__restrict__ A = a.set1 + (size_t)cloud * n * 3;
+    const float *__restrict__ Bp = a.set2 + (size_t)cloud * m * 3;
+    const int row0 = rc * RF_ROWS;                       // first row of this CTA
+    const int nrows = min(RF_ROWS, n - row0);            // real rows of this CTA (>= 1)
+
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    rf_stage_points(rows_s, A + (size_t)row0 * 3, nrows, RF_ROWS, RF_PAD_ROW, &mbar, phase, tid, RF_WARPS * 32);
+    __syncthreads();
+
+    const int wrow0 = warp * RF_WROWS;                   // first (CTA-local) row of this warp
+    const bool warp_active = wrow0 < nrows;              // warp-uniform
+    const int lrow0 = wrow0 + lane * RF_RQ;              // first (CTA-local) row of this lane
+    float qx[RF_RQ], qy[RF_RQ], qz[RF_RQ];
+    {
+        const float4 *rp = reinterpret_cast<const float4 *>(rows_s + lrow0 * 3);  // 24 floats, 16-byte aligned
+        float v[24];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const float4 t4 = rp[i];
+            v[4 * i + 0] = t4.x, v[4 * i + 1] = t4.y, v[4 * i + 2] = t4.z, v[4 * i + 3] = t4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < RF_RQ; ++j) qx[j] = v[3 * j], qy[j] = v[3 * j + 1], qz[j] = v[3 * j + 2];
+    }
+    float *wmn = wmn_s[warp];
+    int *wrot = wrot_s[warp];
+
+    for (int r = 0; r < a.R; ++r) {
+        const int cbase = (cc * a.R + r) * RF_COLS;      // first column of this round
+        if (cbase >= m) break;                           // uniform
+        const int ncols = min(RF_COLS, m - cbase);
+        __syncthreads();                                 // previous round's shared state consumed
+        rf_stage_points(cols_raw, Bp + (size_t)cbase * 3, ncols, RF_COLS, RF_PAD_COL, &mbar, phase, tid, RF_WARPS * 32);
+        __syncthreads();
+        {   // permute column tid into the packed group layout; reset the merge keys and this warp's column state
+            const int g = tid >> 2, k = tid & 3;
+            float *dst = cols_p + g * 12 + ((k & 2) ? 6 : 0) + (k & 1);
+            dst[0] = cols_raw[tid * 3 + 0], dst[2] = cols_raw[tid * 3 + 1], dst[4] = cols_raw[tid * 3 + 2];
+            colkey[tid] = ~0ull;                         // RF_COLS == blockDim.x
+#pragma unroll
+            for (int i = 0; i < RF_RC; ++i) wmn[lane * RF_RC + i] = __int_as_float(0x7f800000), wrot[lane * RF_RC + i] = 0;
+        }
+        __syncthreads();
+        if (warp_active) {
+            // lane L meets column group (31 - L + t) mod 32 at rotation t: ascending with one wrap (at t = L+1);
+            // a group's running minimum is handed from lane to lane through shared memory: it visits lanes
+            // (31 - g + t) mod 32, i.e. ascending rows, wrapping to the lowest rows when lane 0 picks it up.
+            float best[RF_RQ];
+            int rot[RF_RQ];
+#pragma unroll
+            for (int j = 0; j < RF_RQ; ++j) best[j] = __int_as_float(0x7f800000), rot[j] = 0;
+            int g = 31 - lane;
+            RFGroup cur = rf_load_group(cols_p, g);
+#pragma unroll 2
+            for (int t = 0; t < 32; ++t) {
+                const int gn = (g + 1) & 31;
+                const RFGroup nxt = rf_load_group(cols_p, gn);  // prefetch the next rotation's columns
+                float4 mnv = *reinterpret_cast<const float4 *>(wmn + g * RF_RC);
+                int4 rtv = *reinterpret_cast<const int4 *>(wrot + g * RF_RC);
+                {   // at t == lane+1 this lane's column groups wrap to index 0: later groups must win ties (+1 ulp)
+                    const int wrapped = (t == lane + 1) ? 1 : 0;
+#pragma unroll
+                    for (int j = 0; j < RF_RQ; ++j) best[j] = __int_as_float(__float_as_int(best[j]) + wrapped);
+                }
+                float loc[RF_RC];
+#pragma unroll
+                for (int j = 0; j < RF_RQ; j += 2) {
+                    float d[2][4];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const f32x2 px = pack2(qx[j + u], qx[j + u]), py = pack2(qy[j + u], qy[j + u]), pz = pack2(qz[j + u], qz[j + u]);
+                        unpack2(sqdist_exact2(px, py, pz, cur.x01, cur.y01, cur.z01), d[u][0], d[u][1]);
+                        unpack2(sqdist_exact2(px, py, pz, cur.x23, cur.y23, cur.z23), d[u][2], d[u][3]);
+                        const float old = best[j + u];
+                        float nb = min3(old, d[u][0], d[u][1]);
+                        nb = min3(nb, d[u][2], d[u][3]);
+                        best[j + u] = nb;
+                        rot[j + u] = (nb < old) ? t : rot[j + u];
+                    }
+#pragma unroll
+                    for (int i = 0; i < RF_RC; ++i) loc[i] = (j == 0) ? fminf(d[0][i], d[1][i]) : min3(loc[i], d[0][i], d[1][i]);
+                }
+                {   // lane 0 (t >= 1) picks up columns last seen by lane 31: they wrap to the lowest rows (+1 ulp)
+                    const int wrapped = (lane == 0 && t != 0) ? 1 : 0;
+                    mnv.x = __int_as_float(__float_as_int(mnv.x) + wrapped), mnv.y = __int_as_float(__float_as_int(mnv.y) + wrapped);
+                    mnv.z = __int_as_float(__float_as_int(mnv.z) + wrapped), mnv.w = __int_as_float(__float_as_int(mnv.w) + wrapped);
+                }
+                rtv.x = (loc[0] < mnv.x) ? t : rtv.x, rtv.y = (loc[1] < mnv.y) ? t : rtv.y;
+                rtv.z = (loc[2] < mnv.z) ? t : rtv.z, rtv.w = (loc[3] < mnv.w) ? t : rtv.w;
+                mnv.x = fminf(mnv.x, loc[0]), mnv.y = fminf(mnv.y, loc[1]), mnv.z = fminf(mnv.z, loc[2]), mnv.w = fminf(mnv.w, loc[3]);
+                *reinterpret_cast<float4 *>(wmn + g * RF_RC) = mnv;
+                *reinterpret_cast<int4 *>(wrot + g * RF_RC) = rtv;
+                __syncwarp();
+                cur = nxt;
+                g = gn;
+            }
+
+            // ---- rows: exact value, then the lowest column index of the winning group with d == value ----
+#pragma unroll
+            for (int j = 0; j < RF_RQ; ++j) {
+                float bv = best[j];
+                if (lane <= 30 && rot[j] <= lane) bv = bump_down(bv);  // bumped at t = lane+1 and never replaced
+                const int gw = (31 - lane + rot[j]) & 31;
+                const float4 *cp = reinterpret_cast<const float4 *>(cols_p + gw * 12);
+                const float4 v0 = cp[0], v1 = cp[1], v2 = cp[2];  // x0 x1 y0 y1 | z0 z1 x2 x3 | y2 y3 z2 z3
+                const float d0 = sqdist_exact(qx[j], qy[j], qz[j], v0.x, v0.z, v1.x);
+                const float d1 = sqdist_exact(qx[j], qy[j], qz[j], v0.y, v0.w, v1.y);
+                const float d2 = sqdist_exact(qx[j], qy[j], qz[j], v1.z, v2.x, v2.z);
+                const int k = (d0 == bv) ? 0 : (d1 == bv) ? 1 : (d2 == bv) ? 2 : 3;
+                const int row = row0 + lrow0 + j;
+                if (row < n) {
+                    const u64 key = ((u64)__float_as_uint(bv) << 32) | (unsigned)(cbase + gw * RF_RC + k);
+                    atomicMax(a.rowkey + (size_t)cloud * n + row, ~key);
+                }
+            }
+            // ---- columns: lane L finalises group L ----
+            {
+                const float4 *cp = reinterpret_cast<const float4 *>(cols_p + lane * 12);
+                const float4 v0 = cp[0], v1 = cp[1], v2 = cp[2];
+                const float cxs[RF_RC] = {v0.x, v0.y, v1.z, v1.w}, cys[RF_RC] = {v0.z, v0.w, v2.x, v2.y},
+                            czs[RF_RC] = {v1.x, v1.y, v2.z, v2.w};
+                const float4 mnf = *reinterpret_cast<const float4 *>(wmn + lane * RF_RC);
+                const int4 rtf = *reinterpret_cast<const int4 *>(wrot + lane * RF_RC);
+                const float mns[RF_RC] = {mnf.x, mnf.y, mnf.z, mnf.w};
+                const int rts[RF_RC] = {rtf.x, rtf.y, rtf.z, rtf.w};
+#pragma unroll
+                for (int i = 0; i < RF_RC; ++i) {
+                    const int lc = lane * RF_RC + i;  // round-local column
+                    if (lc < ncols) {
+                        float cv = mns[i];
+                        if (lane <= 30 && rts[i] <= lane) cv = bump_down(cv);  // bumped when lane 0 picked it up, never replaced
+                        const int vl = (31 - lane + rts[i]) & 31;              // lane whose rows produced the minimum
+                        const float *rp = rows_s + (wrow0 + vl * RF_RQ) * 3;
+                        int k = RF_RQ - 1;
+#pragma unroll
+                        for (int q = RF_RQ - 2; q >= 0; --q) {
+                            const float dq = sqdist_exact(rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], cxs[i], cys[i], czs[i]);
+                            k = (dq == cv) ? q : k;
+                        }
+                        const u64 key = ((u64)__float_as_uint(cv) << 32) | (unsigned)(row0 + wrow0 + vl * RF_RQ + k);
+                        atomicMin(&colkey[lc], key);
+                    }
+                }
+            }
+        }  // warp_active
+        __syncthreads();
+        if (tid < ncols) atomicMax(a.colkey + (size_t)cloud * m + cbase + tid, ~colkey[tid]);
+    }
+}
+
+// key -> (distance, index); restores the zero state of the key arrays; fixed-order loss.
+// One block per (cloud, direction).  The loss is folded through a two-level ticket (groups of RF_GROUP blocks, then
+// groups) so that no single address sees more than RF_GROUP / (blocks / RF_GROUP) serialised atomics.
+constexpr int RF_GROUP = 32;
+
+__device__ __forceinline__ float rf_block_sum(float v, float *warp_part, int tid) {
+    v = warp_sum(v);
+    __syncthreads();  // warp_part reusable
+    if ((tid & 31) == 0) warp_part[tid >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < RF_MERGE_THREADS / 32; ++i) s += warp_part[i];
+    }
+    return s;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const RingNNArgs a) {
+    __shared__ float warp_part[RF_MERGE_THREADS / 32];
+    __shared__ int flag;
+    const int tid = threadIdx.x;
+    const int cloud = blockIdx.x >> 1;
+    const bool dir2 = blockIdx.x & 1;
+    const int cnt = dir2 ? a.m : a.n;
+    u64 *src = (dir2 ? a.colkey : a.rowkey) + (size_t)cloud * cnt;
+    float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
+    int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
+    // Phase 1 only READS the keys: the device-scope fences of the loss tickets below then have no stores of this SM to
+    // drain (a fence issued after the 3 stores per element costs ~10 us).  Phase 2 (unpack_store) writes the outputs.
+    auto unpack_store = [&]() {
+        for (int e = tid; e < cnt; e += RF_MERGE_THREADS) {
+            const u64 key = ~__ldcg(src + e);
+            src[e] = 0ull;
+            dist[e] = __uint_as_float((unsigned)(key >> 32));
+            idx[e] = (int)(unsigned)(key & 0xffffffffu);
+        }
+    };
+    if (a.loss == nullptr) {
+        unpack_store();
+        return;
+    }
+    float v = 0.f;
+    for (int e = tid; e < cnt; e += RF_MERGE_THREADS) v += __uint_as_float((unsigned)((~__ldcg(src + e)) >> 32));  // fixed order
+    const float s = rf_block_sum(v, warp_part, tid);
+    const int group = blockIdx.x / RF_GROUP, ngroups = (gridDim.x + RF_GROUP - 1) / RF_GROUP;
+    const int gfirst = group * RF_GROUP, gcount = min(RF_GROUP, (int)gridDim.x - gfirst);
+    if (tid == 0) {
+        a.losspart[blockIdx.x] = s;
+        __threadfence();
+        flag = (atomicAdd(a.counters + 1 + group, 1u) == (unsigned)gcount - 1);
+    }
+    __syncthreads();
+    if (flag) {  // block-uniform
+        // last block of its group: fold the group's partials in block order
+        __syncthreads();
+        if (tid < 32) {  // warp 0: one partial per lane (independent loads), summed by lane 0 in block order
+            __threadfence();
+            float p = 0.f;
+            if (tid < gcount) {
+                p = __ldcg(a.losspart + gfirst + tid);
+                a.losspart[gfirst + tid] = 0.f;  // the whole workspace returns to zero (its layout moves with the shape)
+            }
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < RF_GROUP; ++i) {
+                const float pi = __shfl_sync(0xffffffffu, p, i);
+                t += (i < gcount) ? pi : 0.f;
+            }
+            if (tid == 0) {
+                a.grouppart[group] = t;
+                a.counters[1 + group] = 0u;
+                __threadfence();
+                flag = (atomicAdd(a.counters, 1u) == (unsigned)ngroups - 1);
+            }
+        }
+        __syncthreads();
+        if (flag) {
+            // last group: fold the group sums in group order
+            float t = 0.f;
+            for (int i = tid; i < ngroups; i += RF_MERGE_THREADS) t += __ldcg(a.grouppart + i);
+            __threadfence();
+            const float tot = rf_block_sum(t, warp_part, tid);
+            for (int i = tid; i < ngroups; i += RF_MERGE_THREADS) a.grouppart[i] = 0.f;
+            if (tid == 0) {
+                a.loss[0] = tot;
+                a.counters[0] = 0u;
+            }
+        }
+    }
+    unpack_store();
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+// rounds per CTA: 1 unless the grid is many waves deep (then the row staging is amortised over more columns)
+static int rf_rounds_per_cta(int b, int n, int m) {
+    const long long rowchunks = (n + RF_ROWS - 1) / RF_ROWS, rounds = (m + RF_COLS - 1) / RF_COLS;
+    const long long want = (long long)sm_count() * 64;
+    int R = 1;
+    while (R < 8 && (long long)b * rowchunks * ((rounds + 2 * R - 1) / (2 * R)) >= want) R *= 2;
+    return R;
+}
+
+struct RFLayout {
+    int ngroups;
+    size_t off_counters, off_losspart, off_grouppart, off_rowkey, off_colkey, total;
+};
+static RFLayout rf_layout(int b, int n, int m) {
+    RFLayout L;
+    const size_t blocks = (size_t)2 * b;
+    L.ngroups = (int)((blocks + RF_GROUP - 1) / RF_GROUP);
+    L.off_counters = 0;
+    L.off_losspart = (sizeof(unsigned int) * (1 + (size_t)L.ngroups) + 15) & ~(size_t)15;
+    L.off_grouppart = L.off_losspart + blocks * sizeof(float);
+    L.off_rowkey = (L.off_grouppart + (size_t)L.ngroups * sizeof(float) + 15) & ~(size_t)15;
+    L.off_colkey = L.off_rowkey + (size_t)b * n * sizeof(u64);
+    L.total = L.off_colkey + (size_t)b * m * sizeof(u64);
+    return L;
+}
+
+size_t nn_ring_workspace_bytes(int b, int n, int m) {
+    if (b <= 0 || n <= 0 || m <= 0) return 16;
+    return rf_layout(b, n, m).total;
+}
+
+// Inputs must be finite with |coordinate| < 1e15 (padding points sit at +-1e18).  The workspace must be all zero on
+// entry (every byte: the key arrays move with the shape) and is all zero again when the two kernels have run.
+int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
+                           int *idx2, float *loss, void *workspace, cudaStream_t stream) {
+    RingNNArgs a = {};
+    const RFLayout L = rf_layout(b, n, m);
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    a.set1 = xyz1, a.set2 = xyz2, a.b = b, a.n = n, a.m = m;
+    a.R = rf_rounds_per_cta(b, n, m);
+    a.rowchunks = (n + RF_ROWS - 1) / RF_ROWS;
+    a.colchunks = ((m + RF_COLS - 1) / RF_COLS + a.R - 1) / a.R;
+    a.counters = reinterpret_cast<unsigned int *>(ws + L.off_counters);
+    a.losspart = reinterpret_cast<float *>(ws + L.off_losspart);
+    a.grouppart = reinterpret_cast<float *>(ws + L.off_grouppart);
+    a.rowkey = reinterpret_cast<u64 *>(ws + L.off_rowkey);
+    a.colkey = reinterpret_cast<u64 *>(ws + L.off_colkey);
+    a.dist1 = dist1, a.dist2 = dist2, a.idx1 = idx1, a.idx2 = idx2, a.loss = loss;
+    const long long grid = (long long)b * a.rowchunks * a.colchunks;
+    const long long ugrid = (long long)2 * b;
+    HP_REQUIRE(grid <= 0x7fffffffLL && ugrid <= 0x7fffffffLL, "nn ring forward: grid too large (%lld CTAs)", grid);
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("HP_RING_VARIANT");
+        variant = e ? atoi(e) : 0;
+    }
+    if (variant == 1) nn_ring_kernel<5><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    else if (variant == 2) nn_ring_kernel<6><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    else nn_ring_kernel<4><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    HP_LAUNCH_CHECK("nn_ring_kernel");
+    nn_ring_unpack_kernel<<<(unsigned)ugrid, RF_MERGE_THREADS, 0, stream>>>(a);
+    HP_LAUNCH_CHECK("nn_ring_unpack_kernel");
+    return HP_OK;
+}
+
+}  // namespace hp

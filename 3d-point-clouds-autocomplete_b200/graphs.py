@@ -1,0 +1,126 @@
+"""CUDA-graph capture of the hot-path steps.
+
+At the reference's training shapes one Chamfer forward+backward is ~70 us of GPU work, less than the
+Python/launch path that enqueues it, so the eager API is CPU-bound.  These helpers capture a step for
+fixed shapes ONCE into a CUDA graph (torch.cuda.CUDAGraph; our kernels are launched on the capturing
+stream through the C ABI like any other stream) and replay it with one launch:
+
+    step = ChamferStepGraph(batch, n, m, device)          # capture
+    step.xyz1.copy_(a); step.xyz2.copy_(b)                # refresh the static inputs (device tensors)
+    step.replay()                                         # loss, grad_xyz1, grad_xyz2 are refreshed in place
+    step.run_from_host(a_pinned, b_pinned)                # H2D + step + D2H of (loss, grads), one graph
+
+Semantics are those of ``loss = ChamferLoss()(preds=xyz2, gts=xyz1); loss.backward()`` (losses/champfer_loss.py:11-17
+as called by core/epoch_loops.py:25-26) with the kernels of chamfer.py; results are bit-identical to the eager path.
+"""
+from __future__ import annotations
+
+import torch
+
+from .chamfer import chamfer_backward, chamfer_forward
+from .target_network import target_network_backward, target_network_forward, target_network_num_weights
+
+
+def _capture(fn, device, warmup: int = 3):
+    """Warm up on a side stream (allocates workspaces, sets kernel attributes), then capture `fn` once."""
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            fn()
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize(device)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        out = fn()
+    return graph, out, side
+
+
+class ChamferStepGraph:
+    """Chamfer forward (both directions + loss) and backward (both gradients, upstream grad 1) as one graph."""
+
+    def __init__(self, batch: int, n: int, m: int, device, with_host_io: bool = False):
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            self.xyz1 = torch.zeros(batch, n, 3, device=self.device)
+            self.xyz2 = torch.zeros(batch, m, 3, device=self.device)
+            # any finite placeholder works for capture; callers overwrite xyz1 / xyz2 before replaying
+            self.xyz1.uniform_(-0.5, 0.5)
+            self.xyz2.uniform_(-0.5, 0.5)
+            self._one = torch.ones((), device=self.device)
+
+            def step():
+                loss, d1, i1, d2, i2 = chamfer_forward(self.xyz1, self.xyz2)
+                g1, g2 = chamfer_backward(self.xyz1, self.xyz2, i1, i2, self._one)
+                return loss, d1, i1, d2, i2, g1, g2
+
+            self.graph, outs, self._stream = _capture(step, self.device)
+            self.loss, self.dist1, self.idx1, self.dist2, self.idx2, self.grad_xyz1, self.grad_xyz2 = outs
+            self.launches_per_replay = 3  # ring forward + unpack + backward
+
+            self.host_graph = None
+            if with_host_io:
+                self.xyz1_host = torch.empty(batch, n, 3).pin_memory()
+                self.xyz2_host = torch.empty(batch, m, 3).pin_memory()
+                self.loss_host = torch.empty(1).pin_memory()
+                self.grad_xyz1_host = torch.empty(batch, n, 3).pin_memory()
+                self.grad_xyz2_host = torch.empty(batch, m, 3).pin_memory()
+                self.xyz1_host.copy_(self.xyz1)
+                self.xyz2_host.copy_(self.xyz2)
+
+                def host_step():
+                    self.xyz1.copy_(self.xyz1_host, non_blocking=True)
+                    self.xyz2.copy_(self.xyz2_host, non_blocking=True)
+                    loss, _d1, i1, _d2, i2 = chamfer_forward(self.xyz1, self.xyz2)
+                    g1, g2 = chamfer_backward(self.xyz1, self.xyz2, i1, i2, self._one)
+                    self.loss_host.copy_(loss, non_blocking=True)
+                    self.grad_xyz1_host.copy_(g1, non_blocking=True)
+                    self.grad_xyz2_host.copy_(g2, non_blocking=True)
+                    return loss, g1, g2
+
+                self.host_graph, self._host_outs, _ = _capture(host_step, self.device)
+                self.h2d_bytes = (self.xyz1.numel() + self.xyz2.numel()) * 4
+                self.d2h_bytes = (self.xyz1.numel() + self.xyz2.numel()) * 4 + 4
+
+    def replay(self):
+        """Inputs: self.xyz1 / self.xyz2 (device).  Outputs refreshed in place: loss [1], dist*, idx*, grad_xyz*."""
+        self.graph.replay()
+        return self.loss, self.grad_xyz1, self.grad_xyz2
+
+    def run_from_host(self, xyz1_host: torch.Tensor = None, xyz2_host: torch.Tensor = None):
+        """Pinned-host inputs -> (loss_host, grad_xyz1_host, grad_xyz2_host) pinned-host outputs.  The copies are
+        nodes of the graph; call torch.cuda.synchronize() (or record an event) before reading the outputs."""
+        if self.host_graph is None:
+            raise RuntimeError("construct ChamferStepGraph(with_host_io=True) to use run_from_host")
+        if xyz1_host is not None and xyz1_host is not self.xyz1_host:
+            self.xyz1_host.copy_(xyz1_host)
+        if xyz2_host is not None and xyz2_host is not self.xyz2_host:
+            self.xyz2_host.copy_(xyz2_host)
+        self.host_graph.replay()
+        return self.loss_host, self.grad_xyz1_host, self.grad_xyz2_host
+
+
+class TargetNetworkStepGraph:
+    """Fused TargetNetwork forward + backward w.r.t. the weights for fixed (batch, n) as one graph
+    (the model/full_model.py:67-74 loop and its autograd, per training step).  Static inputs: ``weights``,
+    ``points``, ``grad_out``; outputs refreshed in place: ``out``, ``grad_weights``."""
+
+    def __init__(self, batch: int, n: int, layer_out_channels, use_bias: bool, device, channels_first: bool = True):
+        self.device = torch.device(device)
+        W = target_network_num_weights(layer_out_channels, use_bias)
+        loc = tuple(int(c) for c in layer_out_channels)
+        with torch.cuda.device(self.device):
+            self.weights = torch.randn(batch, W, device=self.device) * 0.1
+            self.points = torch.rand(batch, n, 3, device=self.device) - 0.5
+            self.grad_out = torch.randn((batch, 3, n) if channels_first else (batch, n, 3), device=self.device)
+
+            def step():
+                out = target_network_forward(self.weights, self.points, loc, use_bias, channels_first)
+                gw, _ = target_network_backward(self.weights, self.points, self.grad_out, loc, use_bias, channels_first)
+                return out, gw
+
+            self.graph, (self.out, self.grad_weights), self._stream = _capture(step, self.device)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out, self.grad_weights

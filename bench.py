@@ -5,7 +5,8 @@
 
 Workload (BASELINE.json configs[1], named in `config.workload`): Chamfer nearest-neighbour
 distance forward + backward, B=32, N=M=2048, fp32, synthetic clouds ~ U[-0.5,0.5]^3.
-One "step" = ChamferLoss forward (both directions + loss, one kernel) + backward (one kernel).
+One "step" = Chamfer forward (both directions + loss) + backward (both gradients), captured once as a CUDA
+graph (ChamferStepGraph) and replayed: ring kernel + unpack + backward kernel.
 metric = ordered (query, candidate) point pairs evaluated per second = 2*B*N*M / t_step.
 
 One JSON line on stdout (rank 0).  Keys follow the driver contract; in addition
@@ -15,7 +16,10 @@ One JSON line on stdout (rank 0).  Keys follow the driver contract; in addition
   e2e          : same step through the public Python API with pinned HOST buffers,
                  H2D of both clouds and D2H of loss + both gradients inside the timed region.
 N > 1: Chamfer does not shard ("replicas only") -> every rank runs an independent
-replica of the workload ("scaling": "weak"), no data-path collective.
+replica of the workload ("scaling": "weak"), no data-path collective.  The part of BASELINE.json's metric that
+DOES shard -- the all-pairs MMD/COV/1-NNA evaluation (config C5) -- is measured at the same N and reported in
+`metrics_eval` (strong scaling, rows of the cloud-distance matrices sharded over the ranks, NCCL gathers of the
+per-row / per-column minima only).
 """
 from __future__ import annotations
 
@@ -164,6 +168,84 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _events_timed(torch, fn, steps, warmup, flush, stream, barrier):
+    """CUDA-event time of each of `steps` calls of fn on `stream`; L2 evicted (outside the timed interval) before each."""
+    for _ in range(warmup):
+        fn()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for e0, e1 in evs:
+        flush.fill_(1)  # evict L2 (126 MB); the CPU enqueues the timed work while this runs, so no launch gap is timed
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+    barrier()
+    return [e0.elapsed_time(e1) for e0, e1 in evs]  # ms
+
+
+def _other_paths(torch, hp, dev, fp32_peak, mufu_peak, flush, stream, barrier):
+    """Secondary hot-path rows of SURVEY 8 (TargetNetwork C4, EMD C3, pairwise CD C5 sample): time + roofline fraction."""
+    out = {}
+    LOC = [32, 64, 128, 64]
+    tb, tn = 64, 2048
+    tng = hp.TargetNetworkStepGraph(tb, tn, LOC, True, dev, channels_first=True)
+    g = torch.Generator().manual_seed(5)
+    tng.weights.copy_((torch.randn(tb, 19011, generator=g) * 0.15).to(dev))
+    ms = statistics.mean(_events_timed(torch, tng.replay, 20, 3, flush, stream, barrier))
+    flop = (37440.0 + 74688.0) * tb * tn  # algorithmic: fwd + bwd (the in-kernel forward recompute is not counted)
+    out["target_network_fwd+bwd_B64_N2048"] = {"ms": ms, "algorithmic_tflops": flop / ms / 1e9, "frac_fp32_peak": flop / (ms * 1e-3) / fp32_peak,
+                                               "executed_frac_fp32_peak": (flop + 37440.0 * tb * tn) / (ms * 1e-3) / fp32_peak}
+    eb = 32
+    a = (torch.rand(eb, 2048, 3, generator=g) - 0.5).to(dev)
+    b = (torch.rand(eb, 2048, 3, generator=g) - 0.5).to(dev)
+    ms = statistics.mean(_events_timed(torch, lambda: hp.emd_cost_pairs(a, b), 5, 2, flush, stream, barrier))
+    ex2 = 27.0 * eb * 2048 * 2048
+    out["emd_match_cost_fused_B32_2048x2048"] = {"ms": ms, "algorithmic_tex2_per_s": ex2 / ms / 1e9, "frac_mufu_peak": ex2 / (ms * 1e-3) / mufu_peak}
+    ms = statistics.mean(_events_timed(torch, lambda: hp.match_cost(a, b), 3, 1, flush, stream, barrier))
+    out["emd_approx_match+match_cost_B32_2048x2048"] = {"ms": ms}
+    nr = 128
+    ref = (torch.rand(nr, 2048, 3, generator=g) - 0.5).to(dev)
+    smp = (torch.rand(nr, 2048, 3, generator=g) - 0.5).to(dev)
+    ms = statistics.mean(_events_timed(torch, lambda: hp.pairwise_cd(ref, smp), 3, 1, flush, stream, barrier))
+    pairs = float(nr) * nr * 2048 * 2048
+    out["pairwise_cd_128x128_clouds_2048pts"] = {"ms": ms, "unordered_pairs_per_s": pairs / (ms * 1e-3),
+                                                 "frac_fp32_peak_algorithmic_16flop": 16 * pairs / (ms * 1e-3) / fp32_peak}
+    return out
+
+
+def _metrics_eval(torch, dist, hp, dev, world, rank, barrier, full_emd):
+    """Second half of BASELINE.json's metric: all-pairs MMD/COV/1-NNA evaluation, 1000 generated vs 1000 reference
+    clouds x 2048 points (config C5), rows sharded over the ranks (strong scaling).  CD runs at full size with
+    1-NNA (three 1000x1000 matrices); EMD at full size only with --metrics-emd (~2 min on one GPU), else 192x192."""
+    g = torch.Generator().manual_seed(1234)  # identical inputs on every rank
+    smp = (torch.rand(1000, 2048, 3, generator=g) - 0.5).to(dev)
+    ref = (torch.rand(1000, 2048, 3, generator=g) - 0.5).to(dev)
+    out = {"clouds": "1000 generated vs 1000 reference x 2048 pts", "scaling": "strong", "n_gpus": world}
+
+    def timed(fn):
+        barrier()
+        t0 = time.perf_counter()
+        r = fn()
+        {k: float(v) for k, v in r.items()}  # values are read on the host like core/experiments.py:97 does
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), r
+
+    hp.compute_all_metrics(smp[:64], ref[:64], with_emd=False, one_nn=True)  # warm-up
+    t, r = timed(lambda: hp.compute_all_metrics(smp, ref, with_emd=False, one_nn=True))
+    out["cd_mmd_cov_1nna_s"] = t
+    out["cd_unordered_point_pairs_per_s"] = 3 * 1000.0 * 1000 * 2048 * 2048 / t
+    out["1-NN-CD-acc"] = float(r["1-NN-CD-acc"])
+    ne = 1000 if full_emd else 192
+    hp.compute_all_metrics(smp[:16], ref[:16], with_emd=True, one_nn=False)
+    t, r = timed(lambda: hp.compute_all_metrics(smp[:ne], ref[:ne], with_emd=True, one_nn=False))
+    out[f"cd+emd_mmd_cov_{ne}x{ne}_s"] = t
+    out["emd_cloud_pairs_per_s"] = ne * ne / t
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -184,9 +266,6 @@ def run_ours(args):
     loss_mod = hp.ChamferLoss()
 
     a_h, b_h = _synthetic(torch, rank)
-    a_pin, b_pin = a_h.pin_memory(), b_h.pin_memory()
-    a = a_h.to(dev).requires_grad_(True)
-    b = b_h.to(dev).requires_grad_(True)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
@@ -195,59 +274,46 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step_device():
+    # The step, captured once as a CUDA graph (the repo's public API for launch-bound steps, graphs.py):
+    # forward (both directions + loss: ring kernel + unpack) and backward (both gradients).
+    step = hp.ChamferStepGraph(B, N, M, dev, with_host_io=True)
+    step.xyz1.copy_(a_h.to(dev))
+    step.xyz2.copy_(b_h.to(dev))
+    step.xyz1_host.copy_(a_h)
+    step.xyz2_host.copy_(b_h)
+
+    # forward-only / backward-only graphs for the per-kernel roofline
+    fwd_in = (step.xyz1, step.xyz2)
+    fwd_graph, fwd_out, _ = hp.graphs._capture(lambda: hp.chamfer_forward(*fwd_in), dev)
+    one = torch.ones((), device=dev)
+    bwd_graph, _bo, _ = hp.graphs._capture(lambda: hp.chamfer_backward(step.xyz1, step.xyz2, fwd_out[2], fwd_out[4], one), dev)
+
+    # eager public API (autograd module), for reference: CPU/launch bound at this size
+    a = a_h.to(dev).requires_grad_(True)
+    b = b_h.to(dev).requires_grad_(True)
+
+    def step_eager():
         a.grad = b.grad = None
         loss = loss_mod(b, a)  # forward(preds, gts)
         loss.backward()
-        return loss
-
-    ga_host = torch.empty(B, N, 3).pin_memory()
-    gb_host = torch.empty(B, M, 3).pin_memory()
-    loss_host = torch.empty(()).pin_memory()
-
-    def step_e2e():
-        x = a_pin.to(dev, non_blocking=True).requires_grad_(True)
-        y = b_pin.to(dev, non_blocking=True).requires_grad_(True)
-        loss = loss_mod(y, x)
-        loss.backward()
-        loss_host.copy_(loss.detach(), non_blocking=True)
-        ga_host.copy_(x.grad, non_blocking=True)
-        gb_host.copy_(y.grad, non_blocking=True)
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
-        for e0, e1 in evs:
-            flush.fill_(1)  # evict L2 (126 MB) -- outside the timed interval
-            e0.record(stream)
-            fn()
-            e1.record(stream)
-        barrier()
-        return [e0.elapsed_time(e1) for e0, e1 in evs]  # ms
-
-    def fwd_only():
-        hp.chamfer_forward(a.detach(), b.detach())
-
-    def bwd_only(state={}):
-        if not state:
-            _l, _d1, i1, _d2, i2 = hp.chamfer_forward(a.detach(), b.detach())
-            state.update(i1=i1, i2=i2, g=torch.ones((), device=dev))
-        hp.chamfer_backward(a.detach(), b.detach(), state["i1"], state["i2"], state["g"])
 
     # --- roofline denominators, measured live on this GPU ---------------------------------
     peak_ffma = native.measure_peak(0, 8192, stream.cuda_stream)
     peak_ffma2 = native.measure_peak(1, 8192, stream.cuda_stream)
-    peak_mix_packed = native.measure_peak(3, 4096, stream.cuda_stream)
-    peak_mix_scalar = native.measure_peak(4, 4096, stream.cuda_stream)
+    peak_mufu = native.measure_peak(2, 8192, stream.cuda_stream)
     fp32_peak = max(peak_ffma, peak_ffma2)
 
     with ClockSampler(local_rank) as clocks:
-        step_ms = timed(step_device, args.steps, args.warmup)
-        fwd_ms = timed(fwd_only, args.steps, 3)
-        bwd_ms = timed(bwd_only, args.steps, 3)
-    e2e_ms = timed(step_e2e, max(10, args.steps // 4), 3)
+        step_ms = _events_timed(torch, step.replay, args.steps, args.warmup, flush, stream, barrier)
+        fwd_ms = _events_timed(torch, fwd_graph.replay, args.steps, 3, flush, stream, barrier)
+        bwd_ms = _events_timed(torch, bwd_graph.replay, args.steps, 3, flush, stream, barrier)
+    e2e_ms = _events_timed(torch, step.run_from_host, max(20, args.steps // 2), 3, flush, stream, barrier)
+    eager_ms = _events_timed(torch, step_eager, max(20, args.steps // 4), 3, flush, stream, barrier)
+    # the graph and the eager module must agree bit for bit
+    step.replay()
+    step_eager()
+    torch.cuda.synchronize(dev)
+    assert torch.equal(step.grad_xyz1, a.grad) and torch.equal(step.grad_xyz2, b.grad), "graph and eager paths differ"
 
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     e2e_total = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
@@ -258,8 +324,16 @@ def run_ours(args):
     value = world * PAIRS_PER_STEP * args.steps / total_s
     e2e_value = world * PAIRS_PER_STEP * len(e2e_ms) / (float(e2e_total.item()) * 1e-3)
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_paths:
+        other = _other_paths(torch, hp, dev, fp32_peak, peak_mufu, flush, stream, barrier)
+    metrics_eval = None
+    if not args.no_metrics_eval:
+        metrics_eval = _metrics_eval(torch, dist, hp, dev, world, rank, barrier, args.metrics_emd)
+
     if rank == 0:
         fwd_avg_s = statistics.mean(fwd_ms) * 1e-3
+        step_avg_s = total_s / args.steps
         achieved = (PAIRS_PER_STEP * FLOP_PER_PAIR) / fwd_avg_s / 1e12
         peaks_file = {}
         try:
@@ -267,14 +341,19 @@ def run_ours(args):
         except Exception:
             pass
         roofline = {
-            "bound": "fp32", "kernel": "nn_fwd_kernel", "achieved": achieved, "peak": fp32_peak / 1e12,
+            "bound": "fp32", "kernel": "nn_ring_kernel (+ nn_ring_unpack_kernel): Chamfer forward, both directions + loss",
+            "achieved": achieved, "peak": fp32_peak / 1e12,
             "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": None,
             "peak_source": "hp_measure_peak: register-resident FFMA/FFMA2 chains on all SMs, measured live in this run "
-                           "(MEASURED_PEAKS.json has no FP32 entry); nominal 148*128*2*1.965 GHz = 74.4",
+                           "(MEASURED_PEAKS.json has no FP32 entry; K=3 keeps the path off the tensor cores); "
+                           "nominal 148*128*2*1.965 GHz = 74.4",
             "algorithmic_flop_per_launch": PAIRS_PER_STEP * FLOP_PER_PAIR,
+            "executed_flop_per_launch": PAIRS_PER_STEP * FLOP_PER_PAIR // 2,
+            "note": "algorithmic = 8 FLOP per ORDERED (query,candidate) pair (SURVEY 8d); the ring kernel evaluates each "
+                    "unordered pair once for both directions, so executed FLOP = half",
             "kernel_ms": statistics.mean(fwd_ms), "bwd_kernel_ms": statistics.mean(bwd_ms),
-            "peak_ffma_tflops": peak_ffma / 1e12, "peak_ffma2_tflops": peak_ffma2 / 1e12,
-            "inner_loop_mix_packed_tflops": peak_mix_packed / 1e12, "inner_loop_mix_scalar_tflops": peak_mix_scalar / 1e12,
+            "fwd+bwd_frac": (PAIRS_PER_STEP * FLOP_PER_PAIR) / step_avg_s / fp32_peak,
+            "peak_ffma_tflops": peak_ffma / 1e12, "peak_ffma2_tflops": peak_ffma2 / 1e12, "peak_mufu_tex2": peak_mufu / 1e12,
             "hbm_peak_gbs_measured": peaks_file.get("hbm_gbs"),
         }
         cpu = None
@@ -286,13 +365,19 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_s * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": _config(),
+            "dtype": "f32", "data": "synthetic",
+            "config": _config({"launch": "step captured once as a CUDA graph (ChamferStepGraph), one replay per step"}),
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (B * N * 3 + B * M * 3) * 4,
-                    "d2h_bytes_per_step": (B * N * 3 + B * M * 3) * 4 + 4, "ms_per_step": statistics.mean(e2e_ms)},
-            "gpu_launches": 2 * args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": step.d2h_bytes,
+                    "ms_per_step": statistics.mean(e2e_ms),
+                    "api": "ChamferStepGraph.run_from_host: pinned host clouds -> H2D -> fwd+bwd -> D2H of loss and both gradients"},
+            "eager_api": {"ms_per_step": statistics.mean(eager_ms), "value": PAIRS_PER_STEP / (statistics.mean(eager_ms) * 1e-3),
+                          "note": "ChamferLoss()(preds, gts); loss.backward() through torch autograd, no graph: CPU launch path bound"},
+            "gpu_launches": 3 * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "other_paths": other,
+            "metrics_eval": metrics_eval,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -306,6 +391,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-paths", action="store_true", help="skip the TargetNetwork / EMD / pairwise-CD side measurements")
+    ap.add_argument("--no-metrics-eval", action="store_true", help="skip the sharded compute_all_metrics evaluation (config C5)")
+    ap.add_argument("--metrics-emd", action="store_true", help="run the C5 EMD matrices at full size (about 2 min on one GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

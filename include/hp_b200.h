@@ -67,6 +67,14 @@ HP_API const char *hp_last_error_message(void);
 HP_API int hp_nndistance(int b, int n, const float *xyz, int m, const float *xyz2, float *result,
                   int *result_i, float *result2, int *result2_i, void *stream);
 
+/* hp_nndistance with a caller-provided workspace (hp_chamfer_workspace_bytes(b,n,m) bytes, 16-byte aligned,
+ * zero-filled once when allocated; the kernels restore that state).  Runs the "warp ring" kernels, which
+ * evaluate every UNORDERED point pair once for both directions (d is bit-symmetric) -- about twice as fast as
+ * hp_nndistance, identical results.  Coordinates must be finite with |x| < 1e15. */
+HP_API int hp_nndistance_ws(int b, int n, const float *xyz, int m, const float *xyz2, float *result,
+                     int *result_i, float *result2, int *result2_i, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
 /* Replaces `void nndistancegrad(int b,int n,const float*xyz1,int m,const float*xyz2,
  * const float*grad_dist1,const int*idx1,const float*grad_dist2,const int*idx2,
  * float*grad_xyz1,float*grad_xyz2,cudaStream_t)`  (structural_loss.cpp:15,
@@ -84,7 +92,7 @@ HP_API int hp_nndistancegrad(int b, int n, const float *xyz1, int m, const float
 /* Fused ChamferLoss forward (losses/champfer_loss.py:11-17 semantics, direct-form distances):
  * hp_nndistance plus loss[0] = sum(result) + sum(result2), reduced deterministically inside
  * the same launch.  `workspace` must hold hp_chamfer_workspace_bytes(b,n,m) bytes, be
- * 8-byte aligned and ZERO-FILLED once when allocated (the kernel restores that state, so it
+ * 16-byte aligned and ZERO-FILLED once when allocated (the kernel restores that state, so it
  * can be reused across calls on one stream). */
 HP_API size_t hp_chamfer_workspace_bytes(int b, int n, int m);
 HP_API int hp_chamfer_forward(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1,
@@ -128,6 +136,38 @@ HP_API int hp_emd_cost_pairs(int pairs, int n, int m, const float *first, const 
                       size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * (c) TargetNetwork: the per-sample MLP whose weights the hypernetwork emits
+ *     (model/target_network.py:5-45, driven by the loop at model/full_model.py:67-74).
+ * ---------------------------------------------------------------------------------- */
+/* Layer widths: dims_host[0..n_layers] (HOST array) = {3, layer_out_channels..., 3}.  Per sample the flat
+ * weight vector holds, for each layer, W[out][in] row-major then (use_bias) b[out]
+ * (target_network.py:40-45); hp_target_network_num_weights() is its length (19011 for 32,64,128,64). */
+HP_API long long hp_target_network_num_weights(int n_layers, const int *dims_host, int use_bias);
+
+/* out[s] = TargetNetwork(weights[s]).forward(points[s]) for s in [0,b): ReLU after every layer but the
+ * last (target_network.py:31-38).  ONE launch for the whole batch, no activation goes to HBM.
+ *   weights [b, W];  points [b, n, 3] with points_batch_stride = 3n floats, or one shared cloud
+ *   [n, 3] with points_batch_stride = 0;  out [b, n, 3] (channels_first = 0) or [b, 3, n]
+ *   (channels_first = 1: the layout FullModel.forward writes, full_model.py:68,74).
+ * Widths 3,32,64,128,64,3 run the tuned kernel; any other widths a generic one (HP_ERR_UNSUPPORTED if a
+ * layer is too wide for shared memory). */
+HP_API int hp_target_network_forward(int b, int n, int n_layers, const int *dims_host, int use_bias,
+                              const float *weights, const float *points, long long points_batch_stride,
+                              float *out, int channels_first, void *stream);
+
+/* Gradient of sum(out * grad_out) w.r.t. the flat weights (what autograd hands the hypernetwork) and,
+ * when grad_points != NULL (needs per-sample points), w.r.t. the input points.  The forward is recomputed
+ * tile by tile inside the kernel; nothing was stashed.  Deterministic (fixed-order reductions, no float
+ * atomics).  grad_out has the layout of `out` (channels_first).  grad_weights [b, W] is fully overwritten.
+ * `workspace`: hp_target_network_backward_workspace_bytes() bytes, 16-byte aligned, contents irrelevant
+ * (per-CTA partial gradients and arrival counters; the call initialises what it needs on `stream`). */
+HP_API size_t hp_target_network_backward_workspace_bytes(int b, int n, int n_layers, const int *dims_host, int use_bias);
+HP_API int hp_target_network_backward(int b, int n, int n_layers, const int *dims_host, int use_bias,
+                               const float *weights, const float *points, long long points_batch_stride,
+                               const float *grad_out, int channels_first, float *grad_weights,
+                               float *grad_points, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * (d) Set-vs-set metrics (utils/metrics.py:121-158): one row block of the cloud-distance
  *     matrix per call; rows are what gets sharded across GPUs.
  * ---------------------------------------------------------------------------------- */
@@ -141,7 +181,8 @@ HP_API int hp_pairwise_cd(int na, int nb, int n, int m, const float *first, cons
 /* ------------------------------------------------------------------------------------
  * Measurement helpers (used by bench.py for the roofline denominators; not on the path)
  * ---------------------------------------------------------------------------------- */
-/* Runs a register-resident FFMA (kind 0), packed FFMA2 (kind 1) or MUFU.EX2 (kind 2) chain
+/* Runs a register-resident FFMA (kind 0), packed FFMA2 (kind 1) or MUFU.EX2 (kind 2) chain, or the
+ * Chamfer inner-loop instruction mix (kinds 3-5, see csrc/api.cu),
  * on every SM and returns the achieved rate in *rate (FLOP/s for kinds 0-1, ex2/s for kind 2),
  * timed with CUDA events on `stream` (synchronises). */
 HP_API int hp_measure_peak(int kind, int iters, double *rate_host, void *stream);

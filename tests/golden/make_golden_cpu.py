@@ -97,5 +97,18 @@ k = ref_metrics.knn(Mxx, Mxy, Myy, 1, sqrt=False)
 out.update(knn_Mxx=Mxx.numpy(), knn_Mxy=Mxy.numpy(), knn_Myy=Myy.numpy(),
            **{"knn_" + kk: np.float32(float(vv)) for kk, vv in k.items()})
 
+# 5. target-network input sampling (utils/points.py:16-36) from the global torch CPU RNG, seed 1856
+#    (settings/config_3depn_airplane.json.sample:105), three consecutive draws per epoch like the
+#    per-sample loop of full_model.py:70-74
+from utils.points import generate_points as ref_generate_points  # noqa: E402
+
+pcfg = {"target_network_input": {"normalization": {"enable": True, "type": "progressive", "epoch": 100}}}
+for ep in (1, 37, 100, 250):
+    torch.manual_seed(1856)
+    out[f"gp_ep{ep}"] = torch.stack([ref_generate_points(pcfg, ep, (96, 3)) for _ in range(3)]).numpy()
+pcfg_off = {"target_network_input": {"normalization": {"enable": False, "type": "progressive", "epoch": 100}}}
+torch.manual_seed(1856)
+out["gp_plain"] = torch.stack([ref_generate_points(pcfg_off, 5, (96, 3)) for _ in range(2)]).numpy()
+
 np.savez_compressed(os.path.join(HERE, "cpu_reference.npz"), **out)
 print("wrote", os.path.join(HERE, "cpu_reference.npz"), {k: v.shape for k, v in out.items()})

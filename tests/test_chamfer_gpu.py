@@ -209,3 +209,58 @@ def test_large_cloud_fallback_backward(hp, oracle):
     oga, ogb = oracle.nn_distance_grad(a.numpy(), c.numpy(), oi1, oi2, g1.cpu().numpy(), g2.cpu().numpy())
     np.testing.assert_allclose(ga.cpu().numpy(), oga, rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(gb.cpu().numpy(), ogb, rtol=1e-4, atol=1e-6)
+
+
+def _old_kernel_nndistance(hp, ad, cd):
+    """hp_nndistance (no workspace) always runs the first-generation ordered-pair kernel."""
+    b, n, m = ad.size(0), ad.size(1), cd.size(1)
+    d1 = torch.empty(b, n, device=DEV)
+    d2 = torch.empty(b, m, device=DEV)
+    i1 = torch.empty(b, n, dtype=torch.int32, device=DEV)
+    i2 = torch.empty(b, m, dtype=torch.int32, device=DEV)
+    lib = hp._native.load()
+    rc = lib.hp_nndistance(b, n, ad.data_ptr(), m, cd.data_ptr(), d1.data_ptr(), i1.data_ptr(), d2.data_ptr(), i2.data_ptr(),
+                           torch.cuda.current_stream().cuda_stream)
+    hp._native.check(rc, "hp_nndistance")
+    return d1, i1, d2, i2
+
+
+@pytest.mark.parametrize("b,n,m", [(2, 1500, 700), (1, 4097, 130), (3, 256, 2048), (2, 1025, 129), (4, 33, 1), (1, 3000, 3000)])
+@pytest.mark.parametrize("kind", ["ties", "dupes", "uniform"])
+def test_ring_kernel_tie_rule_matches_ordered_kernel_and_oracle(hp, oracle, b, n, m, kind):
+    """The warp-ring kernel meets candidates in a rotated order; its one-ulp bump must reproduce the reference's
+    'lowest index among equal distances' exactly.  Tie-heavy inputs: a 3x3x3 lattice (hundreds of equal minima
+    per row, in every rotation group) and clouds made of a few points repeated many times."""
+    g = torch.Generator().manual_seed(n * 7 + m)
+    if kind == "ties":
+        a = torch.randint(0, 3, (b, n, 3), generator=g).float() / 2
+        c = torch.randint(0, 3, (b, m, 3), generator=g).float() / 2
+    elif kind == "dupes":
+        base = torch.rand(b, 5, 3, generator=g) - 0.5
+        a = torch.gather(base, 1, torch.randint(0, 5, (b, n, 1), generator=g).expand(-1, -1, 3))
+        c = torch.gather(base, 1, torch.randint(0, 5, (b, m, 1), generator=g).expand(-1, -1, 3))
+    else:
+        a, c = torch.rand(b, n, 3, generator=g) - 0.5, torch.rand(b, m, 3, generator=g) - 0.5
+    ad, cd = a.contiguous().to(DEV), c.contiguous().to(DEV)
+    d1, i1, d2, i2 = hp.NNDistance(ad, cd)          # ring kernels (hp_nndistance_ws)
+    e1, j1, e2, j2 = _old_kernel_nndistance(hp, ad, cd)
+    assert torch.equal(i1, j1) and torch.equal(i2, j2), "ring and ordered-pair kernels disagree on indices"
+    assert torch.equal(d1, e1) and torch.equal(d2, e2)
+    od1, oi1, od2, oi2 = oracle.nn_distance(a.numpy(), c.numpy())
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+
+
+def test_ring_kernel_unaligned_views(hp, oracle):
+    """Cloud base addresses that are not 16-byte aligned (bulk-TMA falls back to plain loads)."""
+    g = torch.Generator().manual_seed(3)
+    big_a = torch.rand(2 * 777 * 3 + 1, generator=g) - 0.5
+    big_c = torch.rand(2 * 301 * 3 + 3, generator=g) - 0.5
+    a = big_a[1:].view(2, 777, 3)
+    c = big_c[3:].view(2, 301, 3)
+    ad = big_a.to(DEV)[1:].view(2, 777, 3)
+    cd = big_c.to(DEV)[3:].view(2, 301, 3)
+    d1, i1, d2, i2 = hp.NNDistance(ad, cd)
+    od1, oi1, od2, oi2 = oracle.nn_distance(a.contiguous().numpy(), c.contiguous().numpy())
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)

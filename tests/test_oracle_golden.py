@@ -120,3 +120,21 @@ def test_emd_oracle_properties(oracle):
     a2[0, 7, 1] += eps
     c2 = oracle.match_cost_from_match(a2, b, match)
     assert (c2[0] - cost[0]) / eps == pytest.approx(g1[0, 7, 1], rel=5e-2, abs=5e-3)
+
+
+def test_generate_points_batched_matches_reference_sampler(golden_cpu):
+    """Host-side input sampling (utils/points.py:8-36): same global-RNG draw order, bit-identical clouds."""
+    import importlib
+
+    import torch
+
+    tn = importlib.import_module("3d-point-clouds-autocomplete_b200.target_network")
+    cfg = {"target_network_input": {"normalization": {"enable": True, "type": "progressive", "epoch": 100}}}
+    for ep in (1, 37, 100, 250):
+        torch.manual_seed(1856)
+        got = tn.generate_points_batched(cfg, ep, 3, (96, 3), pin=False)
+        assert np.array_equal(got.numpy(), golden_cpu[f"gp_ep{ep}"]), ep
+    cfg["target_network_input"]["normalization"]["enable"] = False
+    torch.manual_seed(1856)
+    got = tn.generate_points_batched(cfg, 5, 2, (96, 3), pin=False)
+    assert np.array_equal(got.numpy(), golden_cpu["gp_plain"])

@@ -1,0 +1,233 @@
+"""GPU parity tests for the fused TargetNetwork kernels, through the C ABI (ctypes -> libhp_b200.so).
+Bars: outputs and weight/point gradients within 1e-5 relative of the oracle (fp32 C forward, float64
+numpy backward, both pinned to the reference's model/target_network.py by tests/golden/cpu_reference.npz)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+FAST = [32, 64, 128, 64]
+
+
+def _rel_err(x, ref):
+    x, ref = np.asarray(x, np.float64), np.asarray(ref, np.float64)
+    return float(np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def _preacts_f64(w, x, loc, use_bias):
+    """float64 pre-activations of every hidden layer: list of [B, N, width]."""
+    w, h = np.asarray(w, np.float64), np.asarray(x, np.float64)
+    dims = [3] + list(loc) + [3]
+    off, pre = 0, []
+    for l in range(len(dims) - 2):
+        i, o = dims[l], dims[l + 1]
+        W = w[:, off:off + i * o].reshape(-1, o, i)
+        off += i * o
+        z = np.einsum("bni,boi->bno", h, W)
+        if use_bias:
+            z = z + w[:, off:off + o][:, None, :]
+            off += o
+        pre.append(z)
+        h = np.maximum(z, 0.0)
+    return pre
+
+
+def _inputs(b, n, loc, use_bias, seed, wscale=0.15):
+    """Random weights / points / upstream grads.  A point whose pre-activation is within fp32 rounding of zero at some
+    hidden unit has an ill-defined ReLU gate (fp32 and the float64 oracle may legitimately disagree, which changes the
+    gradient by that point's whole contribution); such points (about one in 10^5) are replaced by a copy of a safe one
+    so that the comparison tests arithmetic, not a measure-zero tie."""
+    g = torch.Generator().manual_seed(seed)
+    from oracle import oracle as O
+
+    W = O.target_network_num_weights(loc, use_bias)
+    w = torch.randn(b, W, generator=g) * wscale
+    x = torch.randn(b, n, 3, generator=g) * 0.6
+    go = torch.randn(b, n, 3, generator=g)
+    for _ in range(3):
+        pre = _preacts_f64(w.numpy(), x.numpy(), loc, use_bias)
+        unsafe = np.zeros((b, n), bool)
+        for z in pre:
+            unsafe |= (np.abs(z) < 1e-5 * max(1.0, float(np.abs(z).max()))).any(axis=2)
+        if not unsafe.any():
+            break
+        for s in range(b):
+            safe = np.flatnonzero(~unsafe[s])
+            if len(safe) == 0:
+                continue
+            x[s, torch.from_numpy(np.flatnonzero(unsafe[s]))] = x[s, int(safe[0])].clone()
+    return w, x, go
+
+
+def test_golden_reference_module(hp, golden_cpu):
+    """Vectors produced by the reference's own TargetNetwork class (tests/golden/make_golden_cpu.py)."""
+    g = golden_cpu
+    w = torch.from_numpy(g["tn_w"]).to(DEV).requires_grad_(True)
+    x = torch.from_numpy(g["tn_x"]).to(DEV)
+    y = hp.target_network_forward(w, x, FAST, True)
+    assert _rel_err(y.detach().cpu().numpy(), g["tn_y"]) < 1e-5
+    (y * torch.from_numpy(g["tn_gout"]).to(DEV)).sum().backward()
+    assert _rel_err(w.grad.cpu().numpy(), g["tn_grad_w"]) < 1e-5
+    # generic path: other widths, no bias
+    y2 = hp.target_network_forward(torch.from_numpy(g["tn2_w"]).to(DEV), torch.from_numpy(g["tn2_x"]).to(DEV), [16, 8], False)
+    assert _rel_err(y2.cpu().numpy(), g["tn2_y"]) < 1e-5
+
+
+@pytest.mark.parametrize("b,n", [(1, 1), (2, 127), (3, 128), (2, 129), (5, 300), (4, 2048), (70, 256), (160, 130)])
+@pytest.mark.parametrize("use_bias", [True, False])
+def test_forward_backward_vs_oracle_fast_shape(hp, oracle, b, n, use_bias):
+    w, x, go = _inputs(b, n, FAST, use_bias, seed=b * 100 + n)
+    wd = w.to(DEV).requires_grad_(True)
+    xd = x.to(DEV).requires_grad_(True)
+    y = hp.target_network_forward(wd, xd, FAST, use_bias)
+    oy = oracle.target_network_forward(w.numpy(), x.numpy(), FAST, use_bias)
+    assert tuple(y.shape) == (b, n, 3)
+    assert _rel_err(y.detach().cpu().numpy(), oy) < 1e-5
+    (y * go.to(DEV)).sum().backward()
+    ogw, ogx = oracle.target_network_backward_f64(w.numpy(), x.numpy(), go.numpy(), FAST, use_bias)
+    assert _rel_err(wd.grad.cpu().numpy(), ogw) < 1e-5
+    assert _rel_err(xd.grad.cpu().numpy(), ogx) < 1e-5
+    # weights-only gradient (the trainer's case: input points carry no grad) must agree with the above
+    wd2 = w.to(DEV).requires_grad_(True)
+    (hp.target_network_forward(wd2, x.to(DEV), FAST, use_bias) * go.to(DEV)).sum().backward()
+    assert torch.equal(wd2.grad, wd.grad)
+
+
+def test_channels_first_and_shared_cloud(hp, oracle):
+    b, n = 6, 515
+    w, x, go = _inputs(b, n, FAST, True, seed=9)
+    wd = w.to(DEV).requires_grad_(True)
+    y_cf = hp.target_network_forward(wd, x.to(DEV), FAST, True, channels_first=True)  # [B,3,N], full_model.py:68,74
+    assert tuple(y_cf.shape) == (b, 3, n)
+    y = hp.target_network_forward(wd.detach(), x.to(DEV), FAST, True)
+    assert torch.equal(y_cf.detach().permute(0, 2, 1), y)
+    (y_cf * go.to(DEV).permute(0, 2, 1)).sum().backward()
+    ogw, _ = oracle.target_network_backward_f64(w.numpy(), x.numpy(), go.numpy(), FAST, True)
+    assert _rel_err(wd.grad.cpu().numpy(), ogw) < 1e-5
+    # one shared input cloud for every sample
+    xs = x[0].to(DEV).requires_grad_(True)
+    wd3 = w.to(DEV).requires_grad_(True)
+    ys = hp.target_network_forward(wd3, xs, FAST, True)
+    xe = x[:1].expand(b, n, 3).contiguous()
+    oy = oracle.target_network_forward(w.numpy(), xe.numpy(), FAST, True)
+    assert _rel_err(ys.detach().cpu().numpy(), oy) < 1e-5
+    (ys * go.to(DEV)).sum().backward()
+    ogw, ogx = oracle.target_network_backward_f64(w.numpy(), xe.numpy(), go.numpy(), FAST, True)
+    assert _rel_err(wd3.grad.cpu().numpy(), ogw) < 1e-5
+    assert _rel_err(xs.grad.cpu().numpy(), ogx.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("loc,use_bias", [([16, 8], False), ([7], True), ([32, 64, 128, 64, 5], True), ([200, 31], True)])
+def test_generic_widths_vs_oracle(hp, oracle, loc, use_bias):
+    b, n = 3, 77
+    w, x, go = _inputs(b, n, loc, use_bias, seed=len(loc) * 7 + 1, wscale=0.2)
+    wd = w.to(DEV).requires_grad_(True)
+    xd = x.to(DEV).requires_grad_(True)
+    y = hp.target_network_forward(wd, xd, loc, use_bias)
+    oy = oracle.target_network_forward(w.numpy(), x.numpy(), loc, use_bias)
+    assert _rel_err(y.detach().cpu().numpy(), oy) < 1e-5
+    (y * go.to(DEV)).sum().backward()
+    ogw, ogx = oracle.target_network_backward_f64(w.numpy(), x.numpy(), go.numpy(), loc, use_bias)
+    assert _rel_err(wd.grad.cpu().numpy(), ogw) < 1e-5
+    assert _rel_err(xd.grad.cpu().numpy(), ogx) < 1e-5
+
+
+def test_module_interface_matches_reference_class(hp, oracle):
+    """TargetNetwork(config, weights).forward(x): one sample, x [N,3] -> [N,3] (model/target_network.py:31-38)."""
+    w, x, _ = _inputs(1, 2048, FAST, True, seed=4)
+    cfg = {"use_bias": True, "layer_out_channels": FAST}
+    wd = w[0].to(DEV).requires_grad_(True)
+    net = hp.TargetNetwork(cfg, wd)
+    assert tuple(net.layers["3"]["weight"].shape) == (128, 64) and tuple(net.output["bias"].shape) == (3,)
+    y = net(x[0].to(DEV))
+    oy = oracle.target_network_forward(w.numpy(), x.numpy(), FAST, True)[0]
+    assert tuple(y.shape) == (2048, 3) and _rel_err(y.detach().cpu().numpy(), oy) < 1e-5
+    y.sum().backward()
+    assert wd.grad is not None and tuple(wd.grad.shape) == (19011,)
+    with pytest.raises(AssertionError):
+        hp.TargetNetwork(cfg, wd[:-1].detach())
+
+
+def test_full_size_c4_properties(hp):
+    """BASELINE config C4 shape (B=64 x 2048 points): determinism, linearity of the backward in grad_out,
+    and batch independence (each sample only sees its own weights)."""
+    b, n = 64, 2048
+    w, x, go = _inputs(b, n, FAST, True, seed=1)
+    wd, xd, gd = w.to(DEV), x.to(DEV), go.to(DEV)
+
+    def fwd_bwd(wt, g_out):
+        wt = wt.clone().requires_grad_(True)
+        y = hp.target_network_forward(wt, xd, FAST, True)
+        y.backward(g_out)
+        return y.detach(), wt.grad
+
+    y1, g1 = fwd_bwd(wd, gd)
+    y2, g2 = fwd_bwd(wd, gd)
+    assert torch.equal(y1, y2) and torch.equal(g1, g2), "fused TargetNetwork must be bitwise reproducible"
+    _, g3 = fwd_bwd(wd, 2.0 * gd)
+    torch.testing.assert_close(g3, 2.0 * g1, rtol=1e-6, atol=0)  # scaling by 2 is exact in fp32
+    perm = torch.randperm(b, generator=torch.Generator().manual_seed(0)).to(DEV)
+    yp = hp.target_network_forward(wd[perm], xd[perm], FAST, True)
+    assert torch.equal(yp, y1[perm])
+    # vs plain torch fp32 (the reference's op sequence) on a few samples
+    for s in (0, 17, 63):
+        h = xd[s]
+        off = 0
+        dims = [3] + FAST + [3]
+        for l in range(5):
+            i, o = dims[l], dims[l + 1]
+            Wl = wd[s, off:off + i * o].view(o, i)
+            off += i * o
+            h = torch.mm(h, Wl.t()) + wd[s, off:off + o]
+            off += o
+            if l < 4:
+                h = torch.relu(h)
+        torch.testing.assert_close(y1[s], h, rtol=1e-5, atol=1e-5 * float(h.abs().max()))
+
+
+def test_errors(hp):
+    w = torch.zeros(2, 19011, device=DEV)
+    x = torch.zeros(2, 16, 3, device=DEV)
+    with pytest.raises(AssertionError):
+        hp.target_network_forward(w[:, :-1], x, FAST, True)
+    with pytest.raises(RuntimeError):
+        hp.target_network_forward(w.cpu(), x, FAST, True)
+    with pytest.raises(RuntimeError):
+        hp.target_network_forward(w, x.double(), FAST, True)
+    with pytest.raises(RuntimeError):
+        hp.target_network_forward(w, x[:1], FAST, True)
+    y = hp.target_network_forward(w[:0], x[:0], FAST, True)
+    assert tuple(y.shape) == (0, 16, 3)
+
+
+def test_graph_capture_matches_eager(hp):
+    """TargetNetworkStepGraph / ChamferStepGraph replay the same kernels: bit-identical to the eager calls."""
+    b, n = 8, 640
+    tg = hp.TargetNetworkStepGraph(b, n, FAST, True, DEV, channels_first=True)
+    w, x, go = _inputs(b, n, FAST, True, seed=21)
+    tg.weights.copy_(w.to(DEV))
+    tg.points.copy_(x.to(DEV))
+    tg.grad_out.copy_(go.to(DEV).permute(0, 2, 1))
+    out, gw = tg.replay()
+    torch.cuda.synchronize()
+    wd = w.to(DEV).requires_grad_(True)
+    y = hp.target_network_forward(wd, x.to(DEV), FAST, True, channels_first=True)
+    y.backward(go.to(DEV).permute(0, 2, 1).contiguous())
+    assert torch.equal(out, y.detach()) and torch.equal(gw, wd.grad)
+
+    cg = hp.ChamferStepGraph(3, 700, 900, DEV, with_host_io=True)
+    g = torch.Generator().manual_seed(2)
+    a, c = torch.rand(3, 700, 3, generator=g) - 0.5, torch.rand(3, 900, 3, generator=g) - 0.5
+    cg.xyz1.copy_(a.to(DEV))
+    cg.xyz2.copy_(c.to(DEV))
+    loss, g1, g2 = cg.replay()
+    torch.cuda.synchronize()
+    ad, cd = a.to(DEV).requires_grad_(True), c.to(DEV).requires_grad_(True)
+    ref = hp.ChamferLoss()(cd, ad)
+    ref.backward()
+    assert torch.equal(loss.reshape(()), ref.detach()) and torch.equal(g1, ad.grad) and torch.equal(g2, cd.grad)
+    lh, g1h, g2h = cg.run_from_host(a.pin_memory(), c.pin_memory())
+    torch.cuda.synchronize()
+    assert torch.equal(lh.reshape(()), ref.detach().cpu()) and torch.equal(g1h, ad.grad.cpu()) and torch.equal(g2h, cd.grad.cpu())
