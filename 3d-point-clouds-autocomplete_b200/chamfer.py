@@ -102,8 +102,11 @@ class NNDistanceFunction(Function):
 nn_distance = NNDistanceFunction.apply
 
 
-def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor):
-    """Fused forward: (loss[1], dist1, idx1, dist2, idx2) in ONE launch."""
+def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, want_inverse: bool = False):
+    """Fused forward: (loss[1], dist1, idx1, dist2, idx2) -- ring kernel + unpack.
+
+    With ``want_inverse=True`` a sixth element is returned: ``(inv1, inv2)`` (the inverse index maps, sorted at the
+    tail of the forward) or ``None`` when they are unavailable for this shape; pass it to ``chamfer_backward``."""
     check_points(xyz1, "xyz1")
     check_points(xyz2, "xyz2")
     check_same_device(xyz1, xyz2)
@@ -117,42 +120,64 @@ def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor):
     idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
     loss = torch.empty((1,), dtype=torch.float32, device=dev)
     lib = _native.load()
+    inv = None
     with on_device_of(xyz1) as stream:
         nbytes = lib.hp_chamfer_workspace_bytes(b, n, m)
         ws = zeroed_workspace(dev, stream, nbytes, "chamfer")
-        rc = lib.hp_chamfer_forward(b, n, xyz1.data_ptr(), m, xyz2.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
-                                    dist2.data_ptr(), idx2.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws.numel(),
-                                    stream)
-    _native.check(rc, "hp_chamfer_forward")
+        n1 = lib.hp_chamfer_inverse_ints(b, n, m, 1) if want_inverse else 0
+        if n1 > 0:
+            inv = (torch.empty(n1, dtype=torch.int32, device=dev),
+                   torch.empty(lib.hp_chamfer_inverse_ints(b, n, m, 2), dtype=torch.int32, device=dev))
+            rc = lib.hp_chamfer_forward_inv(b, n, xyz1.data_ptr(), m, xyz2.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
+                                            dist2.data_ptr(), idx2.data_ptr(), loss.data_ptr(), inv[0].data_ptr(),
+                                            inv[1].data_ptr(), ws.data_ptr(), ws.numel(), stream)
+            _native.check(rc, "hp_chamfer_forward_inv")
+        else:
+            rc = lib.hp_chamfer_forward(b, n, xyz1.data_ptr(), m, xyz2.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
+                                        dist2.data_ptr(), idx2.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        stream)
+            _native.check(rc, "hp_chamfer_forward")
+    if want_inverse:
+        return loss, dist1, idx1, dist2, idx2, inv
     return loss, dist1, idx1, dist2, idx2
 
 
-def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_loss: torch.Tensor):
+def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_loss: torch.Tensor, inv=None):
+    """(grad_xyz1, grad_xyz2) of the fused loss.  With ``inv`` (from ``chamfer_forward(want_inverse=True)``) the backward
+    is a pure gather kernel; without it one CTA per (cloud, side) sorts the index map first.  Same bits either way."""
     b, n, m = xyz1.size(0), xyz1.size(1), xyz2.size(1)
     dev = xyz1.device
     g = grad_loss.to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
     grad1 = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
     grad2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+    if b == 0 or n == 0 or m == 0:
+        return grad1.zero_(), grad2.zero_()
     with on_device_of(xyz1) as stream:
-        rc = _native.load().hp_chamfer_backward(b, n, xyz1.data_ptr(), m, xyz2.data_ptr(), idx1.data_ptr(),
-                                                idx2.data_ptr(), g.data_ptr(), grad1.data_ptr(), grad2.data_ptr(),
-                                                stream)
-    _native.check(rc, "hp_chamfer_backward")
+        if inv is not None:
+            rc = _native.load().hp_chamfer_backward_inv(b, n, xyz1.data_ptr(), m, xyz2.data_ptr(), idx1.data_ptr(),
+                                                        idx2.data_ptr(), inv[0].data_ptr(), inv[1].data_ptr(), g.data_ptr(),
+                                                        grad1.data_ptr(), grad2.data_ptr(), stream)
+            _native.check(rc, "hp_chamfer_backward_inv")
+        else:
+            rc = _native.load().hp_chamfer_backward(b, n, xyz1.data_ptr(), m, xyz2.data_ptr(), idx1.data_ptr(),
+                                                    idx2.data_ptr(), g.data_ptr(), grad1.data_ptr(), grad2.data_ptr(),
+                                                    stream)
+            _native.check(rc, "hp_chamfer_backward")
     return grad1, grad2
 
 
 class _ChamferLossFunction(Function):
     @staticmethod
     def forward(ctx, xyz1, xyz2):
-        loss, _d1, idx1, _d2, idx2 = chamfer_forward(xyz1, xyz2)
+        loss, _d1, idx1, _d2, idx2, inv = chamfer_forward(xyz1, xyz2, want_inverse=True)
         ctx.save_for_backward(xyz1, xyz2)
-        ctx.idx1, ctx.idx2 = idx1, idx2
+        ctx.idx1, ctx.idx2, ctx.inv = idx1, idx2, inv
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_loss):
         xyz1, xyz2 = ctx.saved_tensors
-        g1, g2 = chamfer_backward(xyz1, xyz2, ctx.idx1, ctx.idx2, grad_loss)
+        g1, g2 = chamfer_backward(xyz1, xyz2, ctx.idx1, ctx.idx2, grad_loss, ctx.inv)
         return g1, g2
 
 

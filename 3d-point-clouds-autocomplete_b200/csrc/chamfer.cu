@@ -410,7 +410,11 @@ __global__ void nn_grad_atomic_kernel(int b, int n, const float *__restrict__ xy
 // warp-ring forward (chamfer_ring.cu): every unordered pair once, both directions
 size_t nn_ring_workspace_bytes(int b, int n, int m);
 int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
-                           int *idx2, float *loss, void *workspace, cudaStream_t stream);
+                           int *idx2, float *loss, int *inv1, int *inv2, void *workspace, cudaStream_t stream);
+bool nn_ring_inverse_supported(int n, int m);
+int nn_ring_backward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,
+                            const int *inv1, const int *inv2, const float *grad_loss, float *grad1, float *grad2,
+                            cudaStream_t stream);
 
 // HP_NN_RING=0 selects the first-generation ordered-pair kernel (kept for A/B measurements and as the
 // workspace-free path of hp_nndistance).
@@ -550,8 +554,8 @@ extern "C" int hp_nndistance_ws(int b, int n, const float *xyz, int m, const flo
         return HP_ERR_WORKSPACE;
     }
     if (use_ring())
-        return nn_ring_forward_launch(b, n, xyz, m, xyz2, result, result_i, result2, result2_i, nullptr, workspace,
-                                      (cudaStream_t)stream);
+        return nn_ring_forward_launch(b, n, xyz, m, xyz2, result, result_i, result2, result2_i, nullptr, nullptr, nullptr,
+                                      workspace, (cudaStream_t)stream);
     return nn_forward_launch(b, n, xyz, m, xyz2, result, result_i, result2, result2_i, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -574,8 +578,42 @@ extern "C" int hp_chamfer_forward(int b, int n, const float *xyz1, int m, const 
         return HP_ERR_WORKSPACE;
     }
     if (use_ring())
-        return nn_ring_forward_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, workspace, (cudaStream_t)stream);
+        return nn_ring_forward_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, nullptr, nullptr, workspace,
+                                      (cudaStream_t)stream);
     return nn_forward_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, workspace, (cudaStream_t)stream);
+}
+
+extern "C" size_t hp_chamfer_inverse_ints(int b, int n, int m, int which) {
+    if (b <= 0 || n <= 0 || m <= 0 || !use_ring() || !nn_ring_inverse_supported(n, m)) return 0;
+    return which == 2 ? (size_t)b * ((size_t)m + 2 * (size_t)n) : (size_t)b * ((size_t)n + 2 * (size_t)m);
+}
+
+extern "C" int hp_chamfer_forward_inv(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1,
+                                      float *dist2, int *idx2, float *loss, int *inv1, int *inv2, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
+    HP_REQUIRE(b > 0 && n > 0 && m > 0, "hp_chamfer_forward_inv: sizes must be positive (b=%d n=%d m=%d)", b, n, m);
+    HP_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2 && loss && inv1 && inv2, "hp_chamfer_forward_inv: null pointer");
+    HP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+               "hp_chamfer_forward_inv: workspace null or not 16-byte aligned");
+    if (workspace_bytes < hp_chamfer_workspace_bytes(b, n, m)) {
+        set_error("hp_chamfer_forward_inv: workspace %zu < required %zu bytes", workspace_bytes, hp_chamfer_workspace_bytes(b, n, m));
+        return HP_ERR_WORKSPACE;
+    }
+    if (!use_ring() || !nn_ring_inverse_supported(n, m)) {
+        set_error("hp_chamfer_forward_inv: inverse maps unavailable for n=%d m=%d (use hp_chamfer_forward + hp_chamfer_backward)", n, m);
+        return HP_ERR_UNSUPPORTED;
+    }
+    return nn_ring_forward_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, inv1, inv2, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int hp_chamfer_backward_inv(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,
+                                       const int *inv1, const int *inv2, const float *grad_loss, float *grad_xyz1,
+                                       float *grad_xyz2, void *stream) {
+    HP_REQUIRE(b > 0 && n > 0 && m > 0, "hp_chamfer_backward_inv: sizes must be positive (b=%d n=%d m=%d)", b, n, m);
+    HP_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && inv1 && inv2 && grad_loss && grad_xyz1 && grad_xyz2,
+               "hp_chamfer_backward_inv: null pointer");
+    return nn_ring_backward_launch(b, n, xyz1, m, xyz2, idx1, idx2, inv1, inv2, grad_loss, grad_xyz1, grad_xyz2,
+                                   (cudaStream_t)stream);
 }
 
 extern "C" int hp_nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,

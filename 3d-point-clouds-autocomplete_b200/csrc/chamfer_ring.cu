@@ -35,6 +35,7 @@ constexpr int RF_COLS = 32 * RF_RC;             // 128 columns per round
 constexpr float RF_PAD_ROW = 1.0e18f;           // padding points: finite, farther than any real pair
 constexpr float RF_PAD_COL = -1.0e18f;
 constexpr int RF_MERGE_THREADS = 1024;
+constexpr int RF_MAX_PER_THREAD = 32;           // 32768 / RF_MERGE_THREADS: largest cloud of the in-kernel inverse
 
 typedef unsigned long long u64;
 
@@ -50,6 +51,12 @@ struct RingNNArgs {
     float *losspart;           // [2b] per-(cloud,direction) sums
     float *grouppart;          // [ngroups]
     unsigned int *counters;    // [1 + ngroups] tickets; zero on entry, zero on exit
+    // optional inverse index maps for the atomic-free backward (nullptr: not produced).
+    //   inv1 [b][n + 2m]: perm1[n] = row indices i sorted by (idx1[i], i); then begin1[m], end1[m]: bucket of column k
+    //   inv2 [b][m + 2n]: perm2[m] = column indices k sorted by (idx2[k], k); then begin2[n], end2[n]: bucket of row i
+    int *inv1, *inv2;
+    int sort_n, sort_shift;    // power-of-two sort size and bit position of the key in the composite (key << shift | pos)
+    int inv_fast;              // 1: counting-sort layout in shared memory (keys | count | cursor | pbuf), 0: bitonic only
 };
 
 __device__ __forceinline__ float bump_up(float v) { return __int_as_float(__float_as_int(v) + 1); }
@@ -256,6 +263,138 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
     }
 }
 
+
+// Stable inverse of an index map, for the atomic-free backward.  One CTA per (cloud, direction), at the tail of the
+// unpack kernel.  `keys[e]` = target index of source e.  Output per cloud: perm[cnt] = sources sorted by (target, source),
+// begin[ntgt] / end[ntgt] = every target's bucket in perm.
+//   fast path : counting sort -- integer histogram (order-independent atomics), block scan, placement in arrival
+//               order, then every target sorts its own (typically 0-3 element) bucket by source index;
+//   slow path : any bucket above RF_BUCKET_MAX sources (degenerate clouds) or clouds too large for the four
+//               shared-memory arrays -> bitonic sort of the composites (target << shift | source).
+// Both give the same, fully deterministic result.
+constexpr int RF_BUCKET_MAX = 48;
+
+__device__ __forceinline__ void rf_inverse_bitonic(const RingNNArgs &a, unsigned int *sortbuf, const int *keys_or_null, int cnt,
+                                                   int ntgt, int *perm, int *begin, int *end, int tid) {
+    const int N = a.sort_n;
+    if (keys_or_null != nullptr) {  // composites not yet built (coming from the fast path's layout)
+        unsigned int tmp[RF_MAX_PER_THREAD];
+#pragma unroll
+        for (int q = 0; q < RF_MAX_PER_THREAD; ++q) {
+            const int e = tid + q * RF_MERGE_THREADS;
+            tmp[q] = (e < cnt) ? (((unsigned)keys_or_null[e] << a.sort_shift) | (unsigned)e) : 0xffffffffu;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < RF_MAX_PER_THREAD; ++q) {
+            const int e = tid + q * RF_MERGE_THREADS;
+            if (e < N) sortbuf[e] = tmp[q];
+        }
+    } else {
+        for (int e = cnt + tid; e < N; e += RF_MERGE_THREADS) sortbuf[e] = 0xffffffffu;
+    }
+    for (int i = tid; i < 2 * ntgt; i += RF_MERGE_THREADS) begin[i] = 0;  // empty buckets: begin = end = 0 (end follows begin)
+    __syncthreads();
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < N; i += RF_MERGE_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned x = sortbuf[i], y = sortbuf[ixj];
+                    const bool asc = (i & k) == 0;
+                    if ((x > y) == asc) sortbuf[i] = y, sortbuf[ixj] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const unsigned mask = (1u << a.sort_shift) - 1u;
+    for (int p = tid; p < cnt; p += RF_MERGE_THREADS) {
+        const unsigned c = sortbuf[p];
+        const int key = (int)(c >> a.sort_shift);
+        perm[p] = (int)(c & mask);
+        if (p == 0 || (int)(sortbuf[p - 1] >> a.sort_shift) != key) begin[key] = p;
+        if (p == cnt - 1 || (int)(sortbuf[p + 1] >> a.sort_shift) != key) end[key] = p + 1;
+    }
+}
+
+// smem layout of the fast path (ints): keys[cnt] | count[ntgt] -> begin | cursor[ntgt] | pbuf[cnt]
+__device__ __forceinline__ void rf_build_inverse(const RingNNArgs &a, unsigned int *smem_u, int cloud, bool dir2, int tid) {
+    __shared__ int scan_warp[RF_MERGE_THREADS / 32];
+    __shared__ int max_bucket;
+    const int cnt = dir2 ? a.m : a.n;      // sources: the points whose nearest neighbour was searched
+    const int ntgt = dir2 ? a.n : a.m;     // targets: the points they can map to
+    int *inv = (dir2 ? a.inv2 : a.inv1) + (size_t)cloud * (cnt + 2 * ntgt);
+    int *perm = inv, *begin = inv + cnt, *end = begin + ntgt;
+    int *keys = reinterpret_cast<int *>(smem_u);
+    if (!a.inv_fast) {  // composites were written straight into the sort buffer by the caller
+        rf_inverse_bitonic(a, smem_u, nullptr, cnt, ntgt, perm, begin, end, tid);
+        return;
+    }
+    int *count = keys + cnt, *cursor = count + ntgt, *pbuf = cursor + ntgt;
+    for (int i = tid; i < ntgt; i += RF_MERGE_THREADS) count[i] = 0;
+    if (tid == 0) max_bucket = 0;
+    __syncthreads();
+    for (int e = tid; e < cnt; e += RF_MERGE_THREADS) atomicAdd(&count[keys[e]], 1);
+    __syncthreads();
+    // exclusive scan of count[0..ntgt): contiguous chunk per thread, warp scan, scan of the warp totals
+    const int per = (ntgt + RF_MERGE_THREADS - 1) / RF_MERGE_THREADS;
+    const int lo = min(ntgt, tid * per), hi = min(ntgt, lo + per);
+    int local = 0, lmax = 0;
+    for (int i = lo; i < hi; ++i) local += count[i], lmax = max(lmax, count[i]);
+    int inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((tid & 31) >= o) inc += v;
+    }
+    if ((tid & 31) == 31) scan_warp[tid >> 5] = inc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    if ((tid & 31) == 0 && lmax > 0) atomicMax(&max_bucket, lmax);
+    __syncthreads();
+    if (tid < 32) {
+        int w = scan_warp[tid], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, winc, o);
+            if (tid >= o) winc += v;
+        }
+        scan_warp[tid] = winc - w;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    if (max_bucket > RF_BUCKET_MAX) {  // block-uniform: degenerate cloud, take the sorting path (keys are still intact)
+        __syncthreads();
+        rf_inverse_bitonic(a, reinterpret_cast<unsigned int *>(count), keys, cnt, ntgt, perm, begin, end, tid);
+        return;
+    }
+    {
+        int run = scan_warp[tid >> 5] + inc - local;
+        for (int i = lo; i < hi; ++i) {
+            const int c = count[i];
+            count[i] = run;   // begin
+            cursor[i] = run;
+            begin[i] = c ? run : 0;  // empty buckets: begin = end = 0
+            end[i] = c ? run + c : 0;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < cnt; e += RF_MERGE_THREADS) pbuf[atomicAdd(&cursor[keys[e]], 1)] = e;  // arrival order
+    __syncthreads();
+    for (int i = tid; i < ntgt; i += RF_MERGE_THREADS) {  // owner sorts its bucket by source index (insertion sort)
+        const int b0 = count[i], b1 = cursor[i];
+        for (int p = b0 + 1; p < b1; ++p) {
+            const int v = pbuf[p];
+            int q = p - 1;
+            while (q >= b0 && pbuf[q] > v) pbuf[q + 1] = pbuf[q], --q;
+            pbuf[q + 1] = v;
+        }
+    }
+    __syncthreads();
+    for (int p = tid; p < cnt; p += RF_MERGE_THREADS) perm[p] = pbuf[p];
+}
+
 // key -> (distance, index); restores the zero state of the key arrays; fixed-order loss.
 // One block per (cloud, direction).  The loss is folded through a two-level ticket (groups of RF_GROUP blocks, then
 // groups) so that no single address sees more than RF_GROUP / (blocks / RF_GROUP) serialised atomics.
@@ -274,7 +413,9 @@ __device__ __forceinline__ float rf_block_sum(float v, float *warp_part, int tid
     return s;  // valid in thread 0
 }
 
+template <bool INVERT>
 __global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const RingNNArgs a) {
+    extern __shared__ __align__(16) unsigned int sortbuf[];  // INVERT: [sort_n] composites
     __shared__ float warp_part[RF_MERGE_THREADS / 32];
     __shared__ int flag;
     const int tid = threadIdx.x;
@@ -292,7 +433,9 @@ __global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const 
             src[e] = 0ull;
             dist[e] = __uint_as_float((unsigned)(key >> 32));
             idx[e] = (int)(unsigned)(key & 0xffffffffu);
+            if (INVERT) sortbuf[e] = a.inv_fast ? (unsigned)(key & 0xffffffffu) : (((unsigned)(key & 0xffffffffu) << a.sort_shift) | (unsigned)e);
         }
+        if (INVERT) rf_build_inverse(a, sortbuf, cloud, dir2, tid);
     };
     if (a.loss == nullptr) {
         unpack_store();
@@ -383,8 +526,20 @@ size_t nn_ring_workspace_bytes(int b, int n, int m) {
 
 // Inputs must be finite with |coordinate| < 1e15 (padding points sit at +-1e18).  The workspace must be all zero on
 // entry (every byte: the key arrays move with the shape) and is all zero again when the two kernels have run.
+static int ceil_log2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+// the in-kernel inverse needs both sort buffers in shared memory and the composite in 31 bits
+bool nn_ring_inverse_supported(int n, int m) {
+    if (n <= 0 || m <= 0) return false;
+    const int big = n > m ? n : m;
+    return big <= 32768;  // composite (target << shift | source) in 30 bits, sort buffer <= 128 KB
+}
+
 int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
-                           int *idx2, float *loss, void *workspace, cudaStream_t stream) {
+                           int *idx2, float *loss, int *inv1, int *inv2, void *workspace, cudaStream_t stream) {
     RingNNArgs a = {};
     const RFLayout L = rf_layout(b, n, m);
     unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
@@ -410,8 +565,81 @@ int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *
     else if (variant == 2) nn_ring_kernel<6><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     else nn_ring_kernel<4><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     HP_LAUNCH_CHECK("nn_ring_kernel");
-    nn_ring_unpack_kernel<<<(unsigned)ugrid, RF_MERGE_THREADS, 0, stream>>>(a);
+    if (inv1 != nullptr && inv2 != nullptr) {
+        HP_REQUIRE(nn_ring_inverse_supported(n, m), "nn ring forward: clouds too large for the in-kernel inverse (n=%d m=%d)", n, m);
+        a.inv1 = inv1, a.inv2 = inv2;
+        const int big = n > m ? n : m;
+        a.sort_n = 1 << ceil_log2(big);
+        a.sort_shift = ceil_log2(big);
+        // fast (counting-sort) layout: keys[cnt] count[ntgt] cursor[ntgt] pbuf[cnt] <= 4*big ints; its degenerate-bucket
+        // fallback sorts sort_n composites inside the count|cursor|pbuf region (>= 3*big ints >= sort_n)
+        a.inv_fast = ((size_t)4 * big * sizeof(int) <= 160 * 1024 && 3 * (size_t)(n < m ? n : m) >= (size_t)a.sort_n) ? 1 : 0;
+        const size_t smem = a.inv_fast ? (size_t)(2 * (size_t)big + 2 * (size_t)big) * sizeof(int) : (size_t)a.sort_n * sizeof(unsigned int);
+        static SmemAttrCache attr;
+        if (smem > 40 * 1024) HP_CUDA(ensure_dynamic_smem(nn_ring_unpack_kernel<true>, smem, attr));
+        nn_ring_unpack_kernel<true><<<(unsigned)ugrid, RF_MERGE_THREADS, smem, stream>>>(a);
+    } else {
+        nn_ring_unpack_kernel<false><<<(unsigned)ugrid, RF_MERGE_THREADS, 0, stream>>>(a);
+    }
     HP_LAUNCH_CHECK("nn_ring_unpack_kernel");
+    return HP_OK;
+}
+
+
+// ---- backward as a pure gather over the inverse maps produced by the forward --------------------------------
+//   grad_a[i] = 2 g [ (a_i - b_idx1[i]) + sum_{k in bucket2(i), ascending} (a_i - b_k) ]      (nndistance.cu:143-151)
+//   grad_b[k] = 2 g [ (b_k - a_idx2[k]) + sum_{i in bucket1(k), ascending} (b_k - a_i) ]
+// One thread per point, all clouds and both sides in one launch; same summation order as nn_grad_kernel.
+struct RingGradArgs {
+    const float *set1, *set2;
+    const int *idx1, *idx2, *inv1, *inv2;
+    const float *g;  // one device scalar (the loss gradient)
+    float *grad1, *grad2;
+    int b, n, m;
+};
+
+__global__ void __launch_bounds__(256) nn_grad_gather_kernel(const RingGradArgs a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total1 = (long long)a.b * a.n, total = total1 + (long long)a.b * a.m;
+    if (t >= total) return;
+    const bool side2 = t >= total1;
+    const long long u = side2 ? t - total1 : t;
+    const int np = side2 ? a.m : a.n, no = side2 ? a.n : a.m;
+    const int cloud = (int)(u / np), i = (int)(u - (long long)cloud * np);
+    const float *__restrict__ P = (side2 ? a.set2 : a.set1) + (size_t)cloud * np * 3;
+    const float *__restrict__ O = (side2 ? a.set1 : a.set2) + (size_t)cloud * no * 3;
+    const int *__restrict__ idx_own = (side2 ? a.idx2 : a.idx1) + (size_t)cloud * np;
+    // buckets of the OTHER side's index map: inv of the other direction = [perm[no] | begin[np] | end[np]]
+    const int *__restrict__ inv = (side2 ? a.inv1 : a.inv2) + (size_t)cloud * (no + 2 * np);
+    const int *__restrict__ perm = inv;
+    const int pb = __ldg(inv + no + i), pe = __ldg(inv + no + np + i);
+    const float g2 = __ldg(a.g) * 2.f;
+    const float px = __ldg(P + (size_t)i * 3 + 0), py = __ldg(P + (size_t)i * 3 + 1), pz = __ldg(P + (size_t)i * 3 + 2);
+    const int j = min(max(__ldg(idx_own + i), 0), no - 1);
+    float ax = g2 * (px - __ldg(O + (size_t)j * 3 + 0));
+    float ay = g2 * (py - __ldg(O + (size_t)j * 3 + 1));
+    float az = g2 * (pz - __ldg(O + (size_t)j * 3 + 2));
+    for (int p = pb; p < pe; ++p) {  // ascending source index: fixed summation order
+        const int k = __ldg(perm + p);
+        ax += -(g2 * (__ldg(O + (size_t)k * 3 + 0) - px));
+        ay += -(g2 * (__ldg(O + (size_t)k * 3 + 1) - py));
+        az += -(g2 * (__ldg(O + (size_t)k * 3 + 2) - pz));
+    }
+    float *G = (side2 ? a.grad2 : a.grad1) + ((size_t)cloud * np + i) * 3;
+    G[0] = ax, G[1] = ay, G[2] = az;
+}
+
+int nn_ring_backward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,
+                            const int *inv1, const int *inv2, const float *grad_loss, float *grad1, float *grad2,
+                            cudaStream_t stream) {
+    RingGradArgs a;
+    a.set1 = xyz1, a.set2 = xyz2, a.idx1 = idx1, a.idx2 = idx2, a.inv1 = inv1, a.inv2 = inv2, a.g = grad_loss;
+    a.grad1 = grad1, a.grad2 = grad2, a.b = b, a.n = n, a.m = m;
+    const long long total = (long long)b * ((long long)n + m);
+    const long long grid = (total + 255) / 256;
+    HP_REQUIRE(grid <= 0x7fffffffLL, "nn ring backward: grid too large");
+    nn_grad_gather_kernel<<<(unsigned)grid, 256, 0, stream>>>(a);
+    HP_LAUNCH_CHECK("nn_grad_gather_kernel");
     return HP_OK;
 }
 

@@ -50,8 +50,8 @@ class ChamferStepGraph:
             self._one = torch.ones((), device=self.device)
 
             def step():
-                loss, d1, i1, d2, i2 = chamfer_forward(self.xyz1, self.xyz2)
-                g1, g2 = chamfer_backward(self.xyz1, self.xyz2, i1, i2, self._one)
+                loss, d1, i1, d2, i2, inv = chamfer_forward(self.xyz1, self.xyz2, want_inverse=True)
+                g1, g2 = chamfer_backward(self.xyz1, self.xyz2, i1, i2, self._one, inv)
                 return loss, d1, i1, d2, i2, g1, g2
 
             self.graph, outs, self._stream = _capture(step, self.device)
@@ -71,8 +71,8 @@ class ChamferStepGraph:
                 def host_step():
                     self.xyz1.copy_(self.xyz1_host, non_blocking=True)
                     self.xyz2.copy_(self.xyz2_host, non_blocking=True)
-                    loss, _d1, i1, _d2, i2 = chamfer_forward(self.xyz1, self.xyz2)
-                    g1, g2 = chamfer_backward(self.xyz1, self.xyz2, i1, i2, self._one)
+                    loss, _d1, i1, _d2, i2, inv = chamfer_forward(self.xyz1, self.xyz2, want_inverse=True)
+                    g1, g2 = chamfer_backward(self.xyz1, self.xyz2, i1, i2, self._one, inv)
                     self.loss_host.copy_(loss, non_blocking=True)
                     self.grad_xyz1_host.copy_(g1, non_blocking=True)
                     self.grad_xyz2_host.copy_(g2, non_blocking=True)

@@ -284,9 +284,10 @@ def run_ours(args):
 
     # forward-only / backward-only graphs for the per-kernel roofline
     fwd_in = (step.xyz1, step.xyz2)
-    fwd_graph, fwd_out, _ = hp.graphs._capture(lambda: hp.chamfer_forward(*fwd_in), dev)
+    fwd_graph, fwd_out, _ = hp.graphs._capture(lambda: hp.chamfer_forward(*fwd_in, want_inverse=True), dev)
     one = torch.ones((), device=dev)
-    bwd_graph, _bo, _ = hp.graphs._capture(lambda: hp.chamfer_backward(step.xyz1, step.xyz2, fwd_out[2], fwd_out[4], one), dev)
+    bwd_graph, _bo, _ = hp.graphs._capture(
+        lambda: hp.chamfer_backward(step.xyz1, step.xyz2, fwd_out[2], fwd_out[4], one, fwd_out[5]), dev)
 
     # eager public API (autograd module), for reference: CPU/launch bound at this size
     a = a_h.to(dev).requires_grad_(True)

@@ -105,6 +105,22 @@ HP_API int hp_chamfer_backward(int b, int n, const float *xyz1, int m, const flo
                         const int *idx1, const int *idx2, const float *grad_loss,
                         float *grad_xyz1, float *grad_xyz2, void *stream);
 
+/* Training-step pair: the forward additionally emits the INVERSE of both index maps (sorted in shared memory at the
+ * tail of the forward's unpack kernel), so that the backward is a pure gather: one thread per point, no sort, no
+ * atomics, same summation order (ascending source index) and bit-identical gradients to hp_chamfer_backward.
+ *   inv1: hp_chamfer_inverse_ints(b,n,m,1) = b*(n+2m) ints, per cloud [perm1[n] | begin1[m] | end1[m]]: rows i
+ *         sorted by (idx1[i], i), and for every column k its bucket perm1[begin1[k] .. end1[k]);
+ *   inv2: hp_chamfer_inverse_ints(b,n,m,2) = b*(m+2n) ints, the same for columns sorted by (idx2[k], k).
+ * hp_chamfer_inverse_ints returns 0 when the pair is unavailable (a cloud above 32768 points): use
+ * hp_chamfer_forward / hp_chamfer_backward then.  Workspace as for hp_chamfer_forward. */
+HP_API size_t hp_chamfer_inverse_ints(int b, int n, int m, int which);
+HP_API int hp_chamfer_forward_inv(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1,
+                           int *idx1, float *dist2, int *idx2, float *loss, int *inv1, int *inv2,
+                           void *workspace, size_t workspace_bytes, void *stream);
+HP_API int hp_chamfer_backward_inv(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1,
+                            const int *idx2, const int *inv1, const int *inv2, const float *grad_loss,
+                            float *grad_xyz1, float *grad_xyz2, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * (b) Approximate EMD (soft auction)
  * ---------------------------------------------------------------------------------- */

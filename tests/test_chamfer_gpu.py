@@ -264,3 +264,38 @@ def test_ring_kernel_unaligned_views(hp, oracle):
     od1, oi1, od2, oi2 = oracle.nn_distance(a.contiguous().numpy(), c.contiguous().numpy())
     assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
     assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+
+
+@pytest.mark.parametrize("b,n,m,kind", [(3, 700, 1100, "uniform"), (2, 2048, 2048, "uniform"), (2, 1500, 300, "ties"),
+                                        (1, 1, 7, "uniform"), (2, 5000, 4097, "uniform"), (2, 64, 64, "zero")])
+def test_gather_backward_from_forward_inverse_equals_sorting_backward(hp, oracle, b, n, m, kind):
+    """chamfer_forward(want_inverse=True) emits the inverse index maps; the gather backward built on them must give the
+    same bits as the self-contained (sorting) backward and match the oracle."""
+    g = torch.Generator().manual_seed(n + m)
+    if kind == "ties":
+        a = torch.randint(0, 3, (b, n, 3), generator=g).float() / 2
+        c = torch.randint(0, 3, (b, m, 3), generator=g).float() / 2
+    elif kind == "zero":  # every point of xyz1 identical: one bucket holds everything
+        a = torch.zeros(b, n, 3)
+        c = torch.rand(b, m, 3, generator=g)
+    else:
+        a, c = torch.rand(b, n, 3, generator=g) - 0.5, torch.rand(b, m, 3, generator=g) - 0.5
+    ad, cd = a.to(DEV), c.to(DEV)
+    gl = torch.tensor(0.7, device=DEV)
+    loss, d1, i1, d2, i2, inv = hp.chamfer_forward(ad, cd, want_inverse=True)
+    assert inv is not None
+    ga, gb = hp.chamfer_backward(ad, cd, i1, i2, gl, inv)
+    ha, hb = hp.chamfer_backward(ad, cd, i1, i2, gl)  # sorts the index maps itself
+    assert torch.equal(ga, ha) and torch.equal(gb, hb)
+    oga, ogb = oracle.nn_distance_grad(a.numpy(), c.numpy(), i1.cpu().numpy(), i2.cpu().numpy(),
+                                       np.full((b, n), 0.7, np.float32), np.full((b, m), 0.7, np.float32))
+    np.testing.assert_allclose(ga.cpu().numpy(), oga, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gb.cpu().numpy(), ogb, rtol=1e-5, atol=1e-6)
+    # the inverse maps are what they claim: perm sorted by (idx, position), buckets delimit equal idx
+    inv2 = inv[1].view(b, m + 2 * n).cpu().numpy()
+    for s in range(b):
+        perm, begin, end = inv2[s, :m], inv2[s, m:m + n], inv2[s, m + n:]
+        keys = i2[s].cpu().numpy()[perm]
+        assert np.all(np.diff(keys) >= 0) and sorted(perm.tolist()) == list(range(m))
+        cnt = np.bincount(i2[s].cpu().numpy(), minlength=n)
+        assert np.array_equal(end - begin, cnt)

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 set -uo pipefail
 mkdir -p gpurun_out
-echo "== pytest chamfer"; timeout 900 python -m pytest tests/test_chamfer_gpu.py -x -q 2>&1 | tail -3
+echo "== pytest chamfer+tn"; timeout 900 python -m pytest tests/test_chamfer_gpu.py tests/test_target_network_gpu.py -x -q 2>&1 | grep -vE "^E   +\+" | tail -8
 timeout 600 ncu --metrics gpu__time_duration.sum --cache-control none --clock-control none -c 60 --csv --log-file gpurun_out/launches_ring_warm.csv python tools/profile_chamfer.py 6 > /dev/null 2>&1
 echo "warm (cache-control none):"; grep -E "nn_ring|nn_grad" gpurun_out/launches_ring_warm.csv | awk -F'","' '{print $5, $NF}' | tail -3
 echo "== bench"; timeout 300 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-other-paths --no-metrics-eval 2>gpurun_out/bench.err | tee gpurun_out/bench_v0.json | python -c "

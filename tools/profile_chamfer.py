@@ -13,7 +13,7 @@ a = (torch.rand(B, N, 3, generator=g) - 0.5).cuda()
 b = (torch.rand(B, M, 3, generator=g) - 0.5).cuda()
 one = torch.ones((), device="cuda")
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
-    loss, d1, i1, d2, i2 = hp.chamfer_forward(a, b)
-    hp.chamfer_backward(a, b, i1, i2, one)
+    loss, d1, i1, d2, i2, inv = hp.chamfer_forward(a, b, want_inverse=True)
+    hp.chamfer_backward(a, b, i1, i2, one, inv)
 torch.cuda.synchronize()
 print("done", float(loss))
