@@ -34,6 +34,7 @@ constexpr int TN_TP = TN_T + 4;   // activation row stride (floats)
 constexpr int TN_THREADS = 512;
 constexpr int TN_WARPS = TN_THREADS / 32;
 constexpr int TN_MAX_LAYERS = 16;
+constexpr int TN_MAX_GRID = 256;  // fast-path CTAs (one per SM)
 
 struct TNArgs {
     const float *weights;   // [B][W]
@@ -43,9 +44,9 @@ struct TNArgs {
     const float *gout;      // backward: same layout as out
     float *gweights;        // [B][W]
     float *gpoints;         // [B][N][3] or nullptr
-    float *partial;         // [B][S][W] when S > 1
+    float *partial;         // [grid][S][W]: per-CTA partial dW, slot = sample - first sample of the CTA's range
     unsigned int *counters; // [B], zeroed by the launcher
-    int B, N, W, S;
+    int B, N, W, S;         // S = partial slots per CTA (backward)
     int channels_first;
     int offw[TN_MAX_LAYERS], offb[TN_MAX_LAYERS];  // float offsets inside a sample's weight vector; offb < 0: no bias
 };
@@ -111,33 +112,34 @@ __device__ __forceinline__ void tn_layer_fwd(const float *__restrict__ in, float
         const int wp = wt & 3, wo = wt >> 2;
         const int p = wp * 32 + pg * 4;
         const int ob = wo * (4 * OT) + og;
-        float acc[OT][4];
+        // accumulators as fp32x2 pairs over points (p0,p1), (p2,p3): FFMA2 with the weight as the broadcast scalar operand
+        // (SASS: FFMA2 Rd, Rw.F32, Ra.F32x2, Rd) -- half the issue slots of scalar FFMA, bit-identical lanes
+        f32x2 acc[OT][2];
 #pragma unroll
         for (int j = 0; j < OT; ++j) {
             const float b = bs[ob + 4 * j];
-            acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = b;
+            acc[j][0] = acc[j][1] = pack2(b, b);
         }
 #pragma unroll 2
         for (int k0 = 0; k0 < KR; k0 += 4) {
-            float4 a[4];
+            ulonglong2 a[4];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) a[kk] = *reinterpret_cast<const float4 *>(in + (k0 + kk) * TN_TP + p);
+            for (int kk = 0; kk < 4; ++kk) a[kk] = *reinterpret_cast<const ulonglong2 *>(in + (k0 + kk) * TN_TP + p);
 #pragma unroll
             for (int j = 0; j < OT; ++j) {
                 const float4 w = *reinterpret_cast<const float4 *>(Ws + (ob + 4 * j) * KP + k0);
-                acc[j][0] = __fmaf_rn(w.x, a[0].x, acc[j][0]), acc[j][1] = __fmaf_rn(w.x, a[0].y, acc[j][1]);
-                acc[j][2] = __fmaf_rn(w.x, a[0].z, acc[j][2]), acc[j][3] = __fmaf_rn(w.x, a[0].w, acc[j][3]);
-                acc[j][0] = __fmaf_rn(w.y, a[1].x, acc[j][0]), acc[j][1] = __fmaf_rn(w.y, a[1].y, acc[j][1]);
-                acc[j][2] = __fmaf_rn(w.y, a[1].z, acc[j][2]), acc[j][3] = __fmaf_rn(w.y, a[1].w, acc[j][3]);
-                acc[j][0] = __fmaf_rn(w.z, a[2].x, acc[j][0]), acc[j][1] = __fmaf_rn(w.z, a[2].y, acc[j][1]);
-                acc[j][2] = __fmaf_rn(w.z, a[2].z, acc[j][2]), acc[j][3] = __fmaf_rn(w.z, a[2].w, acc[j][3]);
-                acc[j][0] = __fmaf_rn(w.w, a[3].x, acc[j][0]), acc[j][1] = __fmaf_rn(w.w, a[3].y, acc[j][1]);
-                acc[j][2] = __fmaf_rn(w.w, a[3].z, acc[j][2]), acc[j][3] = __fmaf_rn(w.w, a[3].w, acc[j][3]);
+                const f32x2 w0 = pack2(w.x, w.x), w1 = pack2(w.y, w.y), w2 = pack2(w.z, w.z), w3 = pack2(w.w, w.w);
+                acc[j][0] = fma2(w0, a[0].x, acc[j][0]), acc[j][1] = fma2(w0, a[0].y, acc[j][1]);
+                acc[j][0] = fma2(w1, a[1].x, acc[j][0]), acc[j][1] = fma2(w1, a[1].y, acc[j][1]);
+                acc[j][0] = fma2(w2, a[2].x, acc[j][0]), acc[j][1] = fma2(w2, a[2].y, acc[j][1]);
+                acc[j][0] = fma2(w3, a[3].x, acc[j][0]), acc[j][1] = fma2(w3, a[3].y, acc[j][1]);
             }
         }
 #pragma unroll
         for (int j = 0; j < OT; ++j) {
-            float4 r = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            float4 r;
+            unpack2(acc[j][0], r.x, r.y);
+            unpack2(acc[j][1], r.z, r.w);
             if (RELU) r.x = fmaxf(r.x, 0.f), r.y = fmaxf(r.y, 0.f), r.z = fmaxf(r.z, 0.f), r.w = fmaxf(r.w, 0.f);
             *reinterpret_cast<float4 *>(out + (ob + 4 * j) * TN_TP + p) = r;
         }
@@ -160,14 +162,14 @@ __device__ __forceinline__ void tn_layer_dgrad(const float *__restrict__ Z, floa
         const int wp = wt & 3, wk = wt >> 2;
         const int p = wp * 32 + pg * 4;
         const int kb = wk * (4 * TK) + kg * V;  // channel of (h, i): kb + h*4*V + i
-        float acc[H][V][4];
+        f32x2 acc[H][V][2];  // pairs over points, see tn_layer_fwd
 #pragma unroll
         for (int h = 0; h < H; ++h)
 #pragma unroll
-            for (int i = 0; i < V; ++i) acc[h][i][0] = acc[h][i][1] = acc[h][i][2] = acc[h][i][3] = 0.f;
+            for (int i = 0; i < V; ++i) acc[h][i][0] = acc[h][i][1] = pack2(0.f, 0.f);
 #pragma unroll 4
         for (int o = 0; o < OW; ++o) {
-            const float4 z = *reinterpret_cast<const float4 *>(Z + o * TN_TP + p);
+            const ulonglong2 z = *reinterpret_cast<const ulonglong2 *>(Z + o * TN_TP + p);
 #pragma unroll
             for (int h = 0; h < H; ++h) {
                 float w[4];
@@ -180,8 +182,8 @@ __device__ __forceinline__ void tn_layer_dgrad(const float *__restrict__ Z, floa
                 }
 #pragma unroll
                 for (int i = 0; i < V; ++i) {
-                    acc[h][i][0] = __fmaf_rn(w[i], z.x, acc[h][i][0]), acc[h][i][1] = __fmaf_rn(w[i], z.y, acc[h][i][1]);
-                    acc[h][i][2] = __fmaf_rn(w[i], z.z, acc[h][i][2]), acc[h][i][3] = __fmaf_rn(w[i], z.w, acc[h][i][3]);
+                    const f32x2 wi = pack2(w[i], w[i]);
+                    acc[h][i][0] = fma2(wi, z.x, acc[h][i][0]), acc[h][i][1] = fma2(wi, z.y, acc[h][i][1]);
                 }
             }
         }
@@ -191,7 +193,9 @@ __device__ __forceinline__ void tn_layer_dgrad(const float *__restrict__ Z, floa
             for (int i = 0; i < V; ++i) {
                 const int k = kb + h * 4 * V + i;
                 float4 *dst = reinterpret_cast<float4 *>(in + k * TN_TP + p);
-                float4 r = make_float4(acc[h][i][0], acc[h][i][1], acc[h][i][2], acc[h][i][3]);
+                float4 r;
+                unpack2(acc[h][i][0], r.x, r.y);
+                unpack2(acc[h][i][1], r.z, r.w);
                 if (MASK) {
                     const float4 a = *dst;
                     r.x = a.x > 0.f ? r.x : 0.f, r.y = a.y > 0.f ? r.y : 0.f;
@@ -314,21 +318,26 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_forward_kernel(const TNArgs 
     float *bufA = sm + TNF_BUFA, *bufB = sm + TNF_BUFB;
     float *W1 = sm + TNF_W1, *W2 = sm + TNF_W2, *W3 = sm + TNF_W3, *W4 = sm + TNF_W4, *W5 = sm + TNF_W5, *bs = sm + TNF_BIAS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x / a.S, s = blockIdx.x - b * a.S;
-    const float *wg = a.weights + (size_t)b * a.W;
-    const float *pts = a.points + (size_t)b * a.pstride;
-
-    tn_stage_weights<3, C1>(wg + a.offw[0], W1, tid);
-    tn_stage_weights<C1, C2>(wg + a.offw[1], W2, tid);
-    tn_stage_weights<C2, C3>(wg + a.offw[2], W3, tid);
-    tn_stage_weights<C3, C4>(wg + a.offw[3], W4, tid);
-    tn_stage_weights_out3<C4>(wg + a.offw[4], W5, tid);
-    tn_stage_biases(a, wg, bs, tid);
-
+    // flat (sample, tile) list split evenly over the CTAs: every SM gets the same number of tiles (+-1)
     const int ntiles = (a.N + TN_T - 1) / TN_T;
-    for (int t = s; t < ntiles; t += a.S) {
+    const long long TT = (long long)a.B * ntiles;
+    const long long f0 = (long long)blockIdx.x * TT / gridDim.x, f1 = (long long)(blockIdx.x + 1) * TT / gridDim.x;
+    int cur = -1;
+    for (long long f = f0; f < f1; ++f) {
+        const int b = (int)(f / ntiles), t = (int)(f - (long long)b * ntiles);
+        const float *pts = a.points + (size_t)b * a.pstride;
+        if (b != cur) {  // (re)stage this sample's weights; every reader of the old ones is past the last barrier
+            const float *wg = a.weights + (size_t)b * a.W;
+            tn_stage_weights<3, C1>(wg + a.offw[0], W1, tid);
+            tn_stage_weights<C1, C2>(wg + a.offw[1], W2, tid);
+            tn_stage_weights<C2, C3>(wg + a.offw[2], W3, tid);
+            tn_stage_weights<C3, C4>(wg + a.offw[3], W4, tid);
+            tn_stage_weights_out3<C4>(wg + a.offw[4], W5, tid);
+            tn_stage_biases(a, wg, bs, tid);
+            cur = b;
+        }
         const int n0 = t * TN_T;
-        __syncthreads();  // previous tile's Y consumed; (first pass) weights visible
+        __syncthreads();  // previous tile's Y consumed; weights visible
         tn_load_xyz_tile(pts, n0, a.N, bufB, tid);
         __syncthreads();
         tn_layer_fwd<3, C1, 2, true>(bufB, bufA, W1, bs, warp, lane);
@@ -363,32 +372,93 @@ static_assert(C4 * (C3 + 4) <= TNB_WSZ, "weight buffer");
 template <bool GRAD_POINTS>
 __global__ void __launch_bounds__(TN_THREADS, 1) tn_backward_kernel(const TNArgs a) {
     extern __shared__ __align__(16) float sm[];
-    float *A1 = sm + TNB_A1, *A2 = sm + TNB_A2, *A3 = sm + TNB_A3, *A4 = sm + TNB_A4, *X = sm + TNB_X, *G = sm + TNB_G;
+    float *A1 = sm + TNB_A1, *A2 = sm + TNB_A2, *A3 = sm + TNB_A3, *A4 = sm + TNB_A4, *X = sm + TNB_X, *G5 = sm + TNB_G;
     float *wb0 = sm + TNB_WBUF, *wb1 = wb0 + TNB_WSZ, *bs = sm + TNB_BIAS;
     __shared__ int is_last;
+    __shared__ unsigned int slot_of[TN_MAX_GRID];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x / a.S, s = blockIdx.x - b * a.S;
-    const float *wg = a.weights + (size_t)b * a.W;
-    const float *pts = a.points + (size_t)b * a.pstride;
-    const float *gy = a.gout + (size_t)b * a.N * 3;
+    // flat (sample, tile) list split evenly over the CTAs (every SM busy); a CTA's range may straddle samples
+    const int ntiles = (a.N + TN_T - 1) / TN_T;
+    const long long TT = (long long)a.B * ntiles;
+    const long long G = gridDim.x;
+    const long long f0 = (long long)blockIdx.x * TT / G, f1 = (long long)(blockIdx.x + 1) * TT / G;
+    const int first_sample = (int)(f0 / ntiles);
 
     float dW4[16], dW3[16], dW2[4];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) dW4[i] = 0.f, dW3[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dW2[i] = 0.f;
     // small gradients, one role per warp: small0 = dW5 (warps 0-5) | db5 (6) | db4 (7-8) | db3 (9-12) | db2 (13-14) | db1 (15)
     //                                     small1 = dW1 (warps 0-2)
-    float small0 = 0.f, small1 = 0.f;
+    float small0, small1;
+    auto reset_acc = [&]() {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dW4[i] = 0.f, dW3[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dW2[i] = 0.f;
+        small0 = 0.f, small1 = 0.f;
+    };
+    // Write this CTA's accumulated dW of sample `b` (flat weight order).  If other CTAs also hold tiles of `b`, the
+    // vector goes to this CTA's partial slot and the last CTA to arrive folds all slots in ascending CTA order.
+    auto flush = [&](int b) {
+        const long long s0 = (long long)b * ntiles, s1 = s0 + ntiles - 1;  // flat tiles of sample b
+        const int c_lo = (int)(((s0 + 1) * G - 1) / TT), c_hi = (int)(((s1 + 1) * G - 1) / TT);
+        const bool shared_sample = c_lo != c_hi;
+        float *dst = shared_sample ? a.partial + ((size_t)blockIdx.x * a.S + (b - first_sample)) * a.W : a.gweights + (size_t)b * a.W;
+        tn_store_wgrad<C4, C3, 4, 4>(dW4, dst + a.offw[3], warp, lane);
+        tn_store_wgrad<C3, C2, 4, 4>(dW3, dst + a.offw[2], warp, lane);
+        tn_store_wgrad<C2, C1, 2, 2>(dW2, dst + a.offw[1], warp, lane);
+        if (warp < 6) dst[a.offw[4] + tid] = small0;  // dW5[o][k] at o*64 + k = tid
+        else if (warp == 6) { if (lane < 3 && a.offb[4] >= 0) dst[a.offb[4] + lane] = small0; }
+        else if (warp <= 8) { if (a.offb[3] >= 0) dst[a.offb[3] + (warp - 7) * 32 + lane] = small0; }
+        else if (warp <= 12) { if (a.offb[2] >= 0) dst[a.offb[2] + (warp - 9) * 32 + lane] = small0; }
+        else if (warp <= 14) { if (a.offb[1] >= 0) dst[a.offb[1] + (warp - 13) * 32 + lane] = small0; }
+        else { if (a.offb[0] >= 0) dst[a.offb[0] + lane] = small0; }
+        if (warp < 3) dst[a.offw[0] + tid] = small1;  // dW1[o][c] at o*3 + c = tid
+        if (shared_sample) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) is_last = (atomicAdd(a.counters + b, 1u) == (unsigned)(c_hi - c_lo));
+            __syncthreads();
+            if (is_last) {
+                __threadfence();
+                // slot of sample b in every contributing CTA's partial block (64-bit divisions hoisted out of the fold)
+                const int ncontrib = c_hi - c_lo + 1;
+                for (int q = tid; q < ncontrib; q += TN_THREADS) {
+                    const int c = c_lo + q;
+                    const int fs = (int)(((long long)c * TT / G) / ntiles);
+                    slot_of[q] = (unsigned)(c * a.S + (b - fs));
+                }
+                __syncthreads();
+                float *g = a.gweights + (size_t)b * a.W;
+                for (int i = tid; i < a.W; i += TN_THREADS) {
+                    float v = 0.f;
+                    for (int q = 0; q < ncontrib; ++q) v += __ldcg(a.partial + (size_t)slot_of[q] * a.W + i);  // ascending CTA order
+                    g[i] = v;
+                }
+            }
+            __syncthreads();  // is_last reusable
+        }
+    };
 
-    tn_stage_biases(a, wg, bs, tid);
-    const int ntiles = (a.N + TN_T - 1) / TN_T;
-    for (int t = s; t < ntiles; t += a.S) {
+    reset_acc();
+    int cur = -1;
+    for (long long f = f0; f < f1; ++f) {
+        const int b = (int)(f / ntiles), t = (int)(f - (long long)b * ntiles);
+        if (b != cur) {
+            if (cur >= 0) {
+                flush(cur);
+                reset_acc();
+            }
+            __syncthreads();  // every reader of the old biases is done
+            tn_stage_biases(a, a.weights + (size_t)b * a.W, bs, tid);
+            cur = b;
+        }
+        const float *wg = a.weights + (size_t)b * a.W;
+        const float *pts = a.points + (size_t)b * a.pstride;
+        const float *gy = a.gout + (size_t)b * a.N * 3;
         const int n0 = t * TN_T;
         __syncthreads();  // previous tile fully consumed
         tn_load_xyz_tile(pts, n0, a.N, X, tid);
-        if (a.channels_first) tn_load_cf_tile(gy, n0, a.N, G, tid);
-        else tn_load_xyz_tile(gy, n0, a.N, G, tid);
+        if (a.channels_first) tn_load_cf_tile(gy, n0, a.N, G5, tid);
+        else tn_load_xyz_tile(gy, n0, a.N, G5, tid);
         tn_stage_weights<3, C1>(wg + a.offw[0], wb0, tid);
         __syncthreads();
         // ---- recompute the forward of this tile ----
@@ -405,10 +475,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_backward_kernel(const TNArgs
         tn_layer_fwd<C3, C4, 4, true>(A3, A4, wb1, bs + C1 + C2 + C3, warp, lane);
         __syncthreads();
         // ---- layer 5: Z5 = dY ----
-        if (warp < 6) small0 += tn_row_dot(G + (tid >> 6) * TN_TP, A4 + (tid & 63) * TN_TP);        // dW5[o][k], o = tid/64
-        else if (warp == 6) { if (lane < 3) small0 += tn_row_sum(G + lane * TN_TP); }                 // db5
+        if (warp < 6) small0 += tn_row_dot(G5 + (tid >> 6) * TN_TP, A4 + (tid & 63) * TN_TP);       // dW5[o][k], o = tid/64
+        else if (warp == 6) { if (lane < 3) small0 += tn_row_sum(G5 + lane * TN_TP); }                // db5
         __syncthreads();
-        tn_layer_dgrad<C4, 3, 4, true>(G, A4, wb0, warp, lane);  // A4 <- Z4     (wb1 still holds W4)
+        tn_layer_dgrad<C4, 3, 4, true>(G5, A4, wb0, warp, lane);  // A4 <- Z4     (wb1 still holds W4)
         __syncthreads();
         // ---- layer 4 ----
         tn_stage_weights<C2, C3>(wg + a.offw[2], wb0, tid);
@@ -445,39 +515,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_backward_kernel(const TNArgs
             }
         }
     }
-
-    // ---- write this CTA's partial dW (flat weight order) ----
-    float *dst = (a.S > 1) ? a.partial + ((size_t)b * a.S + s) * a.W : a.gweights + (size_t)b * a.W;
-    tn_store_wgrad<C4, C3, 4, 4>(dW4, dst + a.offw[3], warp, lane);
-    tn_store_wgrad<C3, C2, 4, 4>(dW3, dst + a.offw[2], warp, lane);
-    tn_store_wgrad<C2, C1, 2, 2>(dW2, dst + a.offw[1], warp, lane);
-    if (warp < 6) dst[a.offw[4] + tid] = small0;  // dW5[o][k] at o*64 + k = tid
-    else if (warp == 6) { if (lane < 3 && a.offb[4] >= 0) dst[a.offb[4] + lane] = small0; }
-    else if (warp <= 8) { if (a.offb[3] >= 0) dst[a.offb[3] + (warp - 7) * 32 + lane] = small0; }
-    else if (warp <= 12) { if (a.offb[2] >= 0) dst[a.offb[2] + (warp - 9) * 32 + lane] = small0; }
-    else if (warp <= 14) { if (a.offb[1] >= 0) dst[a.offb[1] + (warp - 13) * 32 + lane] = small0; }
-    else { if (a.offb[0] >= 0) dst[a.offb[0] + lane] = small0; }
-    if (warp < 3) dst[a.offw[0] + tid] = small1;  // dW1[o][c] at o*3 + c = tid
-
-    if (a.S > 1) {
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned prev = atomicAdd(a.counters + b, 1u);
-            is_last = (prev == (unsigned)a.S - 1);
-        }
-        __syncthreads();
-        if (is_last) {
-            __threadfence();
-            const float *src = a.partial + (size_t)b * a.S * a.W;
-            float *g = a.gweights + (size_t)b * a.W;
-            for (int i = tid; i < a.W; i += TN_THREADS) {
-                float v = __ldcg(src + i);
-                for (int q = 1; q < a.S; ++q) v += __ldcg(src + (size_t)q * a.W + i);  // ascending CTA order: deterministic
-                g[i] = v;
-            }
-        }
-    }
+    if (cur >= 0) flush(cur);
 }
 
 // ---- generic path: any widths ------------------------------------------------------------------------
@@ -629,13 +667,14 @@ static int tn_fill_offsets(TNArgs &a, int n_layers, const int *dims, int use_bia
     return HP_OK;
 }
 
-// CTAs per sample for the fast path: fill the SMs once, never more CTAs than tiles
-static int tn_split(int b, int n) {
-    const int ntiles = (n + TN_T - 1) / TN_T;
-    int S = sm_count() / (b > 0 ? b : 1);
-    if (S < 1) S = 1;
-    if (S > ntiles) S = ntiles;
-    return S;
+// fast-path launch geometry: one CTA per SM (never more CTAs than tiles); slots = most samples one CTA's range can touch
+static void tn_geometry(int b, int n, int &grid, int &slots) {
+    const long long ntiles = (n + TN_T - 1) / TN_T, TT = (long long)b * ntiles;
+    const long long sms = sm_count();
+    grid = (int)(TT < sms ? TT : sms);
+    if (grid > TN_MAX_GRID) grid = TN_MAX_GRID;
+    const long long per = (TT + grid - 1) / grid;  // tiles per CTA, upper bound
+    slots = (int)((per + ntiles - 2) / ntiles + 1);
 }
 
 static int tn_generic_args(TNGenArgs &g, int n_layers, const int *dims, size_t &smem_fwd, size_t &smem_bwd) {
@@ -687,9 +726,8 @@ extern "C" int hp_target_network_forward(int b, int n, int n_layers, const int *
     a.weights = weights, a.points = points, a.pstride = points_batch_stride, a.out = out;
     a.B = b, a.N = n, a.channels_first = channels_first ? 1 : 0;
     if (tn_is_fast_shape(n_layers, dims)) {
-        a.S = tn_split(b, n);
-        const long long grid = (long long)b * a.S;
-        HP_REQUIRE(grid <= 0x7fffffffLL, "hp_target_network_forward: batch too large");
+        int grid;
+        tn_geometry(b, n, grid, a.S);
         static SmemAttrCache attr;
         HP_CUDA(ensure_dynamic_smem(tn_forward_kernel, TNF_SMEM, attr));
         tn_forward_kernel<<<(unsigned)grid, TN_THREADS, TNF_SMEM, stream>>>(a);
@@ -716,8 +754,9 @@ extern "C" size_t hp_target_network_backward_workspace_bytes(int b, int n, int n
     if (W <= 0) return 16;
     size_t bytes = (size_t)b * sizeof(unsigned int) + 16;  // per-sample arrival counters
     if (tn_is_fast_shape(n_layers, dims)) {
-        const int S = tn_split(b, n);
-        if (S > 1) bytes += (size_t)b * S * (size_t)W * sizeof(float);
+        int grid, slots;
+        tn_geometry(b, n, grid, slots);
+        bytes += (size_t)grid * slots * (size_t)W * sizeof(float);
     }
     return bytes;
 }
@@ -747,23 +786,20 @@ extern "C" int hp_target_network_backward(int b, int n, int n_layers, const int 
     a.gweights = grad_weights, a.gpoints = grad_points;
     a.B = b, a.N = n, a.channels_first = channels_first ? 1 : 0;
     if (tn_is_fast_shape(n_layers, dims)) {
-        a.S = tn_split(b, n);
+        int grid;
+        tn_geometry(b, n, grid, a.S);
         const size_t need = hp_target_network_backward_workspace_bytes(b, n, n_layers, dims, use_bias);
-        if (a.S > 1) {
-            HP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
-                       "hp_target_network_backward: workspace null or not 16-byte aligned");
-            if (workspace_bytes < need) {
-                set_error("hp_target_network_backward: workspace %zu < required %zu bytes", workspace_bytes, need);
-                return HP_ERR_WORKSPACE;
-            }
-            a.counters = reinterpret_cast<unsigned int *>(workspace);
-            a.partial = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(workspace) +
-                                                  (((size_t)b * sizeof(unsigned int) + 15) & ~(size_t)15));
-            // the counter region moves with b, so a reused workspace cannot be trusted to be zero there
-            HP_CUDA(cudaMemsetAsync(a.counters, 0, (size_t)b * sizeof(unsigned int), stream));
+        HP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+                   "hp_target_network_backward: workspace null or not 16-byte aligned");
+        if (workspace_bytes < need) {
+            set_error("hp_target_network_backward: workspace %zu < required %zu bytes", workspace_bytes, need);
+            return HP_ERR_WORKSPACE;
         }
-        const long long grid = (long long)b * a.S;
-        HP_REQUIRE(grid <= 0x7fffffffLL, "hp_target_network_backward: batch too large");
+        a.counters = reinterpret_cast<unsigned int *>(workspace);
+        a.partial = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(workspace) +
+                                              (((size_t)b * sizeof(unsigned int) + 15) & ~(size_t)15));
+        // the counter region moves with b, so a reused workspace cannot be trusted to be zero there
+        HP_CUDA(cudaMemsetAsync(a.counters, 0, (size_t)b * sizeof(unsigned int), stream));
         static SmemAttrCache attr0, attr1;
         if (grad_points) {
             HP_CUDA(ensure_dynamic_smem(tn_backward_kernel<true>, TNB_SMEM, attr1));
