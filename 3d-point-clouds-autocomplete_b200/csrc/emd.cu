@@ -94,8 +94,10 @@ __global__ void __launch_bounds__(THREADS) emd_pass_kernel(const EmdArgs a) {
     float *st = a.state + (size_t)pair * 2 * (n + m);
     const float *colw = (MODE == 1) ? st + n : (MODE == 2) ? st + n + m : st + n + m + n;  // remainR | ratioL | ratioR
     const float level = -powf(4.0f, (float)a.j);  // approxmatch.cu:56, evaluated on the device like the reference
-    const f32x2 level2 = pack2(level, level);
-    const f32x2 log2e2 = pack2(1.4426950216293334961f, 1.4426950216293334961f);
+    // The reference evaluates __expf(level*d) as ex2((d*level)*log2e) with two roundings.  level is a power of two, so
+    // d*level is exact and (d*level)*log2e == d*(level*log2e) bit for bit (level*log2e is exact as well): ONE multiply.
+    const float scale = level * 1.4426950216293334961f;
+    const f32x2 scale2 = pack2(scale, scale);
 
     f32x2 qx[RQ], qy[RQ], qz[RQ];
     float acc[RQ], rl[RQ], cost[RQ];
@@ -136,8 +138,8 @@ __global__ void __launch_bounds__(THREADS) emd_pass_kernel(const EmdArgs a) {
                 const f32x2 d01 = sqdist_exact2(qx[q], qy[q], qz[q], cx.x, cy.x, cz.x);
                 const f32x2 d23 = sqdist_exact2(qx[q], qy[q], qz[q], cx.y, cy.y, cz.y);
                 float t0, t1, t2, t3;
-                unpack2(mul2(mul2(d01, level2), log2e2), t0, t1);  // (d*level)*log2e, two roundings like the reference
-                unpack2(mul2(mul2(d23, level2), log2e2), t2, t3);
+                unpack2(mul2(d01, scale2), t0, t1);
+                unpack2(mul2(d23, scale2), t2, t3);
                 const float e0 = ex2_approx(t0), e1 = ex2_approx(t1), e2 = ex2_approx(t2), e3 = ex2_approx(t3);
                 if (MODE != 3) {
                     acc[q] = __fmaf_rn(e0, w.x, acc[q]);
@@ -416,16 +418,29 @@ static int run_auction(EmdArgs a, cudaStream_t stream) {
     return HP_OK;
 }
 
-// column split for the workspace-backed path: enough CTAs to fill the GPU even for a single cloud pair
+// Column split for the workspace-backed path.  Work items = pairs x row tiles x column slices, all of equal cost; the
+// slice count is chosen so that the items spread evenly over the SMs (items / (ceil(items/SMs)*SMs) close to 1: the
+// reference shape B=32, 2048^2 gets 8 slices -> 1024 items = 6.9 per SM instead of 512 = 3.5 per SM), preferring fewer
+// slices on ties.  Returns the number of NON-EMPTY slices for spans rounded up to whole shared-memory chunks.
 static int choose_split(int pairs, int n, int m) {
-    const long long want = (long long)sm_count() * 8;
+    const int sms = sm_count();
     const int big = n > m ? n : m, small_ = n > m ? m : n;
-    long long base = (long long)pairs * ((small_ + 255) / 256);  // CTAs at the smallest useful row tile (64x4)
-    int S = (int)((want + base - 1) / base);
     const int maxS = (big + EMD_CC - 1) / EMD_CC;
-    if (S > maxS) S = maxS;
-    if (S < 1) S = 1;
-    return S;
+    const long long row_tiles = (small_ + 511) / 512;  // the 128x4 row tile launch_pass_auto prefers
+    double best_eff = -1.0;
+    int best = 1;
+    for (int S = 1; S <= maxS; ++S) {
+        const int span = ((big + S - 1) / S + EMD_CC - 1) / EMD_CC * EMD_CC;
+        const int real = (big + span - 1) / span;
+        if (real != S) continue;  // rounding left an empty slice: skip this count
+        const long long items = (long long)pairs * row_tiles * S;
+        const long long waves = (items + sms - 1) / sms;
+        double eff = (double)items / (double)(waves * sms);
+        if (items < 2LL * sms) eff *= 0.5 * (double)items / (2.0 * sms) + 0.5;  // too few items: poor latency hiding
+        if (eff > best_eff + 0.02) best_eff = eff, best = S;
+        if (items >= 16LL * sms) break;
+    }
+    return best;
 }
 
 }  // namespace hp
