@@ -37,6 +37,7 @@ struct EmdArgs {
     float *partial;               // [pairs][S][rstride] row partial sums (column-split mode) or nullptr
     float *match;                 // [pairs][m][n] or nullptr
     float *costpart;              // [pairs][cp_stride] per-CTA cost partials or nullptr
+    float *hist;                  // [pairs][9][n+m] per-level ratioL[n] ratioR[m] (match written once at the end) or nullptr
     int n, m, pairs;
     int S, span;                  // column split: slice s covers columns [s*span, min(nc,(s+1)*span))
     int row_tiles, rstride;
@@ -58,15 +59,18 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 }
 
 template <int MODE>
-__device__ __forceinline__ void emd_row_epilogue(float acc, float *st, int n, int m, int r) {
+__device__ __forceinline__ void emd_row_epilogue(float acc, float *st, int n, int m, int r, float *hist_level = nullptr) {
     float *remainL = st, *remainR = st + n, *ratioL = st + n + m, *ratioR = st + n + m + n;
     if (MODE == 1) {
-        ratioL[r] = remainL[r] / acc;  // acc already includes the 1e-9 start (approxmatch.cu:68,92)
+        const float v = remainL[r] / acc;  // acc already includes the 1e-9 start (approxmatch.cu:68,92)
+        ratioL[r] = v;
+        if (hist_level) hist_level[r] = v;
     } else if (MODE == 2) {
         const float rem = remainR[r];
         const float sumr = acc * rem;                                   // approxmatch.cu:137
         const float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);    // :138
         ratioR[r] = consumption * rem;                                  // :139
+        if (hist_level) hist_level[n + r] = consumption * rem;
         remainR[r] = fmaxf(0.0f, rem - sumr);                           // :140
     } else {
         remainL[r] = fmaxf(0.0f, remainL[r] - acc);                     // :193
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(THREADS) emd_pass_kernel(const EmdArgs a) {
     for (int q = 0; q < RQ; ++q) {
         if (row[q] < nr) {
             if (SPLIT) a.partial[((size_t)pair * a.S + s) * a.rstride + row[q]] = acc[q];
-            else emd_row_epilogue<MODE>(acc[q], st, n, m, row[q]);
+            else emd_row_epilogue<MODE>(acc[q], st, n, m, row[q], a.hist ? a.hist + ((size_t)pair * 9 + a.level_index) * (n + m) : nullptr);
         }
     }
     if (COST) {
@@ -214,7 +218,8 @@ __global__ void emd_combine_kernel(const EmdArgs a) {
         const float *p = a.partial + (size_t)pair * a.S * a.rstride + r;
         float acc = p[0];
         for (int s = 1; s < a.S; ++s) acc += p[(size_t)s * a.rstride];
-        emd_row_epilogue<MODE>(acc, a.state + (size_t)pair * 2 * (a.n + a.m), a.n, a.m, r);
+        emd_row_epilogue<MODE>(acc, a.state + (size_t)pair * 2 * (a.n + a.m), a.n, a.m, r,
+                               a.hist ? a.hist + ((size_t)pair * 9 + a.level_index) * (a.n + a.m) : nullptr);
     }
 }
 
@@ -348,6 +353,69 @@ __global__ void matchcostgrad2_kernel(int b, int n, int m, const float *__restri
     }
 }
 
+
+// ---- match written ONCE (hp_approxmatch_ws): match[l][k] = sum over the 9 levels, in level order, of
+//      fma(ratioL_lvl[k] * e_lvl(k,l), ratioR_lvl[l], .)  -- the same fma chain the reference builds with nine
+//      read-modify-write sweeps over the [b,m,n] matrix (approxmatch.cu:181-188), from the per-level ratios the
+//      auction recorded.  9 more ex2 per pair, but 4*n*m bytes of HBM traffic per cloud instead of 9*2*4*n*m.
+constexpr int MW_THREADS = 128, MW_RQ = 2, MW_LC = 32;  // k rows per CTA = 256, l columns staged per chunk = 32
+
+__global__ void __launch_bounds__(MW_THREADS) emd_match_write_kernel(const EmdArgs a, int l_span) {
+    __shared__ float cx[MW_LC], cy[MW_LC], cz[MW_LC], rr[9][MW_LC];
+    const int tid = threadIdx.x;
+    const int n = a.n, m = a.m;
+    const int ktiles = (n + MW_THREADS * MW_RQ - 1) / (MW_THREADS * MW_RQ);
+    int bid = blockIdx.x;
+    const int kt = bid % ktiles;
+    bid /= ktiles;
+    const int nls = (m + l_span - 1) / l_span;
+    const int ls = bid % nls;
+    const int pair = bid / nls;
+    const float *__restrict__ X1 = a.first + (size_t)pair * n * 3;
+    const float *__restrict__ X2 = a.second + (size_t)pair * m * 3;
+    const float *__restrict__ H = a.hist + (size_t)pair * 9 * (n + m);
+    float *__restrict__ M = a.match + (size_t)pair * n * m;
+    float scale[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) scale[i] = -powf(4.0f, (float)(7 - i)) * 1.4426950216293334961f;
+    float qx[MW_RQ], qy[MW_RQ], qz[MW_RQ], rl[MW_RQ][9];
+    int k[MW_RQ];
+#pragma unroll
+    for (int q = 0; q < MW_RQ; ++q) {
+        k[q] = kt * (MW_THREADS * MW_RQ) + q * MW_THREADS + tid;
+        const bool ok = k[q] < n;
+        qx[q] = ok ? __ldg(X1 + (size_t)k[q] * 3 + 0) : 0.f, qy[q] = ok ? __ldg(X1 + (size_t)k[q] * 3 + 1) : 0.f;
+        qz[q] = ok ? __ldg(X1 + (size_t)k[q] * 3 + 2) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) rl[q][i] = ok ? __ldg(H + (size_t)i * (n + m) + k[q]) : 0.f;
+    }
+    const int l_begin = ls * l_span, l_end = min(m, l_begin + l_span);
+    for (int l0 = l_begin; l0 < l_end; l0 += MW_LC) {
+        __syncthreads();
+        for (int i = tid; i < MW_LC * 12; i += MW_THREADS) {
+            const int c = i % MW_LC, f = i / MW_LC, l = l0 + c;
+            float v = 0.f;
+            if (l < l_end) v = (f < 3) ? __ldg(X2 + (size_t)l * 3 + f) : __ldg(H + (size_t)(f - 3) * (n + m) + n + l);
+            if (f == 0) cx[c] = v;
+            else if (f == 1) cy[c] = v;
+            else if (f == 2) cz[c] = v;
+            else rr[f - 3][c] = v;
+        }
+        __syncthreads();
+        const int cnt = min(MW_LC, l_end - l0);
+        for (int c = 0; c < cnt; ++c) {
+#pragma unroll
+            for (int q = 0; q < MW_RQ; ++q) {
+                const float d = sqdist_exact(qx[q], qy[q], qz[q], cx[c], cy[c], cz[c]);
+                float mv = 0.f;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) mv = __fmaf_rn(__fmul_rn(rl[q][i], ex2_approx(__fmul_rn(d, scale[i]))), rr[i][c], mv);
+                if (k[q] < n) M[(size_t)(l0 + c) * n + k[q]] = mv;
+            }
+        }
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 template <int MODE, int RQ, int THREADS, bool SPLIT, bool MATCH, bool COST>
 static int launch_pass(EmdArgs a, cudaStream_t stream) {
@@ -458,6 +526,51 @@ extern "C" int hp_approxmatch(int b, int n, int m, const float *xyz1, const floa
     a.state = temp, a.partial = nullptr, a.match = match, a.costpart = nullptr;
     a.n = n, a.m = m, a.pairs = b, a.S = 1, a.rstride = 0, a.cp_stride = 0;
     return run_auction<false, true, false>(a, (cudaStream_t)stream);
+}
+
+extern "C" size_t hp_approxmatch_workspace_bytes(int b, int n, int m) {
+    if (b <= 0 || n <= 0 || m <= 0) return 16;
+    return (size_t)b * 9 * ((size_t)n + m) * sizeof(float) + 64;  // per-level ratioL | ratioR
+}
+
+extern "C" int hp_approxmatch_ws(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *temp,
+                                 void *workspace, size_t workspace_bytes, void *stream_v) {
+    HP_REQUIRE(b >= 0 && n >= 0 && m >= 0, "hp_approxmatch_ws: negative size (b=%d n=%d m=%d)", b, n, m);
+    if (b == 0 || (n == 0 && m == 0)) return HP_OK;
+    HP_REQUIRE(n > 0 && m > 0, "hp_approxmatch_ws: one point set is empty (n=%d m=%d): the reference divides n/m", n, m);
+    HP_REQUIRE(xyz1 && xyz2 && match && temp && workspace, "hp_approxmatch_ws: null pointer");
+    HP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "hp_approxmatch_ws: workspace must be 16-byte aligned");
+    if (workspace_bytes < hp_approxmatch_workspace_bytes(b, n, m)) {
+        set_error("hp_approxmatch_ws: workspace %zu < required %zu bytes", workspace_bytes, hp_approxmatch_workspace_bytes(b, n, m));
+        return HP_ERR_WORKSPACE;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    EmdArgs a = {};
+    a.first = xyz1, a.second = xyz2, a.ia = nullptr, a.ib = nullptr;
+    a.state = temp;  // remainL | remainR | ratioL | ratioR, returned like the reference's temp
+    // No column split here: every row sum runs over ALL columns in ascending order like the reference's thread does.
+    // The 9-level feedback amplifies a different association to ~1e-3 on the gradients (measured), which would miss
+    // the 1e-5 bar; the match-free metrics path (hp_emd_cost_pairs) may split because the COST stays within 1e-6.
+    a.partial = nullptr;
+    a.hist = reinterpret_cast<float *>(workspace);
+    a.match = match, a.costpart = nullptr;
+    a.n = n, a.m = m, a.pairs = b, a.S = 1, a.rstride = 0, a.cp_stride = 0;
+    int rc = run_auction<false, false, false>(a, stream);
+    if (rc != HP_OK) return rc;
+    // one sweep over match: k tiles x l slices sized for ~8 CTAs per SM
+    const int ktiles = (n + MW_THREADS * MW_RQ - 1) / (MW_THREADS * MW_RQ);
+    long long want = (long long)sm_count() * 8;
+    long long slices = (want + (long long)b * ktiles - 1) / ((long long)b * ktiles);
+    const long long max_slices = (m + MW_LC - 1) / MW_LC;
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    int l_span = (int)(((m + slices - 1) / slices + MW_LC - 1) / MW_LC * MW_LC);
+    const long long nls = (m + l_span - 1) / l_span;
+    const long long grid = (long long)b * nls * ktiles;
+    HP_REQUIRE(grid <= 0x7fffffffLL, "hp_approxmatch_ws: grid too large; split the batch");
+    emd_match_write_kernel<<<(unsigned)grid, MW_THREADS, 0, stream>>>(a, l_span);
+    HP_LAUNCH_CHECK("emd_match_write_kernel");
+    return HP_OK;
 }
 
 extern "C" size_t hp_emd_cost_workspace_bytes(int pairs, int n, int m) {

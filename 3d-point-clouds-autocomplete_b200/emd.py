@@ -35,10 +35,13 @@ def ApproxMatch(set_d: torch.Tensor, set_q: torch.Tensor):
     dev = set_d.device
     match = torch.empty((b, m, n), dtype=torch.float32, device=dev)
     temp = torch.empty((b, (n + m) * 2), dtype=torch.float32, device=dev)
+    lib = _native.load()
     with on_device_of(set_d) as stream:
-        rc = _native.load().hp_approxmatch(b, n, m, set_d.data_ptr(), set_q.data_ptr(), match.data_ptr(),
-                                           temp.data_ptr(), stream)
-    _native.check(rc, "hp_approxmatch")
+        nbytes = lib.hp_approxmatch_workspace_bytes(b, n, m)
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)  # per call: freed (stream-ordered) on return
+        rc = lib.hp_approxmatch_ws(b, n, m, set_d.data_ptr(), set_q.data_ptr(), match.data_ptr(), temp.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), stream)
+    _native.check(rc, "hp_approxmatch_ws")
     return [match, temp]
 
 
