@@ -124,3 +124,39 @@ class TargetNetworkStepGraph:
     def replay(self):
         self.graph.replay()
         return self.out, self.grad_weights
+
+
+class HotPathStepGraph:
+    """The point-set hot path of one HyperPocket training step (BASELINE config C4 without the encoder / hypernetwork):
+
+        rec  = TargetNetwork_b(points_b)            for every sample b     (model/full_model.py:67-74)
+        loss = loss_coef * ChamferLoss(gt, rec)                            (core/epoch_loops.py:25-26)
+        d loss / d weights                                                  (what autograd hands the hypernetwork)
+
+    as one CUDA graph: fused TargetNetwork forward -> ring Chamfer forward -> gather Chamfer backward -> fused
+    TargetNetwork backward.  Static inputs: ``weights`` [B,W], ``points`` [B,N,3], ``gt`` [B,N,3]; outputs refreshed in
+    place: ``rec`` [B,N,3], ``loss`` [1] (unscaled Chamfer sum), ``grad_weights`` [B,W]."""
+
+    def __init__(self, batch: int, n: int, layer_out_channels, use_bias: bool, device, loss_coef: float = 0.05):
+        self.device = torch.device(device)
+        W = target_network_num_weights(layer_out_channels, use_bias)
+        loc = tuple(int(c) for c in layer_out_channels)
+        with torch.cuda.device(self.device):
+            self.weights = torch.randn(batch, W, device=self.device) * 0.1
+            self.points = torch.rand(batch, n, 3, device=self.device) - 0.5
+            self.gt = torch.rand(batch, n, 3, device=self.device) - 0.5
+            self._coef = torch.full((), float(loss_coef), device=self.device)
+
+            def step():
+                rec = target_network_forward(self.weights, self.points, loc, use_bias, False)
+                loss, _d1, i1, _d2, i2, inv = chamfer_forward(self.gt, rec, want_inverse=True)
+                _g_gt, g_rec = chamfer_backward(self.gt, rec, i1, i2, self._coef, inv)
+                gw, _ = target_network_backward(self.weights, self.points, g_rec, loc, use_bias, False)
+                return rec, loss, gw
+
+            self.graph, (self.rec, self.loss, self.grad_weights), self._stream = _capture(step, self.device)
+            self.launches_per_replay = 5
+
+    def replay(self):
+        self.graph.replay()
+        return self.rec, self.loss, self.grad_weights

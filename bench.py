@@ -39,6 +39,7 @@ if REPO not in sys.path:
 B, N, M = 32, 2048, 2048
 PAIRS_PER_STEP = 2 * B * N * M  # ordered (query, candidate) evaluations, both directions
 FLOP_PER_PAIR = 8  # 3 sub, 3 mul, 2 add
+NCU_RING_DRAM_BYTES = 1604608  # profiles/r01_ncu_full_nn_ring.txt (per launch)
 METRIC = "chamfer_point_pairs_per_s"
 UNIT = "pairs/s"
 WORKLOAD = f"chamfer_nn_distance_fwd+bwd_B{B}_N{N}_M{M}_fp32"
@@ -195,6 +196,52 @@ def _other_paths(torch, hp, dev, fp32_peak, mufu_peak, flush, stream, barrier):
     flop = (37440.0 + 74688.0) * tb * tn  # algorithmic: fwd + bwd (the in-kernel forward recompute is not counted)
     out["target_network_fwd+bwd_B64_N2048"] = {"ms": ms, "algorithmic_tflops": flop / ms / 1e9, "frac_fp32_peak": flop / (ms * 1e-3) / fp32_peak,
                                                "executed_frac_fp32_peak": (flop + 37440.0 * tb * tn) / (ms * 1e-3) / fp32_peak}
+    hpg = hp.HotPathStepGraph(tb, tn, LOC, True, dev)
+    hpg.weights.copy_(tng.weights)
+    ms = statistics.mean(_events_timed(torch, hpg.replay, 20, 3, flush, stream, barrier))
+    out["c4_hot_path_step_B64_N2048"] = {
+        "ms": ms, "what": "fused TargetNetwork fwd -> Chamfer fwd (ring) -> Chamfer bwd (gather) -> TargetNetwork bwd, one CUDA graph "
+                          "(config C4 without encoder / hypernetwork)",
+        "algorithmic_tflops": ((37440.0 + 74688.0) * tb * tn + 16.0 * tb * tn * tn) / ms / 1e9}
+    # the reference's op sequence for the same hot path on this GPU: per-sample torch loop (model/full_model.py:70-74,
+    # model/target_network.py:31-38) + expansion-form Chamfer via three bmm and two min (losses/champfer_loss.py:11-35)
+    def torch_chamfer(preds, gts):
+        xx, yy, zz = torch.bmm(gts, gts.transpose(2, 1)), torch.bmm(preds, preds.transpose(2, 1)), torch.bmm(gts, preds.transpose(2, 1))
+        rx = torch.diagonal(xx, dim1=1, dim2=2).unsqueeze(1).expand_as(zz.transpose(2, 1))
+        ry = torch.diagonal(yy, dim1=1, dim2=2).unsqueeze(1).expand_as(zz)
+        P = rx.transpose(2, 1) + ry - 2 * zz
+        return torch.min(P, 1)[0].sum() + torch.min(P, 2)[0].sum()
+
+    wref = tng.weights.detach().clone().requires_grad_(True)
+    pts, gt = hpg.points, hpg.gt
+    dims = [3] + LOC + [3]
+
+    def ref_step():
+        wref.grad = None
+        outs = []
+        for s_ in range(tb):
+            h, off = pts[s_], 0
+            for l in range(5):
+                i_, o_ = dims[l], dims[l + 1]
+                Wl = wref[s_, off:off + i_ * o_].view(o_, i_)
+                off += i_ * o_
+                h = torch.mm(h, Wl.t()) + wref[s_, off:off + o_]
+                off += o_
+                if l < 4:
+                    h = torch.relu(h)
+            outs.append(h)
+        rec = torch.stack(outs)
+        (0.05 * torch_chamfer(rec, gt)).backward()
+
+    ref_step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        ref_step()
+    torch.cuda.synchronize(dev)
+    out["c4_hot_path_step_B64_N2048"]["reference_op_sequence_on_this_gpu_ms"] = (time.perf_counter() - t0) / 2 * 1e3
+    del wref
+    torch.cuda.empty_cache()
     eb = 32
     a = (torch.rand(eb, 2048, 3, generator=g) - 0.5).to(dev)
     b = (torch.rand(eb, 2048, 3, generator=g) - 0.5).to(dev)
@@ -344,7 +391,10 @@ def run_ours(args):
         roofline = {
             "bound": "fp32", "kernel": "nn_ring_kernel (+ nn_ring_unpack_kernel): Chamfer forward, both directions + loss",
             "achieved": achieved, "peak": fp32_peak / 1e12,
-            "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12),
+            "traffic": NCU_RING_DRAM_BYTES,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of nn_ring_kernel, ncu --set full capture "
+                              "profiles/r01_ncu_full_nn_ring.txt (inputs are 1.5 MiB; results stay in L2 for the unpack kernel)",
             "peak_source": "hp_measure_peak: register-resident FFMA/FFMA2 chains on all SMs, measured live in this run "
                            "(MEASURED_PEAKS.json has no FP32 entry; K=3 keeps the path off the tensor cores); "
                            "nominal 148*128*2*1.965 GHz = 74.4",
