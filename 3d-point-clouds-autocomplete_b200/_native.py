@@ -39,6 +39,7 @@ SIGNATURES = {
     "hp_chamfer_inverse_ints": (_sz, [_int, _int, _int, _int]),
     "hp_chamfer_forward_inv": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hp_chamfer_backward_inv": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hp_nndistancegrad_inv": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_approxmatch": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "hp_approxmatch_workspace_bytes": (_sz, [_int, _int, _int]),
     "hp_approxmatch_ws": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -77,21 +77,53 @@ def NNDistanceGrad(set_d, set_q, idx1, idx2, grad_dist1, grad_dist2):
 
 class NNDistanceFunction(Function):
     """nn_distance(seta, setb) -> (dist1, dist2); the indices ride on ctx like in
-    nn_distance.py:22-23.  Gradients flow to both point sets."""
+    nn_distance.py:22-23.  Gradients flow to both point sets.  When a gradient is needed the forward also emits the
+    inverse index maps, so the backward is the gather kernel (no sort)."""
 
     @staticmethod
     def forward(ctx, seta, setb):
-        dist1, idx1, dist2, idx2 = NNDistance(seta, setb)
+        check_points(seta, "set_d")
+        check_points(setb, "set_q")
+        check_same_device(seta, setb)
+        b, n, m = _batch_of(seta, setb, "NNDistance"), seta.size(1), setb.size(1)
+        lib = _native.load()
+        inv = None
+        if (seta.requires_grad or setb.requires_grad) and lib.hp_chamfer_inverse_ints(b, n, m, 1) > 0:
+            dev = seta.device
+            dist1 = torch.empty((b, n), dtype=torch.float32, device=dev)
+            idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+            dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
+            idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+            inv = (torch.empty(lib.hp_chamfer_inverse_ints(b, n, m, 1), dtype=torch.int32, device=dev),
+                   torch.empty(lib.hp_chamfer_inverse_ints(b, n, m, 2), dtype=torch.int32, device=dev))
+            with on_device_of(seta) as stream:
+                ws = zeroed_workspace(dev, stream, lib.hp_chamfer_workspace_bytes(b, n, m), "chamfer")
+                rc = lib.hp_chamfer_forward_inv(b, n, seta.data_ptr(), m, setb.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
+                                                dist2.data_ptr(), idx2.data_ptr(), None, inv[0].data_ptr(), inv[1].data_ptr(),
+                                                ws.data_ptr(), ws.numel(), stream)
+            _native.check(rc, "hp_chamfer_forward_inv")
+        else:
+            dist1, idx1, dist2, idx2 = NNDistance(seta, setb)
         ctx.save_for_backward(seta, setb)
-        ctx.idx1, ctx.idx2 = idx1, idx2
+        ctx.idx1, ctx.idx2, ctx.inv = idx1, idx2, inv
         return dist1, dist2
 
     @staticmethod
     def backward(ctx, grad_dist1, grad_dist2):
         seta, setb = ctx.saved_tensors
-        b = seta.size(0)
-        grada, gradb = NNDistanceGrad(seta, setb, ctx.idx1, ctx.idx2, grad_dist1.contiguous(),
-                                      grad_dist2.contiguous())
+        b, n, m = seta.size(0), seta.size(1), setb.size(1)
+        g1, g2 = grad_dist1.contiguous(), grad_dist2.contiguous()
+        if ctx.inv is not None and g1.dtype == torch.float32 and g2.dtype == torch.float32:
+            grada = torch.empty((b, n, 3), dtype=torch.float32, device=seta.device)
+            gradb = torch.empty((b, m, 3), dtype=torch.float32, device=seta.device)
+            with on_device_of(seta) as stream:
+                rc = _native.load().hp_nndistancegrad_inv(b, n, seta.data_ptr(), m, setb.data_ptr(), g1.data_ptr(),
+                                                          ctx.idx1.data_ptr(), g2.data_ptr(), ctx.idx2.data_ptr(),
+                                                          ctx.inv[0].data_ptr(), ctx.inv[1].data_ptr(), grada.data_ptr(),
+                                                          gradb.data_ptr(), stream)
+            _native.check(rc, "hp_nndistancegrad_inv")
+        else:
+            grada, gradb = NNDistanceGrad(seta, setb, ctx.idx1, ctx.idx2, g1, g2)
         if setb.size(0) != b:  # Q3 quirk: only the first `b` clouds of setb took part
             full = torch.zeros_like(setb)
             full[:b] = gradb

@@ -413,8 +413,8 @@ int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *
                            int *idx2, float *loss, int *inv1, int *inv2, void *workspace, cudaStream_t stream);
 bool nn_ring_inverse_supported(int n, int m);
 int nn_ring_backward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,
-                            const int *inv1, const int *inv2, const float *grad_loss, float *grad1, float *grad2,
-                            cudaStream_t stream);
+                            const int *inv1, const int *inv2, const float *grad_loss, const float *grad_dist1,
+                            const float *grad_dist2, float *grad1, float *grad2, cudaStream_t stream);
 
 // HP_NN_RING=0 selects the first-generation ordered-pair kernel (kept for A/B measurements and as the
 // workspace-free path of hp_nndistance).
@@ -592,7 +592,7 @@ extern "C" int hp_chamfer_forward_inv(int b, int n, const float *xyz1, int m, co
                                       float *dist2, int *idx2, float *loss, int *inv1, int *inv2, void *workspace,
                                       size_t workspace_bytes, void *stream) {
     HP_REQUIRE(b > 0 && n > 0 && m > 0, "hp_chamfer_forward_inv: sizes must be positive (b=%d n=%d m=%d)", b, n, m);
-    HP_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2 && loss && inv1 && inv2, "hp_chamfer_forward_inv: null pointer");
+    HP_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2 && inv1 && inv2, "hp_chamfer_forward_inv: null pointer");
     HP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
                "hp_chamfer_forward_inv: workspace null or not 16-byte aligned");
     if (workspace_bytes < hp_chamfer_workspace_bytes(b, n, m)) {
@@ -612,8 +612,18 @@ extern "C" int hp_chamfer_backward_inv(int b, int n, const float *xyz1, int m, c
     HP_REQUIRE(b > 0 && n > 0 && m > 0, "hp_chamfer_backward_inv: sizes must be positive (b=%d n=%d m=%d)", b, n, m);
     HP_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && inv1 && inv2 && grad_loss && grad_xyz1 && grad_xyz2,
                "hp_chamfer_backward_inv: null pointer");
-    return nn_ring_backward_launch(b, n, xyz1, m, xyz2, idx1, idx2, inv1, inv2, grad_loss, grad_xyz1, grad_xyz2,
-                                   (cudaStream_t)stream);
+    return nn_ring_backward_launch(b, n, xyz1, m, xyz2, idx1, idx2, inv1, inv2, grad_loss, nullptr, nullptr, grad_xyz1,
+                                   grad_xyz2, (cudaStream_t)stream);
+}
+
+extern "C" int hp_nndistancegrad_inv(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,
+                                     const int *idx1, const float *grad_dist2, const int *idx2, const int *inv1,
+                                     const int *inv2, float *grad_xyz1, float *grad_xyz2, void *stream) {
+    HP_REQUIRE(b > 0 && n > 0 && m > 0, "hp_nndistancegrad_inv: sizes must be positive (b=%d n=%d m=%d)", b, n, m);
+    HP_REQUIRE(xyz1 && xyz2 && grad_dist1 && idx1 && grad_dist2 && idx2 && inv1 && inv2 && grad_xyz1 && grad_xyz2,
+               "hp_nndistancegrad_inv: null pointer");
+    return nn_ring_backward_launch(b, n, xyz1, m, xyz2, idx1, idx2, inv1, inv2, nullptr, grad_dist1, grad_dist2, grad_xyz1,
+                                   grad_xyz2, (cudaStream_t)stream);
 }
 
 extern "C" int hp_nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,

@@ -593,7 +593,8 @@ int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *
 struct RingGradArgs {
     const float *set1, *set2;
     const int *idx1, *idx2, *inv1, *inv2;
-    const float *g;  // one device scalar (the loss gradient)
+    const float *g;          // one device scalar (the loss gradient), or nullptr when per-point gradients are given
+    const float *gd1, *gd2;  // per-point upstream gradients [b,n], [b,m] (nn_distance), or nullptr
     float *grad1, *grad2;
     int b, n, m;
 };
@@ -613,7 +614,10 @@ __global__ void __launch_bounds__(256) nn_grad_gather_kernel(const RingGradArgs 
     const int *__restrict__ inv = (side2 ? a.inv1 : a.inv2) + (size_t)cloud * (no + 2 * np);
     const int *__restrict__ perm = inv;
     const int pb = __ldg(inv + no + i), pe = __ldg(inv + no + np + i);
-    const float g2 = __ldg(a.g) * 2.f;
+    const float *__restrict__ g_own = a.g ? nullptr : (side2 ? a.gd2 : a.gd1) + (size_t)cloud * np;
+    const float *__restrict__ g_oth = a.g ? nullptr : (side2 ? a.gd1 : a.gd2) + (size_t)cloud * no;
+    const float gs = a.g ? __ldg(a.g) * 2.f : 0.f;
+    const float g2 = a.g ? gs : __ldg(g_own + i) * 2.f;
     const float px = __ldg(P + (size_t)i * 3 + 0), py = __ldg(P + (size_t)i * 3 + 1), pz = __ldg(P + (size_t)i * 3 + 2);
     const int j = min(max(__ldg(idx_own + i), 0), no - 1);
     float ax = g2 * (px - __ldg(O + (size_t)j * 3 + 0));
@@ -621,19 +625,21 @@ __global__ void __launch_bounds__(256) nn_grad_gather_kernel(const RingGradArgs 
     float az = g2 * (pz - __ldg(O + (size_t)j * 3 + 2));
     for (int p = pb; p < pe; ++p) {  // ascending source index: fixed summation order
         const int k = __ldg(perm + p);
-        ax += -(g2 * (__ldg(O + (size_t)k * 3 + 0) - px));
-        ay += -(g2 * (__ldg(O + (size_t)k * 3 + 1) - py));
-        az += -(g2 * (__ldg(O + (size_t)k * 3 + 2) - pz));
+        const float gk = a.g ? gs : __ldg(g_oth + k) * 2.f;
+        ax += -(gk * (__ldg(O + (size_t)k * 3 + 0) - px));
+        ay += -(gk * (__ldg(O + (size_t)k * 3 + 1) - py));
+        az += -(gk * (__ldg(O + (size_t)k * 3 + 2) - pz));
     }
     float *G = (side2 ? a.grad2 : a.grad1) + ((size_t)cloud * np + i) * 3;
     G[0] = ax, G[1] = ay, G[2] = az;
 }
 
 int nn_ring_backward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,
-                            const int *inv1, const int *inv2, const float *grad_loss, float *grad1, float *grad2,
-                            cudaStream_t stream) {
+                            const int *inv1, const int *inv2, const float *grad_loss, const float *grad_dist1,
+                            const float *grad_dist2, float *grad1, float *grad2, cudaStream_t stream) {
     RingGradArgs a;
     a.set1 = xyz1, a.set2 = xyz2, a.idx1 = idx1, a.idx2 = idx2, a.inv1 = inv1, a.inv2 = inv2, a.g = grad_loss;
+    a.gd1 = grad_dist1, a.gd2 = grad_dist2;
     a.grad1 = grad1, a.grad2 = grad2, a.b = b, a.n = n, a.m = m;
     const long long total = (long long)b * ((long long)n + m);
     const long long grid = (total + 255) / 256;

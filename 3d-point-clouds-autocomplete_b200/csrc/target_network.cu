@@ -221,22 +221,31 @@ __device__ __forceinline__ void tn_layer_wgrad(const float *__restrict__ Z, cons
     using M = TNWgradMap<OW, KW, TO, TK>;
     const float *zr = Z + M::o(warp, lane, 0) * TN_TP;
     const float *ar = A + M::k(warp, lane, 0) * TN_TP;
+    // per tile: even / odd point partial sums as fp32x2 pairs (FFMA2: half the issue slots), folded into the
+    // persistent scalar accumulators once per tile
+    f32x2 t2[TO * TK];
+#pragma unroll
+    for (int i = 0; i < TO * TK; ++i) t2[i] = pack2(0.f, 0.f);
 #pragma unroll 2
     for (int p0 = 0; p0 < TN_T; p0 += 4) {
-        float4 z[TO], a[TK];
+        ulonglong2 z[TO], a[TK];
 #pragma unroll
-        for (int j = 0; j < TO; ++j) z[j] = *reinterpret_cast<const float4 *>(zr + j * 8 * TN_TP + p0);
+        for (int j = 0; j < TO; ++j) z[j] = *reinterpret_cast<const ulonglong2 *>(zr + j * 8 * TN_TP + p0);
 #pragma unroll
-        for (int i = 0; i < TK; ++i) a[i] = *reinterpret_cast<const float4 *>(ar + i * 4 * TN_TP + p0);
+        for (int i = 0; i < TK; ++i) a[i] = *reinterpret_cast<const ulonglong2 *>(ar + i * 4 * TN_TP + p0);
 #pragma unroll
         for (int j = 0; j < TO; ++j)
 #pragma unroll
             for (int i = 0; i < TK; ++i) {
-                float s = acc[j * TK + i];
-                s = __fmaf_rn(z[j].x, a[i].x, s), s = __fmaf_rn(z[j].y, a[i].y, s);
-                s = __fmaf_rn(z[j].z, a[i].z, s), s = __fmaf_rn(z[j].w, a[i].w, s);
-                acc[j * TK + i] = s;
+                t2[j * TK + i] = fma2(z[j].x, a[i].x, t2[j * TK + i]);
+                t2[j * TK + i] = fma2(z[j].y, a[i].y, t2[j * TK + i]);
             }
+    }
+#pragma unroll
+    for (int i = 0; i < TO * TK; ++i) {
+        float lo, hi;
+        unpack2(t2[i], lo, hi);
+        acc[i] += lo + hi;
     }
 }
 template <int OW, int KW, int TO, int TK>

@@ -120,6 +120,11 @@ HP_API int hp_chamfer_forward_inv(int b, int n, const float *xyz1, int m, const 
 HP_API int hp_chamfer_backward_inv(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1,
                             const int *idx2, const int *inv1, const int *inv2, const float *grad_loss,
                             float *grad_xyz1, float *grad_xyz2, void *stream);
+/* hp_nndistancegrad (per-point upstream gradients, nn_distance.py:28-39) as the same gather over inverse maps from
+ * hp_chamfer_forward_inv (whose `loss` may be NULL when only distances and indices are wanted). */
+HP_API int hp_nndistancegrad_inv(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,
+                          const int *idx1, const float *grad_dist2, const int *idx2, const int *inv1,
+                          const int *inv2, float *grad_xyz1, float *grad_xyz2, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * (b) Approximate EMD (soft auction)

@@ -299,3 +299,18 @@ def test_gather_backward_from_forward_inverse_equals_sorting_backward(hp, oracle
         assert np.all(np.diff(keys) >= 0) and sorted(perm.tolist()) == list(range(m))
         cnt = np.bincount(i2[s].cpu().numpy(), minlength=n)
         assert np.array_equal(end - begin, cnt)
+
+
+def test_nn_distance_autograd_gather_path_equals_sorting_kernel(hp):
+    """nn_distance(...).backward with per-point upstream gradients: the gather over forward-emitted inverse maps
+    (hp_nndistancegrad_inv) must give the same bits as the self-contained hp_nndistancegrad."""
+    g = torch.Generator().manual_seed(8)
+    a = (torch.rand(3, 900, 3, generator=g) - 0.5).to(DEV).requires_grad_(True)
+    c = (torch.rand(3, 1300, 3, generator=g) - 0.5).to(DEV).requires_grad_(True)
+    w1, w2 = torch.randn(3, 900, generator=g).to(DEV), torch.randn(3, 1300, generator=g).to(DEV)
+    d1, d2 = hp.nn_distance(a, c)
+    ((d1 * w1).sum() + (d2 * w2).sum()).backward()
+    e1, i1, e2, i2 = hp.NNDistance(a.detach(), c.detach())
+    assert torch.equal(d1.detach(), e1) and torch.equal(d2.detach(), e2)
+    ga, gc = hp.NNDistanceGrad(a.detach(), c.detach(), i1, i2, w1, w2)
+    assert torch.equal(a.grad, ga) and torch.equal(c.grad, gc)
