@@ -17,7 +17,7 @@ from . import target_network  # noqa: F401
 from .target_network import (TargetNetwork, generate_points, generate_points_batched, target_network_backward,  # noqa: F401
                              target_network_forward, target_network_num_weights)
 from . import graphs  # noqa: F401
-from .graphs import ChamferStepGraph, HotPathStepGraph, TargetNetworkStepGraph  # noqa: F401
+from .graphs import ChamferHostPipeline, ChamferStepGraph, HotPathStepGraph, TargetNetworkStepGraph  # noqa: F401
 
 from . import metrics  # noqa: F401
 from .metrics import compute_all_metrics, pairwise_cd, pairwise_emd  # noqa: F401

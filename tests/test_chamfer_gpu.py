@@ -225,7 +225,8 @@ def _old_kernel_nndistance(hp, ad, cd):
     return d1, i1, d2, i2
 
 
-@pytest.mark.parametrize("b,n,m", [(2, 1500, 700), (1, 4097, 130), (3, 256, 2048), (2, 1025, 129), (4, 33, 1), (1, 3000, 3000)])
+@pytest.mark.parametrize("b,n,m", [(2, 1500, 700), (1, 4097, 130), (3, 256, 2048), (2, 1025, 129), (4, 33, 1), (1, 3000, 3000),
+                                   (600, 100, 4096)])  # the last one: deep grid -> several column rounds per CTA (R = 2)
 @pytest.mark.parametrize("kind", ["ties", "dupes", "uniform"])
 def test_ring_kernel_tie_rule_matches_ordered_kernel_and_oracle(hp, oracle, b, n, m, kind):
     """The warp-ring kernel meets candidates in a rotated order; its one-ulp bump must reproduce the reference's
