@@ -22,4 +22,6 @@ from .graphs import ChamferHostPipeline, ChamferStepGraph, HotPathStepGraph, Tar
 from . import metrics  # noqa: F401
 from .metrics import compute_all_metrics, pairwise_cd, pairwise_emd  # noqa: F401
 
+from . import evaluation  # noqa: F401
+
 __version__ = "0.1.0"

@@ -110,5 +110,12 @@ pcfg_off = {"target_network_input": {"normalization": {"enable": False, "type": 
 torch.manual_seed(1856)
 out["gp_plain"] = torch.stack([ref_generate_points(pcfg_off, 5, (96, 3)) for _ in range(2)]).numpy()
 
+# 6. KD-tree Chamfer of the evaluation scripts (utils/evaluation/chamfer.py:8-32), used by TMD
+from utils.evaluation.chamfer import compute_trimesh_chamfer  # noqa: E402
+
+tm = (torch.rand(5, 200, 3, generator=g) - 0.5).numpy()
+out["tm_pcs"] = tm
+out["tm_cd"] = np.array([[compute_trimesh_chamfer(tm[j], tm[k]) for k in range(5)] for j in range(5)])
+
 np.savez_compressed(os.path.join(HERE, "cpu_reference.npz"), **out)
 print("wrote", os.path.join(HERE, "cpu_reference.npz"), {k: v.shape for k, v in out.items()})

@@ -138,3 +138,11 @@ def test_generate_points_batched_matches_reference_sampler(golden_cpu):
     torch.manual_seed(1856)
     got = tn.generate_points_batched(cfg, 5, 2, (96, 3), pin=False)
     assert np.array_equal(got.numpy(), golden_cpu["gp_plain"])
+
+
+def test_trimesh_chamfer_restatement_matches_reference_kdtree(oracle, golden_cpu):
+    """oracle.trimesh_chamfer (brute force) vs the reference's KD-tree compute_trimesh_chamfer outputs."""
+    pcs = golden_cpu["tm_pcs"]
+    for j in range(5):
+        for k in range(5):
+            assert oracle.trimesh_chamfer(pcs[j], pcs[k]) == pytest.approx(float(golden_cpu["tm_cd"][j, k]), rel=1e-9, abs=1e-15)
