@@ -40,6 +40,27 @@ int sm_count() {
 // kind 3/5: the Chamfer inner loop (candidates from a shared-memory SoA table, 2 / 4 queries per
 //         thread): per candidate PAIR 3 FADD2 + FMUL2 + 2 FFMA2 + 1 FMNMX3 -> 8 algorithmic FLOP per eval
 // kind 4: the same loop in scalar form: per candidate 3 FADD + FMUL + 2 FFMA + 1 FMNMX
+// kind 6: legacy tensor path, mma.sync.aligned.m16n8k8 tf32 (8 independent accumulator tiles per warp) -> 2*16*8*8 FLOP each
+__global__ void __launch_bounds__(256) peak_mma_tf32_kernel(int iters, float seed, float *sink) {
+    float c[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = seed * i;
+    const unsigned a0 = __float_as_uint(seed), a1 = __float_as_uint(seed * 0.5f), a2 = __float_as_uint(seed * 0.25f),
+                   a3 = __float_as_uint(seed * 0.125f);
+    const unsigned b0 = __float_as_uint(1e-3f * (threadIdx.x & 3)), b1 = __float_as_uint(2e-3f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    if (s == 123.456f) sink[0] = s;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256) peak_kernel(int iters, float seed, float *sink) {
     const float x = seed * 0.999f, y = seed * 1e-3f;
@@ -156,7 +177,7 @@ extern "C" const char *hp_last_error_message(void) { return g_err; }
 
 extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *stream_v) {
     HP_REQUIRE(rate_host != nullptr, "hp_measure_peak: null result pointer");
-    HP_REQUIRE(kind >= 0 && kind <= 5 && iters > 0, "hp_measure_peak: bad kind/iters (%d, %d)", kind, iters);
+    HP_REQUIRE(kind >= 0 && kind <= 6 && iters > 0, "hp_measure_peak: bad kind/iters (%d, %d)", kind, iters);
     cudaStream_t stream = (cudaStream_t)stream_v;
     float *sink = nullptr;
     HP_CUDA(cudaMalloc(&sink, sizeof(float)));  // measurement helper only: not on the product path
@@ -173,6 +194,7 @@ extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *str
             case 2: peak_kernel<2><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
             case 3: peak_kernel<3><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
             case 4: peak_kernel<4><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
+            case 6: peak_mma_tf32_kernel<<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
             default: peak_kernel<5><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
         }
         HP_CUDA(cudaEventRecord(e1, stream));
@@ -192,6 +214,7 @@ extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *str
         case 1: per_thread_iter = 8 * 4.0; break;          // FLOP
         case 2: per_thread_iter = 8.0; break;              // ex2
         case 3: per_thread_iter = 1024 * 2 * 8.0; break;   // 1024 candidates x 2 queries x 8 algorithmic FLOP
+        case 6: per_thread_iter = 8 * 2.0 * 16 * 8 * 8 / 32.0; break;  // 8 mma per warp-iteration, 2048 FLOP each, per thread
         default: per_thread_iter = 1024 * 4 * 8.0; break;  // 1024 candidates x 4 queries x 8 algorithmic FLOP
     }
     *rate_host = threads_total * per_thread_iter * (double)iters / ((double)best_ms * 1e-3);
