@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
     __shared__ __align__(128) float cols_p[RF_COLS * 3];
     __shared__ __align__(16) float wmn_s[RF_WARPS][RF_COLS];  // per warp: running column minima ...
     __shared__ __align__(16) int wrot_s[RF_WARPS][RF_COLS];   // ... and the rotation that last improved them
-    __shared__ __align__(8) u64 colkey[RF_COLS];
+    __shared__ __align__(16) u64 wcolkey[RF_WARPS][RF_COLS];  // per warp: best (distance, row) key of every column of the round
     __shared__ __align__(8) uint64_t mbar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
             const int g = tid >> 2, k = tid & 3;
             float *dst = cols_p + g * 12 + ((k & 2) ? 6 : 0) + (k & 1);
             dst[0] = cols_raw[tid * 3 + 0], dst[2] = cols_raw[tid * 3 + 1], dst[4] = cols_raw[tid * 3 + 2];
-            colkey[tid] = ~0ull;                         // RF_COLS == blockDim.x
+#pragma unroll
+            for (int w = 0; w < RF_WARPS; ++w) wcolkey[w][tid] = ~0ull;  // RF_COLS == blockDim.x; inactive warps stay at 'none'
 #pragma unroll
             for (int i = 0; i < RF_RC; ++i) wmn[lane * RF_RC + i] = __int_as_float(0x7f800000), wrot[lane * RF_RC + i] = 0;
         }
@@ -177,7 +178,12 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
 #pragma unroll
                     for (int j = 0; j < RF_RQ; ++j) best[j] = __int_as_float(__float_as_int(best[j]) + wrapped);
                 }
-                float loc[RF_RC];
+                {   // lane 0 (t >= 1) picks up columns last seen by lane 31: they wrap to the lowest rows (+1 ulp)
+                    const int wrapped = (lane == 0 && t != 0) ? 1 : 0;
+                    mnv.x = __int_as_float(__float_as_int(mnv.x) + wrapped), mnv.y = __int_as_float(__float_as_int(mnv.y) + wrapped);
+                    mnv.z = __int_as_float(__float_as_int(mnv.z) + wrapped), mnv.w = __int_as_float(__float_as_int(mnv.w) + wrapped);
+                }
+                float cm[RF_RC] = {mnv.x, mnv.y, mnv.z, mnv.w};  // running column minima, continued from the handed-over state
 #pragma unroll
                 for (int j = 0; j < RF_RQ; j += 2) {
                     float d[2][4];
@@ -193,16 +199,11 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
                         rot[j + u] = (nb < old) ? t : rot[j + u];
                     }
 #pragma unroll
-                    for (int i = 0; i < RF_RC; ++i) loc[i] = (j == 0) ? fminf(d[0][i], d[1][i]) : min3(loc[i], d[0][i], d[1][i]);
+                    for (int i = 0; i < RF_RC; ++i) cm[i] = min3(cm[i], d[0][i], d[1][i]);
                 }
-                {   // lane 0 (t >= 1) picks up columns last seen by lane 31: they wrap to the lowest rows (+1 ulp)
-                    const int wrapped = (lane == 0 && t != 0) ? 1 : 0;
-                    mnv.x = __int_as_float(__float_as_int(mnv.x) + wrapped), mnv.y = __int_as_float(__float_as_int(mnv.y) + wrapped);
-                    mnv.z = __int_as_float(__float_as_int(mnv.z) + wrapped), mnv.w = __int_as_float(__float_as_int(mnv.w) + wrapped);
-                }
-                rtv.x = (loc[0] < mnv.x) ? t : rtv.x, rtv.y = (loc[1] < mnv.y) ? t : rtv.y;
-                rtv.z = (loc[2] < mnv.z) ? t : rtv.z, rtv.w = (loc[3] < mnv.w) ? t : rtv.w;
-                mnv.x = fminf(mnv.x, loc[0]), mnv.y = fminf(mnv.y, loc[1]), mnv.z = fminf(mnv.z, loc[2]), mnv.w = fminf(mnv.w, loc[3]);
+                rtv.x = (cm[0] < mnv.x) ? t : rtv.x, rtv.y = (cm[1] < mnv.y) ? t : rtv.y;
+                rtv.z = (cm[2] < mnv.z) ? t : rtv.z, rtv.w = (cm[3] < mnv.w) ? t : rtv.w;
+                mnv = make_float4(cm[0], cm[1], cm[2], cm[3]);
                 *reinterpret_cast<float4 *>(wmn + g * RF_RC) = mnv;
                 *reinterpret_cast<int4 *>(wrot + g * RF_RC) = rtv;
                 __syncwarp();
@@ -245,21 +246,31 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
                         float cv = mns[i];
                         if (lane <= 30 && rts[i] <= lane) cv = bump_down(cv);  // bumped when lane 0 picked it up, never replaced
                         const int vl = (31 - lane + rts[i]) & 31;              // lane whose rows produced the minimum
-                        const float *rp = rows_s + (wrow0 + vl * RF_RQ) * 3;
+                        const float4 *rp = reinterpret_cast<const float4 *>(rows_s + (wrow0 + vl * RF_RQ) * 3);  // 8 rows, 96 B
+                        float rv[24];
+#pragma unroll
+                        for (int q4 = 0; q4 < 6; ++q4) {
+                            const float4 t4 = rp[q4];
+                            rv[4 * q4 + 0] = t4.x, rv[4 * q4 + 1] = t4.y, rv[4 * q4 + 2] = t4.z, rv[4 * q4 + 3] = t4.w;
+                        }
                         int k = RF_RQ - 1;
 #pragma unroll
                         for (int q = RF_RQ - 2; q >= 0; --q) {
-                            const float dq = sqdist_exact(rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], cxs[i], cys[i], czs[i]);
+                            const float dq = sqdist_exact(rv[3 * q], rv[3 * q + 1], rv[3 * q + 2], cxs[i], cys[i], czs[i]);
                             k = (dq == cv) ? q : k;
                         }
-                        const u64 key = ((u64)__float_as_uint(cv) << 32) | (unsigned)(row0 + wrow0 + vl * RF_RQ + k);
-                        atomicMin(&colkey[lc], key);
+                        wcolkey[warp][lc] = ((u64)__float_as_uint(cv) << 32) | (unsigned)(row0 + wrow0 + vl * RF_RQ + k);
                     }
                 }
             }
         }  // warp_active
         __syncthreads();
-        if (tid < ncols) atomicMax(a.colkey + (size_t)cloud * m + cbase + tid, ~colkey[tid]);
+        if (tid < ncols) {
+            u64 key = wcolkey[0][tid];
+#pragma unroll
+            for (int w = 1; w < RF_WARPS; ++w) key = wcolkey[w][tid] < key ? wcolkey[w][tid] : key;
+            atomicMax(a.colkey + (size_t)cloud * m + cbase + tid, ~key);
+        }
     }
 }
 
