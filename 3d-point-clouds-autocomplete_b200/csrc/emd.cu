@@ -255,6 +255,9 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS)
     __shared__ float cluster_part[MC_CLUSTER];
     unsigned rank;
     asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    // every CTA of the cluster must have started before anyone writes into rank 0's shared memory: arrive now,
+    // wait right before the remote store (the main loop runs in between)
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     const int pair = blockIdx.x / MC_CLUSTER;
     const int tid = threadIdx.x;
     const int l_begin = (int)(((long long)m * rank) / MC_CLUSTER), l_end = (int)(((long long)m * (rank + 1)) / MC_CLUSTER);
@@ -272,6 +275,7 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS)
     sum = warp_sum(sum);
     if ((tid & 31) == 0) warp_part[tid >> 5] = sum;
     __syncthreads();
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");  // all CTAs of the cluster are running
     if (tid == 0) {
         float t = 0.f;
 #pragma unroll
