@@ -1,6 +1,40 @@
-"""Drop-in for the hot-path part of the reference's utils/metrics.py (MMD / COV / 1-NNA).
-JSD and the mAP helpers of that file are CPU code outside the hot path and are not provided."""
+"""Drop-in for the reference's utils/metrics.py.
+
+The hot-path functions (MMD / COV / 1-NNA over all-pairs CD and EMD matrices) come from the B200 implementation.
+Everything else the reference module defines (JSD, average precision, ...: CPU code outside the hot path, which
+callers such as core/experiments.py:19 import from the same module) is taken from the reference's own file when it
+is found further down sys.path, so `from utils.metrics import compute_all_metrics, jsd_between_point_cloud_sets`
+keeps working.  That file's `from utils.pytorch_structural_losses... import match_cost / nn_distance` resolve to the
+drop-in ops, so no compiled reference backend is needed."""
+import importlib.util as _ilu
+import os as _os
+import sys as _sys
+
 from _pkg import pkg as _hp
+
+
+def _load_reference_module():
+    here = _os.path.dirname(_os.path.abspath(__file__))
+    for p in list(_sys.path):
+        cand = _os.path.join(_os.path.abspath(p or "."), "utils", "metrics.py")
+        if _os.path.isfile(cand) and _os.path.dirname(cand) != here:
+            spec = _ilu.spec_from_file_location("utils._reference_metrics", cand)
+            mod = _ilu.module_from_spec(spec)
+            try:
+                spec.loader.exec_module(mod)
+            except Exception as e:  # a missing optional dependency of the CPU-side helpers must not break the hot path
+                import warnings
+
+                warnings.warn(f"reference utils/metrics.py found at {cand} but not importable ({e!r}); "
+                              f"only the B200 hot-path functions are available")
+                return None
+            return mod
+    return None
+
+
+_ref = _load_reference_module()
+if _ref is not None:
+    globals().update({k: v for k, v in vars(_ref).items() if not k.startswith("__")})
 
 _m = _hp.metrics
 match_cost = _hp.match_cost

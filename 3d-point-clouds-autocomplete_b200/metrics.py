@@ -204,9 +204,35 @@ def mmd_cov_from_block(block_rs: torch.Tensor, row_begin: int, n_ref: int, group
     return {"mmd(Fidelity)": mmd, "cov(Coverage)": cov, "mmd_smp": mmd_smp}
 
 
+def _two_sample_stats(pred: torch.Tensor, label: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Confusion counts and the derived rates of the k-NN two-sample test (keys as in utils/metrics.py:177-190)."""
+    tp, fp = (pred * label).sum(), (pred * (1 - label)).sum()
+    fn, tn = ((1 - pred) * label).sum(), ((1 - pred) * (1 - label)).sum()
+    eps = 1e-10
+    return {"tp": tp, "fp": fp, "fn": fn, "tn": tn,
+            "precision": tp / (tp + fp + eps), "recall": tp / (tp + fn + eps),
+            "acc_t": tp / (tp + fn + eps), "acc_f": tn / (tn + fp + eps),
+            "acc": torch.eq(label, pred).float().mean()}
+
+
 def knn(Mxx, Mxy, Myy, k, sqrt=False):
-    """1-NN two-sample test on full matrices (utils/metrics.py:162-191), k = 1."""
-    return knn_from_blocks(Mxx, Mxy, Myy, 0, 0, Mxx.size(0), Myy.size(0), k, sqrt, None)
+    """k-NN two-sample test on full matrices (utils/metrics.py:162-191).  k = 1 (1-NNA, the only value the metrics
+    use) goes through the sharding-aware column/row-minimum formulation; other k vote over the k smallest entries
+    of every column of the stacked matrix [[Mxx, Mxy], [Mxy^T, Myy]] + inf*I, majority (ties -> label 1) wins."""
+    n0, n1 = Mxx.size(0), Myy.size(0)
+    if k == 1:
+        return knn_from_blocks(Mxx, Mxy, Myy, 0, 0, n0, n1, k, sqrt, None)
+    top = torch.cat((Mxx, Mxy), dim=1)
+    bottom = torch.cat((Mxy.t(), Myy), dim=1)
+    stacked = torch.cat((top, bottom), dim=0)
+    if sqrt:
+        stacked = stacked.abs().sqrt()
+    stacked = stacked + torch.diag(torch.full((n0 + n1,), INF, dtype=stacked.dtype, device=stacked.device))
+    nearest = stacked.topk(k, dim=0, largest=False).indices            # [k, n0+n1]
+    label = (torch.arange(n0 + n1, device=stacked.device) < n0).to(stacked.dtype)
+    votes = label[nearest].sum(dim=0)
+    pred = (votes >= k / 2.0).to(stacked.dtype)
+    return _two_sample_stats(pred, label)
 
 
 def knn_from_blocks(Mxx_blk, Mxy_blk, Myy_blk, x_begin: int, y_begin: int, n0: int, n1: int, k: int = 1,
@@ -234,18 +260,7 @@ def knn_from_blocks(Mxx_blk, Mxy_blk, Myy_blk, x_begin: int, y_begin: int, n0: i
     pred_y = (xy_col_v <= yy_v).to(Mxy_blk.dtype)
     pred = torch.cat((pred_x, pred_y))
     label = torch.cat((torch.ones(n0), torch.zeros(n1))).to(Mxy_blk)
-    s = {
-        "tp": (pred * label).sum(), "fp": (pred * (1 - label)).sum(),
-        "fn": ((1 - pred) * label).sum(), "tn": ((1 - pred) * (1 - label)).sum(),
-    }
-    s.update({
-        "precision": s["tp"] / (s["tp"] + s["fp"] + 1e-10),
-        "recall": s["tp"] / (s["tp"] + s["fn"] + 1e-10),
-        "acc_t": s["tp"] / (s["tp"] + s["fn"] + 1e-10),
-        "acc_f": s["tn"] / (s["tn"] + s["fp"] + 1e-10),
-        "acc": torch.eq(label, pred).float().mean(),
-    })
-    return s
+    return _two_sample_stats(pred, label)
 
 
 def compute_all_metrics(sample_pcs, ref_pcs, batch_size=None, chamfer_loss=None, group=None, with_emd: bool = True,

@@ -315,3 +315,28 @@ def test_nn_distance_autograd_gather_path_equals_sorting_kernel(hp):
     assert torch.equal(d1.detach(), e1) and torch.equal(d2.detach(), e2)
     ga, gc = hp.NNDistanceGrad(a.detach(), c.detach(), i1, i2, w1, w2)
     assert torch.equal(a.grad, ga) and torch.equal(c.grad, gc)
+
+
+def test_random_shapes_sweep_vs_oracle(hp, oracle):
+    """Seeded sweep over awkward shapes (sizes around the 128-column round, the 256-row warp block and the 1024-row CTA
+    chunk; unequal clouds; tiny clouds): indices and distances bit-exact, gradients of the fused loss within 1e-5."""
+    rng = np.random.default_rng(2026)
+    specials = [1, 2, 3, 4, 5, 7, 8, 31, 32, 33, 127, 128, 129, 255, 256, 257, 511, 513, 1023, 1024, 1025, 1500, 2047, 2049]
+    for it in range(24):
+        b = int(rng.integers(1, 5))
+        n = int(rng.choice(specials))
+        m = int(rng.choice(specials))
+        kind = ["uniform", "lattice"][it % 2]
+        a, c = _clouds((b, n, 3), (b, m, 3), kind, seed=1000 + it)
+        ad, cd = a.to(DEV).requires_grad_(True), c.to(DEV).requires_grad_(True)
+        d1, i1, d2, i2 = hp.NNDistance(ad.detach(), cd.detach())
+        od1, oi1, od2, oi2 = oracle.nn_distance(a.numpy(), c.numpy())
+        assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2), (b, n, m, kind)
+        assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2), (b, n, m, kind)
+        loss = hp.ChamferLoss()(cd, ad)
+        loss.backward()
+        oga, ogb = oracle.nn_distance_grad(a.numpy(), c.numpy(), oi1, oi2, np.ones_like(od1), np.ones_like(od2))
+        np.testing.assert_allclose(ad.grad.cpu().numpy(), oga, rtol=1e-5, atol=1e-6, err_msg=str((b, n, m, kind)))
+        np.testing.assert_allclose(cd.grad.cpu().numpy(), ogb, rtol=1e-5, atol=1e-6, err_msg=str((b, n, m, kind)))
+        ref_loss = float(od1.sum(dtype=np.float64) + od2.sum(dtype=np.float64))
+        assert abs(float(loss.detach()) - ref_loss) <= 1e-5 * max(abs(ref_loss), 1e-12)

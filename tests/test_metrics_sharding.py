@@ -94,3 +94,30 @@ def test_world_size_2_gloo_equals_single_process(hp, tmp_path, n_ref, n_smp):
     for rank in range(2):
         got = torch.load(f"{path}.rank{rank}")
         assert got == single, (rank, got, single)
+
+
+def test_knn_general_k_matches_reference_golden_semantics():
+    """knn(k>1) votes over the k nearest columns like utils/metrics.py:162-191; checked against a direct numpy vote."""
+    import importlib
+
+    import numpy as np
+    import torch
+
+    m = importlib.import_module("3d-point-clouds-autocomplete_b200.metrics")
+    g = torch.Generator().manual_seed(4)
+    n0, n1, k = 9, 7, 3
+    Mxx = torch.rand(n0, n0, generator=g)
+    Mxx = (Mxx + Mxx.t()) / 2
+    Myy = torch.rand(n1, n1, generator=g)
+    Myy = (Myy + Myy.t()) / 2
+    Mxy = torch.rand(n0, n1, generator=g)
+    s = m.knn(Mxx, Mxy, Myy, k)
+    M = np.block([[Mxx.numpy(), Mxy.numpy()], [Mxy.numpy().T, Myy.numpy()]]) + np.diag(np.full(n0 + n1, np.inf))
+    label = np.r_[np.ones(n0), np.zeros(n1)]
+    pred = np.array([(label[np.argsort(M[:, c], kind="stable")[:k]].sum() >= k / 2) for c in range(n0 + n1)], float)
+    assert float(s["acc"]) == np.mean(pred == label).astype(np.float32)
+    assert float(s["tp"]) == float((pred * label).sum()) and float(s["tn"]) == float(((1 - pred) * (1 - label)).sum())
+    # k = 1 path agrees with the general path
+    s1 = m.knn(Mxx, Mxy, Myy, 1)
+    M1 = np.array([(label[np.argmin(M[:, c])]) for c in range(n0 + n1)], float)
+    assert float(s1["acc"]) == np.mean(M1 == label).astype(np.float32)
