@@ -56,7 +56,7 @@ struct RingNNArgs {
     //   inv2 [b][m + 2n]: perm2[m] = column indices k sorted by (idx2[k], k); then begin2[n], end2[n]: bucket of row i
     int *inv1, *inv2;
     int sort_n, sort_shift;    // power-of-two sort size and bit position of the key in the composite (key << shift | pos)
-    int inv_fast;              // 1: counting-sort layout in shared memory (keys | count | cursor | pbuf), 0: bitonic only
+    int inv_fast;              // 1: counting sort with radix fallback in shared memory, 0: bitonic only
 };
 
 __device__ __forceinline__ float bump_up(float v) { return __int_as_float(__float_as_int(v) + 1); }
@@ -278,12 +278,9 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
 // Stable inverse of an index map, for the atomic-free backward.  One CTA per (cloud, direction), at the tail of the
 // unpack kernel.  `keys[e]` = target index of source e.  Output per cloud: perm[cnt] = sources sorted by (target, source),
 // begin[ntgt] / end[ntgt] = every target's bucket in perm.
-//   fast path : counting sort -- integer histogram (order-independent atomics), block scan, placement in arrival
-//               order, then every target sorts its own (typically 0-3 element) bucket by source index;
-//   slow path : any bucket above RF_BUCKET_MAX sources (degenerate clouds) or clouds too large for the four
-//               shared-memory arrays -> bitonic sort of the composites (target << shift | source).
-// Both give the same, fully deterministic result.
-constexpr int RF_BUCKET_MAX = 48;
+//   clouds up to 8192 points : stable radix sort of the composites (target << shift | source), see rf_build_inverse;
+//   larger clouds            : bitonic sort of the composites.
+// Both give the same, fully deterministic result whatever the bucket sizes are.
 
 __device__ __forceinline__ void rf_inverse_bitonic(const RingNNArgs &a, unsigned int *sortbuf, const int *keys_or_null, int cnt,
                                                    int ntgt, int *perm, int *begin, int *end, int tid) {
@@ -329,7 +326,95 @@ __device__ __forceinline__ void rf_inverse_bitonic(const RingNNArgs &a, unsigned
     }
 }
 
-// smem layout of the fast path (ints): keys[cnt] | count[ntgt] -> begin | cursor[ntgt] | pbuf[cnt]
+// Fast path: stable LSD radix sort of the composites (target << shift | source) on the TARGET bits, 6 bits per pass.
+// Stability keeps the sources of a bucket in ascending order, so no per-bucket sort is needed and the cost does not
+// depend on how skewed the assignment is (early in training most points map to a handful of targets).
+//   per pass: digit histogram (warp-aggregated) -> exclusive scan -> rounds of 1024 elements in order: every warp ranks
+//   its elements among equal digits with __match_any_sync, a 64 x 32 (digit x warp) table turns the ranks into positions.
+// smem (uints): buf0[cnt] | buf1[cnt] | wcnt[32][64] | dbase[64]
+constexpr int RX_BITS = 6, RX_BINS = 1 << RX_BITS, RX_WARPS = RF_MERGE_THREADS / 32;
+
+// `cur` holds the cnt composites, `alt` is the second buffer (both `big` uints), `wcnt` the rank table + digit starts.
+__device__ __forceinline__ void rf_inverse_radix(const RingNNArgs &a, unsigned int *cur, unsigned int *alt, unsigned int *wcnt, int cnt,
+                                                 int ntgt, int *perm, int *begin, int *end, int tid) {
+    unsigned int *dbase = wcnt + RX_WARPS * RX_BINS;  // [RX_BINS] running start of every digit
+    const int lane = tid & 31, warp = tid >> 5;
+    const int shift0 = a.sort_shift;                  // composites: target << shift0 | source
+    int tbits = 0;
+    while ((1 << tbits) < ntgt) ++tbits;
+    for (int i = tid; i < 2 * ntgt; i += RF_MERGE_THREADS) begin[i] = 0;  // empty buckets: begin = end = 0
+    const int rounds = (cnt + RF_MERGE_THREADS - 1) / RF_MERGE_THREADS;
+    for (int sh = shift0; sh < shift0 + tbits; sh += RX_BITS) {
+        if (tid < RX_BINS) dbase[tid] = 0u;
+        __syncthreads();  // composites / previous pass visible
+        for (int r = 0; r < rounds; ++r) {  // histogram, one aggregated atomic per (warp, digit)
+            const int e = r * RF_MERGE_THREADS + tid;
+            const int d = e < cnt ? (int)((cur[e] >> sh) & (RX_BINS - 1)) : RX_BINS;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            if (d < RX_BINS && lane == __ffs(peers) - 1) atomicAdd(&dbase[d], (unsigned)__popc(peers));
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the 64 digit counts (two per lane)
+            const unsigned c0 = dbase[2 * lane], c1 = dbase[2 * lane + 1];
+            unsigned inc = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const unsigned ex = inc - (c0 + c1);
+            dbase[2 * lane] = ex, dbase[2 * lane + 1] = ex + c0;
+        }
+        for (int r = 0; r < rounds; ++r) {
+            for (int i = tid; i < RX_WARPS * RX_BINS; i += RF_MERGE_THREADS) wcnt[i] = 0u;
+            __syncthreads();  // table cleared; (first round) scan visible; previous round's scatter done
+            const int e = r * RF_MERGE_THREADS + tid;
+            const unsigned c = e < cnt ? cur[e] : 0u;
+            const int d = e < cnt ? (int)((c >> sh) & (RX_BINS - 1)) : RX_BINS;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            if (d < RX_BINS && rank == 0) wcnt[warp * RX_BINS + d] = (unsigned)__popc(peers);
+            __syncthreads();
+            // per digit: exclusive scan over the 32 warps (one warp scans two digits, lane = source warp) -> positions
+#pragma unroll
+            for (int q = 0; q < RX_BINS / RX_WARPS; ++q) {
+                const int dg = warp * (RX_BINS / RX_WARPS) + q;
+                const unsigned v = wcnt[lane * RX_BINS + dg];
+                unsigned inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += u;
+                }
+                const unsigned run = dbase[dg];
+                wcnt[lane * RX_BINS + dg] = run + inc - v;
+                __syncwarp();
+                if (lane == 31) dbase[dg] = run + inc;
+            }
+            __syncthreads();
+            if (d < RX_BINS) alt[wcnt[warp * RX_BINS + d] + rank] = c;
+            __syncthreads();  // positions consumed before the table is cleared again
+        }
+        unsigned int *t = cur;
+        cur = alt, alt = t;
+    }
+    __syncthreads();
+    const unsigned mask = (1u << shift0) - 1u;
+    for (int p = tid; p < cnt; p += RF_MERGE_THREADS) {
+        const unsigned c = cur[p];
+        const int key = (int)(c >> shift0);
+        perm[p] = (int)(c & mask);
+        if (p == 0 || (int)(cur[p - 1] >> shift0) != key) begin[key] = p;
+        if (p == cnt - 1 || (int)(cur[p + 1] >> shift0) != key) end[key] = p + 1;
+    }
+}
+
+// Entry: counting sort when the assignment is benign (every bucket <= RF_BUCKET_MAX sources: histogram, scan, placement
+// in arrival order, owner sorts its tiny bucket), stable radix sort otherwise.  smem (ints):
+//   keys[cnt] | count[ntgt] | cursor[ntgt] | pbuf[cnt]   (<= 4*big)  followed by the radix rank table (RX_WARPS*RX_BINS + RX_BINS);
+//   the radix fallback re-uses count.. as its two composite buffers (2*big <= 3*big).
+constexpr int RF_BUCKET_MAX = 48;
+
 __device__ __forceinline__ void rf_build_inverse(const RingNNArgs &a, unsigned int *smem_u, int cloud, bool dir2, int tid) {
     __shared__ int scan_warp[RF_MERGE_THREADS / 32];
     __shared__ int max_bucket;
@@ -337,12 +422,14 @@ __device__ __forceinline__ void rf_build_inverse(const RingNNArgs &a, unsigned i
     const int ntgt = dir2 ? a.n : a.m;     // targets: the points they can map to
     int *inv = (dir2 ? a.inv2 : a.inv1) + (size_t)cloud * (cnt + 2 * ntgt);
     int *perm = inv, *begin = inv + cnt, *end = begin + ntgt;
-    int *keys = reinterpret_cast<int *>(smem_u);
-    if (!a.inv_fast) {  // composites were written straight into the sort buffer by the caller
+    if (!a.inv_fast) {  // big clouds: bitonic sort of the composites the caller wrote into the buffer
         rf_inverse_bitonic(a, smem_u, nullptr, cnt, ntgt, perm, begin, end, tid);
         return;
     }
-    int *count = keys + cnt, *cursor = count + ntgt, *pbuf = cursor + ntgt;
+    const int big = a.n > a.m ? a.n : a.m;
+    int *keys = reinterpret_cast<int *>(smem_u);
+    int *count = keys + big, *cursor = count + big, *pbuf = cursor + big;
+    unsigned int *table = smem_u + 4 * (size_t)big;
     for (int i = tid; i < ntgt; i += RF_MERGE_THREADS) count[i] = 0;
     if (tid == 0) max_bucket = 0;
     __syncthreads();
@@ -374,9 +461,11 @@ __device__ __forceinline__ void rf_build_inverse(const RingNNArgs &a, unsigned i
         scan_warp[tid] = winc - w;  // exclusive prefix of the warp totals
     }
     __syncthreads();
-    if (max_bucket > RF_BUCKET_MAX) {  // block-uniform: degenerate cloud, take the sorting path (keys are still intact)
+    if (max_bucket > RF_BUCKET_MAX) {  // block-uniform: skewed assignment -> data-independent radix sort (keys are intact)
+        unsigned int *buf0 = reinterpret_cast<unsigned int *>(count), *buf1 = buf0 + big;
         __syncthreads();
-        rf_inverse_bitonic(a, reinterpret_cast<unsigned int *>(count), keys, cnt, ntgt, perm, begin, end, tid);
+        for (int e = tid; e < cnt; e += RF_MERGE_THREADS) buf0[e] = ((unsigned)keys[e] << a.sort_shift) | (unsigned)e;
+        rf_inverse_radix(a, buf0, buf1, table, cnt, ntgt, perm, begin, end, tid);
         return;
     }
     {
@@ -405,6 +494,7 @@ __device__ __forceinline__ void rf_build_inverse(const RingNNArgs &a, unsigned i
     __syncthreads();
     for (int p = tid; p < cnt; p += RF_MERGE_THREADS) perm[p] = pbuf[p];
 }
+
 
 // key -> (distance, index); restores the zero state of the key arrays; fixed-order loss.
 // One block per (cloud, direction).  The loss is folded through a two-level ticket (groups of RF_GROUP blocks, then
@@ -582,10 +672,11 @@ int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *
         const int big = n > m ? n : m;
         a.sort_n = 1 << ceil_log2(big);
         a.sort_shift = ceil_log2(big);
-        // fast (counting-sort) layout: keys[cnt] count[ntgt] cursor[ntgt] pbuf[cnt] <= 4*big ints; its degenerate-bucket
-        // fallback sorts sort_n composites inside the count|cursor|pbuf region (>= 3*big ints >= sort_n)
-        a.inv_fast = ((size_t)4 * big * sizeof(int) <= 160 * 1024 && 3 * (size_t)(n < m ? n : m) >= (size_t)a.sort_n) ? 1 : 0;
-        const size_t smem = a.inv_fast ? (size_t)(2 * (size_t)big + 2 * (size_t)big) * sizeof(int) : (size_t)a.sort_n * sizeof(unsigned int);
+        // counting sort (keys | count | cursor | pbuf = 4*big ints) with radix fallback + its 32 x 64 rank table (<= 8192 points);
+        // larger clouds: one bitonic buffer of sort_n uints
+        a.inv_fast = (big <= 8192) ? 1 : 0;
+        const size_t smem = a.inv_fast ? ((size_t)4 * big + RX_WARPS * RX_BINS + RX_BINS) * sizeof(unsigned int)
+                                       : (size_t)a.sort_n * sizeof(unsigned int);
         static SmemAttrCache attr;
         if (smem > 40 * 1024) HP_CUDA(ensure_dynamic_smem(nn_ring_unpack_kernel<true>, smem, attr));
         nn_ring_unpack_kernel<true><<<(unsigned)ugrid, RF_MERGE_THREADS, smem, stream>>>(a);
@@ -610,39 +701,79 @@ struct RingGradArgs {
     int b, n, m;
 };
 
+// Buckets above GATHER_COOP entries (skewed assignments: early in training most ground-truth points map to a few
+// reconstructed points) are summed by the whole warp: lane l takes entries l, l+32, ... in ascending order and the 32
+// partial sums are folded by a fixed shuffle tree -- still deterministic, and no thread walks thousands of entries alone.
+constexpr int GATHER_COOP = 32;
+
 __global__ void __launch_bounds__(256) nn_grad_gather_kernel(const RingGradArgs a) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total1 = (long long)a.b * a.n, total = total1 + (long long)a.b * a.m;
-    if (t >= total) return;
-    const bool side2 = t >= total1;
-    const long long u = side2 ? t - total1 : t;
+    const int lane = threadIdx.x & 31;
+    const bool valid = t < total;
+    const bool side2 = valid && t >= total1;
+    const long long u = side2 ? t - total1 : (valid ? t : 0);
     const int np = side2 ? a.m : a.n, no = side2 ? a.n : a.m;
     const int cloud = (int)(u / np), i = (int)(u - (long long)cloud * np);
     const float *__restrict__ P = (side2 ? a.set2 : a.set1) + (size_t)cloud * np * 3;
     const float *__restrict__ O = (side2 ? a.set1 : a.set2) + (size_t)cloud * no * 3;
     const int *__restrict__ idx_own = (side2 ? a.idx2 : a.idx1) + (size_t)cloud * np;
     // buckets of the OTHER side's index map: inv of the other direction = [perm[no] | begin[np] | end[np]]
-    const int *__restrict__ inv = (side2 ? a.inv1 : a.inv2) + (size_t)cloud * (no + 2 * np);
-    const int *__restrict__ perm = inv;
-    const int pb = __ldg(inv + no + i), pe = __ldg(inv + no + np + i);
+    const int *__restrict__ perm = (side2 ? a.inv1 : a.inv2) + (size_t)cloud * (no + 2 * np);
     const float *__restrict__ g_own = a.g ? nullptr : (side2 ? a.gd2 : a.gd1) + (size_t)cloud * np;
     const float *__restrict__ g_oth = a.g ? nullptr : (side2 ? a.gd1 : a.gd2) + (size_t)cloud * no;
     const float gs = a.g ? __ldg(a.g) * 2.f : 0.f;
-    const float g2 = a.g ? gs : __ldg(g_own + i) * 2.f;
-    const float px = __ldg(P + (size_t)i * 3 + 0), py = __ldg(P + (size_t)i * 3 + 1), pz = __ldg(P + (size_t)i * 3 + 2);
-    const int j = min(max(__ldg(idx_own + i), 0), no - 1);
-    float ax = g2 * (px - __ldg(O + (size_t)j * 3 + 0));
-    float ay = g2 * (py - __ldg(O + (size_t)j * 3 + 1));
-    float az = g2 * (pz - __ldg(O + (size_t)j * 3 + 2));
-    for (int p = pb; p < pe; ++p) {  // ascending source index: fixed summation order
-        const int k = __ldg(perm + p);
-        const float gk = a.g ? gs : __ldg(g_oth + k) * 2.f;
-        ax += -(gk * (__ldg(O + (size_t)k * 3 + 0) - px));
-        ay += -(gk * (__ldg(O + (size_t)k * 3 + 1) - py));
-        az += -(gk * (__ldg(O + (size_t)k * 3 + 2) - pz));
+    int pb = 0, pe = 0;
+    float px = 0.f, py = 0.f, pz = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    if (valid) {
+        pb = __ldg(perm + no + i), pe = __ldg(perm + no + np + i);
+        const float g2 = a.g ? gs : __ldg(g_own + i) * 2.f;
+        px = __ldg(P + (size_t)i * 3 + 0), py = __ldg(P + (size_t)i * 3 + 1), pz = __ldg(P + (size_t)i * 3 + 2);
+        const int j = min(max(__ldg(idx_own + i), 0), no - 1);
+        ax = g2 * (px - __ldg(O + (size_t)j * 3 + 0));
+        ay = g2 * (py - __ldg(O + (size_t)j * 3 + 1));
+        az = g2 * (pz - __ldg(O + (size_t)j * 3 + 2));
     }
-    float *G = (side2 ? a.grad2 : a.grad1) + ((size_t)cloud * np + i) * 3;
-    G[0] = ax, G[1] = ay, G[2] = az;
+    const bool big = valid && (pe - pb) > GATHER_COOP;
+    if (valid && !big) {
+        for (int p = pb; p < pe; ++p) {  // ascending source index: fixed summation order
+            const int k = __ldg(perm + p);
+            const float gk = a.g ? gs : __ldg(g_oth + k) * 2.f;
+            ax += -(gk * (__ldg(O + (size_t)k * 3 + 0) - px));
+            ay += -(gk * (__ldg(O + (size_t)k * 3 + 1) - py));
+            az += -(gk * (__ldg(O + (size_t)k * 3 + 2) - pz));
+        }
+    }
+    // warp-cooperative pass over the big buckets of this warp's 32 points (rare; uniform loop over the ballot)
+    unsigned todo = __ballot_sync(0xffffffffu, big);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int b0 = __shfl_sync(0xffffffffu, pb, src), b1 = __shfl_sync(0xffffffffu, pe, src);
+        const float qx = __shfl_sync(0xffffffffu, px, src), qy = __shfl_sync(0xffffffffu, py, src), qz = __shfl_sync(0xffffffffu, pz, src);
+        // all lanes of a warp may straddle a cloud / side boundary: take the owner's arrays
+        const unsigned long long permv = __shfl_sync(0xffffffffu, (unsigned long long)perm, src);
+        const unsigned long long Ov = __shfl_sync(0xffffffffu, (unsigned long long)O, src);
+        const unsigned long long gv = __shfl_sync(0xffffffffu, (unsigned long long)g_oth, src);
+        const int *__restrict__ perm_s = reinterpret_cast<const int *>(permv);
+        const float *__restrict__ O_s = reinterpret_cast<const float *>(Ov);
+        const float *__restrict__ g_s = reinterpret_cast<const float *>(gv);
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll 4
+        for (int p = b0 + lane; p < b1; p += 32) {  // unrolled: four dependent (perm -> point) load chains in flight
+            const int k = __ldg(perm_s + p);
+            const float gk = a.g ? gs : __ldg(g_s + k) * 2.f;
+            sx += -(gk * (__ldg(O_s + (size_t)k * 3 + 0) - qx));
+            sy += -(gk * (__ldg(O_s + (size_t)k * 3 + 1) - qy));
+            sz += -(gk * (__ldg(O_s + (size_t)k * 3 + 2) - qz));
+        }
+        sx = warp_sum(sx), sy = warp_sum(sy), sz = warp_sum(sz);
+        if (lane == src) ax += sx, ay += sy, az += sz;
+    }
+    if (valid) {
+        float *G = (side2 ? a.grad2 : a.grad1) + ((size_t)cloud * np + i) * 3;
+        G[0] = ax, G[1] = ay, G[2] = az;
+    }
 }
 
 int nn_ring_backward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,

@@ -268,7 +268,8 @@ def test_ring_kernel_unaligned_views(hp, oracle):
 
 
 @pytest.mark.parametrize("b,n,m,kind", [(3, 700, 1100, "uniform"), (2, 2048, 2048, "uniform"), (2, 1500, 300, "ties"),
-                                        (1, 1, 7, "uniform"), (2, 5000, 4097, "uniform"), (2, 64, 64, "zero")])
+                                        (1, 1, 7, "uniform"), (2, 5000, 4097, "uniform"), (2, 64, 64, "zero"),
+                                        (2, 2048, 2048, "zero"), (1, 9000, 300, "uniform"), (2, 2048, 2048, "skewed")])
 def test_gather_backward_from_forward_inverse_equals_sorting_backward(hp, oracle, b, n, m, kind):
     """chamfer_forward(want_inverse=True) emits the inverse index maps; the gather backward built on them must give the
     same bits as the self-contained (sorting) backward and match the oracle."""
@@ -279,6 +280,9 @@ def test_gather_backward_from_forward_inverse_equals_sorting_backward(hp, oracle
     elif kind == "zero":  # every point of xyz1 identical: one bucket holds everything
         a = torch.zeros(b, n, 3)
         c = torch.rand(b, m, 3, generator=g)
+    elif kind == "skewed":  # a collapsed reconstruction (early training): buckets of hundreds of points
+        a = torch.rand(b, n, 3, generator=g) - 0.5
+        c = (torch.rand(b, m, 3, generator=g) - 0.5) * 0.05
     else:
         a, c = torch.rand(b, n, 3, generator=g) - 0.5, torch.rand(b, m, 3, generator=g) - 0.5
     ad, cd = a.to(DEV), c.to(DEV)
@@ -287,11 +291,19 @@ def test_gather_backward_from_forward_inverse_equals_sorting_backward(hp, oracle
     assert inv is not None
     ga, gb = hp.chamfer_backward(ad, cd, i1, i2, gl, inv)
     ha, hb = hp.chamfer_backward(ad, cd, i1, i2, gl)  # sorts the index maps itself
-    assert torch.equal(ga, ha) and torch.equal(gb, hb)
+    big_buckets = max(int(torch.bincount(i1.flatten().long()).max()), int(torch.bincount(i2.flatten().long()).max())) > 32
+    if big_buckets:  # buckets above 32 entries are summed warp-cooperatively: same terms, different (fixed) association
+        torch.testing.assert_close(ga, ha, rtol=1e-4, atol=1e-6)  # sums of up to thousands of fp32 terms, two associations
+        torch.testing.assert_close(gb, hb, rtol=1e-4, atol=1e-6)
+        ga2, gb2 = hp.chamfer_backward(ad, cd, i1, i2, gl, inv)
+        assert torch.equal(ga, ga2) and torch.equal(gb, gb2), "cooperative gather must be reproducible"
+    else:
+        assert torch.equal(ga, ha) and torch.equal(gb, hb)
     oga, ogb = oracle.nn_distance_grad(a.numpy(), c.numpy(), i1.cpu().numpy(), i2.cpu().numpy(),
                                        np.full((b, n), 0.7, np.float32), np.full((b, m), 0.7, np.float32))
-    np.testing.assert_allclose(ga.cpu().numpy(), oga, rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(gb.cpu().numpy(), ogb, rtol=1e-5, atol=1e-6)
+    rtol = 1e-4 if big_buckets else 1e-5  # thousands of fp32 terms per sum in the degenerate cases
+    np.testing.assert_allclose(ga.cpu().numpy(), oga, rtol=rtol, atol=1e-6)
+    np.testing.assert_allclose(gb.cpu().numpy(), ogb, rtol=rtol, atol=1e-6)
     # the inverse maps are what they claim: perm sorted by (idx, position), buckets delimit equal idx
     inv2 = inv[1].view(b, m + 2 * n).cpu().numpy()
     for s in range(b):
