@@ -357,31 +357,65 @@ __global__ void __launch_bounds__(THREADS) nn_grad_kernel(const NNGradArgs a, co
     }
     __syncthreads();
 
-    auto finish = [&](int i, float px, float py, float pz, float ox, float oy, float oz, float g) {
-        float ax = g * (px - ox), ay = g * (py - oy), az = g * (pz - oz);
-        const int e = start[i + 1];
-        for (int p = start[i]; p < e; ++p) {  // ascending k: fixed summation order
-            int k = perm[p];
-            float gk = (a.scalar_grad ? gs_oth : __ldg(g_oth + k)) * 2.f;
-            float kx = __ldg(O + (size_t)k * 3 + 0), ky = __ldg(O + (size_t)k * 3 + 1), kz = __ldg(O + (size_t)k * 3 + 2);
-            ax += -(gk * (kx - px));
-            ay += -(gk * (ky - py));
-            az += -(gk * (kz - pz));
+    // Gather.  Buckets up to GRAD_COOP entries are walked by their owner in ascending k; larger ones (skewed assignments)
+    // by the whole warp: lane l takes entries l, l+32, ... and the partial sums are folded by a fixed shuffle tree.
+    constexpr int GRAD_COOP = 32;
+    const int lane_g = tid & 31;
+    for (int base = 0; base < np; base += THREADS) {  // block-uniform trip count: the warp-cooperative part needs all lanes
+        const int i = base + tid;
+        const bool valid = i < np;
+        const int u = base / THREADS;
+        float px = 0.f, py = 0.f, pz = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+        int pb = 0, pe = 0;
+        if (valid) {
+            float ox, oy, oz, g;
+            static_assert(PRE == 2, "the preloaded points are selected with static register indices");
+            if (u < PRE) {
+                px = u ? pre_p[1][0] : pre_p[0][0], py = u ? pre_p[1][1] : pre_p[0][1], pz = u ? pre_p[1][2] : pre_p[0][2];
+                ox = u ? pre_o[1][0] : pre_o[0][0], oy = u ? pre_o[1][1] : pre_o[0][1], oz = u ? pre_o[1][2] : pre_o[0][2];
+                g = u ? pre_g[1] : pre_g[0];
+            } else {
+                const int j2 = min(max(__ldg(idx_own + i), 0), no - 1);
+                px = __ldg(P + (size_t)i * 3 + 0), py = __ldg(P + (size_t)i * 3 + 1), pz = __ldg(P + (size_t)i * 3 + 2);
+                ox = __ldg(O + (size_t)j2 * 3 + 0), oy = __ldg(O + (size_t)j2 * 3 + 1), oz = __ldg(O + (size_t)j2 * 3 + 2);
+                g = (a.scalar_grad ? gs_own : __ldg(g_own + i)) * 2.f;
+            }
+            ax = g * (px - ox), ay = g * (py - oy), az = g * (pz - oz);
+            pb = start[i], pe = start[i + 1];
         }
-        G[(size_t)i * 3 + 0] = ax;
-        G[(size_t)i * 3 + 1] = ay;
-        G[(size_t)i * 3 + 2] = az;
-    };
-#pragma unroll
-    for (int u = 0; u < PRE; ++u) {
-        const int i = tid + u * THREADS;
-        if (i < np) finish(i, pre_p[u][0], pre_p[u][1], pre_p[u][2], pre_o[u][0], pre_o[u][1], pre_o[u][2], pre_g[u]);
-    }
-    for (int i = tid + PRE * THREADS; i < np; i += THREADS) {
-        const int j2 = min(max(__ldg(idx_own + i), 0), no - 1);
-        finish(i, __ldg(P + (size_t)i * 3 + 0), __ldg(P + (size_t)i * 3 + 1), __ldg(P + (size_t)i * 3 + 2),
-               __ldg(O + (size_t)j2 * 3 + 0), __ldg(O + (size_t)j2 * 3 + 1), __ldg(O + (size_t)j2 * 3 + 2),
-               (a.scalar_grad ? gs_own : __ldg(g_own + i)) * 2.f);
+        const bool big = valid && (pe - pb) > GRAD_COOP;
+        if (valid && !big) {
+            for (int p = pb; p < pe; ++p) {  // ascending k: fixed summation order
+                const int k = perm[p];
+                const float gk = (a.scalar_grad ? gs_oth : __ldg(g_oth + k)) * 2.f;
+                ax += -(gk * (__ldg(O + (size_t)k * 3 + 0) - px));
+                ay += -(gk * (__ldg(O + (size_t)k * 3 + 1) - py));
+                az += -(gk * (__ldg(O + (size_t)k * 3 + 2) - pz));
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, big);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int b0 = __shfl_sync(0xffffffffu, pb, src), b1 = __shfl_sync(0xffffffffu, pe, src);
+            const float qx = __shfl_sync(0xffffffffu, px, src), qy = __shfl_sync(0xffffffffu, py, src), qz = __shfl_sync(0xffffffffu, pz, src);
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll 4
+            for (int p = b0 + lane_g; p < b1; p += 32) {
+                const int k = perm[p];
+                const float gk = (a.scalar_grad ? gs_oth : __ldg(g_oth + k)) * 2.f;
+                sx += -(gk * (__ldg(O + (size_t)k * 3 + 0) - qx));
+                sy += -(gk * (__ldg(O + (size_t)k * 3 + 1) - qy));
+                sz += -(gk * (__ldg(O + (size_t)k * 3 + 2) - qz));
+            }
+            sx = warp_sum(sx), sy = warp_sum(sy), sz = warp_sum(sz);
+            if (lane_g == src) ax += sx, ay += sy, az += sz;
+        }
+        if (valid) {
+            G[(size_t)i * 3 + 0] = ax;
+            G[(size_t)i * 3 + 1] = ay;
+            G[(size_t)i * 3 + 2] = az;
+        }
     }
 }
 

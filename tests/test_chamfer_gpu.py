@@ -127,7 +127,10 @@ def test_degenerate_all_points_identical_backward(hp, oracle):
     oga, ogb = oracle.nn_distance_grad(a.numpy(), c.numpy(), i1.cpu().numpy(), i2.cpu().numpy(),
                                        np.ones((2, 1024), np.float32), np.ones((2, 1024), np.float32))
     np.testing.assert_allclose(ga.cpu().numpy(), oga, rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(gb.cpu().numpy(), ogb, rtol=1e-5, atol=1e-6)
+    # one bucket of 1024 terms, summed lane-strided + shuffle tree here and sequentially in the oracle: fp32 association
+    np.testing.assert_allclose(gb.cpu().numpy(), ogb, rtol=1e-4, atol=1e-6)
+    ga2, gb2 = hp.NNDistanceGrad(ad, cd, i1, i2, ones1, ones2)
+    assert torch.equal(ga, ga2) and torch.equal(gb, gb2)
 
 
 def test_autograd_op_and_batch_quirk(hp):
