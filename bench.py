@@ -441,6 +441,8 @@ def run_ours(args):
                     "ms_per_step": pipe_ms,
                     "api": "ChamferHostPipeline.submit/result: pinned host clouds -> H2D -> fwd+bwd -> D2H of loss and both gradients, "
                            "every step; copies of neighbouring steps overlap the compute (3 buffer sets, 3 streams)",
+                    "l2_policy": "none needed: every step copies fresh inputs from host memory (value, by contrast, is timed with "
+                                 "an L2 flush before every step, which is why e2e can read slightly higher)",
                     "unpipelined_ms_per_step": statistics.mean(e2e_ms),
                     "unpipelined_api": "ChamferStepGraph.run_from_host: the same copies and step serialised in one graph"},
             "eager_api": {"ms_per_step": statistics.mean(eager_ms), "value": PAIRS_PER_STEP / (statistics.mean(eager_ms) * 1e-3),
