@@ -8,7 +8,7 @@ shim at the repository root.  ``dropin/`` mirrors the reference's import paths
 """
 from . import _native  # noqa: F401
 from .chamfer import (ChamferLoss, NNDistance, NNDistanceFunction, NNDistanceGrad, chamfer_backward,  # noqa: F401
-                      chamfer_forward, nn_distance)
+                      chamfer_forward, chamfer_step, chamfer_step_supported, nn_distance)
 
 from .emd import (ApproxMatch, MatchCost, MatchCostFunction, MatchCostGrad, approx_match, emd_cost_pairs,  # noqa: F401
                   match_cost)

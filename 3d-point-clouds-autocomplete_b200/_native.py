@@ -38,6 +38,8 @@ SIGNATURES = {
     "hp_chamfer_backward": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_chamfer_inverse_ints": (_sz, [_int, _int, _int, _int]),
     "hp_chamfer_forward_inv": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hp_chamfer_step_supported": (_int, [_int, _int, _int]),
+    "hp_chamfer_step": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hp_chamfer_backward_inv": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_nndistancegrad_inv": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_approxmatch": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp]),

@@ -156,6 +156,76 @@ __global__ void __launch_bounds__(256) peak_kernel(int iters, float seed, float 
     }
 }
 
+
+// KIND 7 / 8 / 9: the register pattern of the ring kernel's rotation (8 rows x 4 columns per lane, packed distance
+// evaluation with the scalar-broadcast row operand, column groups from shared memory).
+//   7: FMA pipe only (results folded with 16 extra FADD2: 112 packed ops per rotation)
+//   8: 96 packed ops + the 32 FMNMX3 of the row / column minima
+//   9: 8 + the rotation bookkeeping (FSETP + SEL per row and per column)
+template <int KIND>
+__global__ void __launch_bounds__(128, 4) ring_pattern_kernel(int iters, float seed, float *sink) {
+    __shared__ __align__(16) float cols[32 * 12];
+    for (int i = threadIdx.x; i < 32 * 12; i += blockDim.x) cols[i] = seed * 0.001f * (float)(i ^ 5);
+    __syncthreads();
+    float qx[8], qy[8], qz[8], best[8], cm[4];
+    int rot[8], crot[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        qx[j] = seed + j + threadIdx.x * 0.01f, qy[j] = seed - j, qz[j] = seed * j, best[j] = 3.0e38f, rot[j] = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cm[i] = 3.0e38f, crot[i] = 0;
+    f32x2 acc = pack2(0.f, 0.f);
+    int g = threadIdx.x & 31;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 2
+        for (int t = 0; t < 32; ++t) {
+            const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(cols + g * 12);
+            const ulonglong2 c0 = p[0], c1 = p[1], c2 = p[2];
+            const f32x2 x01 = c0.x, y01 = c0.y, z01 = c1.x, x23 = c1.y, y23 = c2.x, z23 = c2.y;
+            float cold[4] = {cm[0], cm[1], cm[2], cm[3]};
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                float d[2][4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const f32x2 px = pack2(qx[j + u], qx[j + u]), py = pack2(qy[j + u], qy[j + u]), pz = pack2(qz[j + u], qz[j + u]);
+                    const f32x2 da = sqdist_exact2(px, py, pz, x01, y01, z01), db = sqdist_exact2(px, py, pz, x23, y23, z23);
+                    if (KIND == 7) {
+                        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(da));
+                        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(db));
+                    } else {
+                        unpack2(da, d[u][0], d[u][1]);
+                        unpack2(db, d[u][2], d[u][3]);
+                        const float old = best[j + u];
+                        float nb = min3(old, d[u][0], d[u][1]);
+                        nb = min3(nb, d[u][2], d[u][3]);
+                        best[j + u] = nb;
+                        if (KIND == 9) rot[j + u] = (nb < old) ? t : rot[j + u];
+                    }
+                }
+                if (KIND != 7) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cm[i] = min3(cm[i], d[0][i], d[1][i]);
+                }
+            }
+            if (KIND == 9) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) crot[i] = (cm[i] < cold[i]) ? t : crot[i];
+            }
+            g = (g + 1) & 31;
+        }
+    }
+    float lo, hi;
+    unpack2(acc, lo, hi);
+    float s = lo + hi;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += best[j] + (float)rot[j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += cm[i] + (float)crot[i];
+    if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace hp
 
 using namespace hp;
@@ -177,11 +247,11 @@ extern "C" const char *hp_last_error_message(void) { return g_err; }
 
 extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *stream_v) {
     HP_REQUIRE(rate_host != nullptr, "hp_measure_peak: null result pointer");
-    HP_REQUIRE(kind >= 0 && kind <= 6 && iters > 0, "hp_measure_peak: bad kind/iters (%d, %d)", kind, iters);
+    HP_REQUIRE(kind >= 0 && kind <= 9 && iters > 0, "hp_measure_peak: bad kind/iters (%d, %d)", kind, iters);
     cudaStream_t stream = (cudaStream_t)stream_v;
     float *sink = nullptr;
     HP_CUDA(cudaMalloc(&sink, sizeof(float)));  // measurement helper only: not on the product path
-    const int blocks = sm_count() * 8, threads = 256;
+    const int blocks = kind >= 7 ? sm_count() * 4 : sm_count() * 8, threads = kind >= 7 ? 128 : 256;
     cudaEvent_t e0, e1;
     HP_CUDA(cudaEventCreate(&e0));
     HP_CUDA(cudaEventCreate(&e1));
@@ -195,6 +265,9 @@ extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *str
             case 3: peak_kernel<3><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
             case 4: peak_kernel<4><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
             case 6: peak_mma_tf32_kernel<<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
+            case 7: ring_pattern_kernel<7><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
+            case 8: ring_pattern_kernel<8><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
+            case 9: ring_pattern_kernel<9><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
             default: peak_kernel<5><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
         }
         HP_CUDA(cudaEventRecord(e1, stream));
@@ -214,7 +287,9 @@ extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *str
         case 1: per_thread_iter = 8 * 4.0; break;          // FLOP
         case 2: per_thread_iter = 8.0; break;              // ex2
         case 3: per_thread_iter = 1024 * 2 * 8.0; break;   // 1024 candidates x 2 queries x 8 algorithmic FLOP
-        case 6: per_thread_iter = 8 * 2.0 * 16 * 8 * 8 / 32.0; break;  // 8 mma per warp-iteration, 2048 FLOP each, per thread
+        case 6: per_thread_iter = 8 * 2.0 * 16 * 8 * 8 / 32.0; break;
+        case 7: per_thread_iter = 32 * 112.0; break;       // packed FMA-pipe instructions per lane
+        case 8: case 9: per_thread_iter = 32 * 96.0; break;  // 8 mma per warp-iteration, 2048 FLOP each, per thread
         default: per_thread_iter = 1024 * 4 * 8.0; break;  // 1024 candidates x 4 queries x 8 algorithmic FLOP
     }
     *rate_host = threads_total * per_thread_iter * (double)iters / ((double)best_ms * 1e-3);

@@ -446,6 +446,9 @@ size_t nn_ring_workspace_bytes(int b, int n, int m);
 int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
                            int *idx2, float *loss, int *inv1, int *inv2, void *workspace, cudaStream_t stream);
 bool nn_ring_inverse_supported(int n, int m);
+bool nn_ring_step_supported(int n, int m);
+int nn_ring_step_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_loss, float *dist1, int *idx1,
+                        float *dist2, int *idx2, float *loss, float *grad1, float *grad2, void *workspace, cudaStream_t stream);
 int nn_ring_backward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,
                             const int *inv1, const int *inv2, const float *grad_loss, const float *grad_dist1,
                             const float *grad_dist2, float *grad1, float *grad2, cudaStream_t stream);
@@ -648,6 +651,30 @@ extern "C" int hp_chamfer_backward_inv(int b, int n, const float *xyz1, int m, c
                "hp_chamfer_backward_inv: null pointer");
     return nn_ring_backward_launch(b, n, xyz1, m, xyz2, idx1, idx2, inv1, inv2, grad_loss, nullptr, nullptr, grad_xyz1,
                                    grad_xyz2, (cudaStream_t)stream);
+}
+
+extern "C" int hp_chamfer_step_supported(int b, int n, int m) {
+    return (b > 0 && use_ring() && nn_ring_step_supported(n, m)) ? 1 : 0;
+}
+
+extern "C" int hp_chamfer_step(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_loss, float *dist1,
+                               int *idx1, float *dist2, int *idx2, float *loss, float *grad_xyz1, float *grad_xyz2,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+    HP_REQUIRE(b > 0 && n > 0 && m > 0, "hp_chamfer_step: sizes must be positive (b=%d n=%d m=%d)", b, n, m);
+    HP_REQUIRE(xyz1 && xyz2 && grad_loss && dist1 && idx1 && dist2 && idx2 && loss && grad_xyz1 && grad_xyz2,
+               "hp_chamfer_step: null pointer");
+    HP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+               "hp_chamfer_step: workspace null or not 16-byte aligned");
+    if (workspace_bytes < hp_chamfer_workspace_bytes(b, n, m)) {
+        set_error("hp_chamfer_step: workspace %zu < required %zu bytes", workspace_bytes, hp_chamfer_workspace_bytes(b, n, m));
+        return HP_ERR_WORKSPACE;
+    }
+    if (!hp_chamfer_step_supported(b, n, m)) {
+        set_error("hp_chamfer_step: fused step unavailable for n=%d m=%d (use hp_chamfer_forward_inv + hp_chamfer_backward_inv)", n, m);
+        return HP_ERR_UNSUPPORTED;
+    }
+    return nn_ring_step_launch(b, n, xyz1, m, xyz2, grad_loss, dist1, idx1, dist2, idx2, loss, grad_xyz1, grad_xyz2, workspace,
+                               (cudaStream_t)stream);
 }
 
 extern "C" int hp_nndistancegrad_inv(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,

@@ -62,23 +62,15 @@ struct RingNNArgs {
 __device__ __forceinline__ float bump_up(float v) { return __int_as_float(__float_as_int(v) + 1); }
 __device__ __forceinline__ float bump_down(float v) { return __int_as_float(__float_as_int(v) - 1); }
 
-// stage `cnt` points (AoS) from global to shared: bulk-TMA for the 16-byte aligned body, plain loads for the rest,
-// pad up to `total` points with `pad`.
-__device__ __forceinline__ void rf_stage_points(float *dst, const float *src, int cnt, int total, float pad, uint64_t *mbar,
-                                                uint32_t &phase, int tid, int nthreads) {
-    const bool tma_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-    const uint32_t bulk_bytes = tma_ok ? ((uint32_t)(cnt * 12) & ~15u) : 0u;
-    if (bulk_bytes && tid == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(mbar, bulk_bytes);
-        bulk_g2s(dst, src, bulk_bytes, mbar);
-    }
+// Staging of `cnt` points (AoS) from global to shared memory: bulk-TMA for the 16-byte aligned body (rf_bulk_bytes, issued
+// by one thread under an mbarrier), plain loads for the rest and padding up to `total` points with `pad` (rf_stage_tail).
+__device__ __forceinline__ uint32_t rf_bulk_bytes(const float *src, int cnt) {
+    return (reinterpret_cast<uintptr_t>(src) & 15) == 0 ? ((uint32_t)(cnt * 12) & ~15u) : 0u;
+}
+__device__ __forceinline__ void rf_stage_tail(float *dst, const float *src, int cnt, int total, float pad, uint32_t bulk_bytes,
+                                              int tid, int nthreads) {
     for (int i = (int)(bulk_bytes / 4) + tid; i < cnt * 3; i += nthreads) dst[i] = __ldg(src + i);
     for (int i = cnt * 3 + tid; i < total * 3; i += nthreads) dst[i] = pad;
-    if (bulk_bytes) {
-        mbar_wait(mbar, phase);
-        phase ^= 1;
-    }
 }
 
 // A column group = 4 consecutive columns stored as 12 floats [x0 x1 y0 y1 | z0 z1 x2 x3 | y2 y3 z2 z3]: three LDS.128
@@ -94,7 +86,7 @@ __device__ __forceinline__ RFGroup rf_load_group(const float *cols_p, int g) {
     return r;
 }
 
-template <int MINB>
+template <int MINB, int DBG = 0, int PIPE = 0>
 __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const RingNNArgs a) {
     __shared__ __align__(128) float rows_s[RF_ROWS * 3];
     __shared__ __align__(128) float cols_raw[RF_COLS * 3];
@@ -105,6 +97,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
     __shared__ __align__(8) uint64_t mbar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    asm volatile("griddepcontrol.launch_dependents;");  // a programmatically dependent tail kernel may start its prologue
     int bid = blockIdx.x;
     const int cc = bid % a.colchunks;
     bid /= a.colchunks;
@@ -116,10 +109,28 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
     const int row0 = rc * RF_ROWS;                       // first row of this CTA
     const int nrows = min(RF_ROWS, n - row0);            // real rows of this CTA (>= 1)
 
+    // rows and the first round's columns arrive together: one mbarrier phase, two bulk copies in flight
+    const int cbase0 = cc * a.R * RF_COLS;               // < m by construction of colchunks
+    const int ncols0 = min(RF_COLS, m - cbase0);
     if (tid == 0) mbar_init(&mbar, 1);
     __syncthreads();
     uint32_t phase = 0;
-    rf_stage_points(rows_s, A + (size_t)row0 * 3, nrows, RF_ROWS, RF_PAD_ROW, &mbar, phase, tid, RF_WARPS * 32);
+    {
+        const float *rsrc = A + (size_t)row0 * 3, *csrc = Bp + (size_t)cbase0 * 3;
+        const uint32_t rb = rf_bulk_bytes(rsrc, nrows), cb = rf_bulk_bytes(csrc, ncols0);
+        if (tid == 0 && rb + cb) {
+            fence_proxy_async();
+            mbar_expect_tx(&mbar, rb + cb);
+            if (rb) bulk_g2s(rows_s, rsrc, rb, &mbar);
+            if (cb) bulk_g2s(cols_raw, csrc, cb, &mbar);
+        }
+        rf_stage_tail(rows_s, rsrc, nrows, RF_ROWS, RF_PAD_ROW, rb, tid, RF_WARPS * 32);
+        rf_stage_tail(cols_raw, csrc, ncols0, RF_COLS, RF_PAD_COL, cb, tid, RF_WARPS * 32);
+        if (rb + cb) {
+            mbar_wait(&mbar, phase);
+            phase ^= 1;
+        }
+    }
     __syncthreads();
 
     const int wrow0 = warp * RF_WROWS;                   // first (CTA-local) row of this warp
@@ -144,9 +155,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
         const int cbase = (cc * a.R + r) * RF_COLS;      // first column of this round
         if (cbase >= m) break;                           // uniform
         const int ncols = min(RF_COLS, m - cbase);
-        __syncthreads();                                 // previous round's shared state consumed
-        rf_stage_points(cols_raw, Bp + (size_t)cbase * 3, ncols, RF_COLS, RF_PAD_COL, &mbar, phase, tid, RF_WARPS * 32);
-        __syncthreads();
+        // here: cols_raw holds this round's columns (all threads have waited + synchronised), previous round's state consumed
         {   // permute column tid into the packed group layout; reset the merge keys and this warp's column state
             const int g = tid >> 2, k = tid & 3;
             float *dst = cols_p + g * 12 + ((k & 2) ? 6 : 0) + (k & 1);
@@ -157,6 +166,21 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
             for (int i = 0; i < RF_RC; ++i) wmn[lane * RF_RC + i] = __int_as_float(0x7f800000), wrot[lane * RF_RC + i] = 0;
         }
         __syncthreads();
+        // cols_raw is free again: the next round's columns fly in under this round's rotations
+        const int cbase_n = cbase + RF_COLS;
+        const bool more = (r + 1 < a.R) && (cbase_n < m);  // uniform
+        uint32_t nb_bytes = 0;
+        if (more) {
+            const int ncols_n = min(RF_COLS, m - cbase_n);
+            const float *csrc = Bp + (size_t)cbase_n * 3;
+            nb_bytes = rf_bulk_bytes(csrc, ncols_n);
+            if (tid == 0 && nb_bytes) {
+                fence_proxy_async();
+                mbar_expect_tx(&mbar, nb_bytes);
+                bulk_g2s(cols_raw, csrc, nb_bytes, &mbar);
+            }
+            rf_stage_tail(cols_raw, csrc, ncols_n, RF_COLS, RF_PAD_COL, nb_bytes, tid, RF_WARPS * 32);
+        }
         if (warp_active) {
             // lane L meets column group (31 - L + t) mod 32 at rotation t: ascending with one wrap (at t = L+1);
             // a group's running minimum is handed from lane to lane through shared memory: it visits lanes
@@ -167,31 +191,67 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
             for (int j = 0; j < RF_RQ; ++j) best[j] = __int_as_float(0x7f800000), rot[j] = 0;
             int g = 31 - lane;
             RFGroup cur = rf_load_group(cols_p, g);
+            if (PIPE == 0) {
 #pragma unroll 2
-            for (int t = 0; t < 32; ++t) {
-                const int gn = (g + 1) & 31;
-                const RFGroup nxt = rf_load_group(cols_p, gn);  // prefetch the next rotation's columns
-                float4 mnv = *reinterpret_cast<const float4 *>(wmn + g * RF_RC);
-                int4 rtv = *reinterpret_cast<const int4 *>(wrot + g * RF_RC);
-                {   // at t == lane+1 this lane's column groups wrap to index 0: later groups must win ties (+1 ulp)
-                    const int wrapped = (t == lane + 1) ? 1 : 0;
-#pragma unroll
-                    for (int j = 0; j < RF_RQ; ++j) best[j] = __int_as_float(__float_as_int(best[j]) + wrapped);
+                for (int t = 0; t < ((DBG & 1) ? 2 : 32); ++t) {
+                    const int gn = (g + 1) & 31;
+                    const RFGroup nxt = rf_load_group(cols_p, gn);  // prefetch the next rotation's columns
+                    float4 mnv = *reinterpret_cast<const float4 *>(wmn + g * RF_RC);
+                    int4 rtv = *reinterpret_cast<const int4 *>(wrot + g * RF_RC);
+                    {   // at t == lane+1 this lane's column groups wrap to index 0: later groups must win ties (+1 ulp)
+                        const int wrapped = (t == lane + 1) ? 1 : 0;
+    #pragma unroll
+                        for (int j = 0; j < RF_RQ; ++j) best[j] = __int_as_float(__float_as_int(best[j]) + wrapped);
+                    }
+                    {   // lane 0 (t >= 1) picks up columns last seen by lane 31: they wrap to the lowest rows (+1 ulp)
+                        const int wrapped = (lane == 0 && t != 0) ? 1 : 0;
+                        mnv.x = __int_as_float(__float_as_int(mnv.x) + wrapped), mnv.y = __int_as_float(__float_as_int(mnv.y) + wrapped);
+                        mnv.z = __int_as_float(__float_as_int(mnv.z) + wrapped), mnv.w = __int_as_float(__float_as_int(mnv.w) + wrapped);
+                    }
+                    float cm[RF_RC] = {mnv.x, mnv.y, mnv.z, mnv.w};  // running column minima, continued from the handed-over state
+    #pragma unroll
+                    for (int j = 0; j < RF_RQ; j += 2) {
+                        float d[2][4];
+    #pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const f32x2 px = pack2(qx[j + u], qx[j + u]), py = pack2(qy[j + u], qy[j + u]), pz = pack2(qz[j + u], qz[j + u]);
+                            unpack2(sqdist_exact2(px, py, pz, cur.x01, cur.y01, cur.z01), d[u][0], d[u][1]);
+                            unpack2(sqdist_exact2(px, py, pz, cur.x23, cur.y23, cur.z23), d[u][2], d[u][3]);
+                            const float old = best[j + u];
+                            float nb = min3(old, d[u][0], d[u][1]);
+                            nb = min3(nb, d[u][2], d[u][3]);
+                            best[j + u] = nb;
+                            rot[j + u] = (nb < old) ? t : rot[j + u];
+                        }
+    #pragma unroll
+                        for (int i = 0; i < RF_RC; ++i) cm[i] = min3(cm[i], d[0][i], d[1][i]);
+                    }
+                    rtv.x = (cm[0] < mnv.x) ? t : rtv.x, rtv.y = (cm[1] < mnv.y) ? t : rtv.y;
+                    rtv.z = (cm[2] < mnv.z) ? t : rtv.z, rtv.w = (cm[3] < mnv.w) ? t : rtv.w;
+                    mnv = make_float4(cm[0], cm[1], cm[2], cm[3]);
+                    *reinterpret_cast<float4 *>(wmn + g * RF_RC) = mnv;
+                    *reinterpret_cast<int4 *>(wrot + g * RF_RC) = rtv;
+                    __syncwarp();
+                    cur = nxt;
+                    g = gn;
                 }
-                {   // lane 0 (t >= 1) picks up columns last seen by lane 31: they wrap to the lowest rows (+1 ulp)
-                    const int wrapped = (lane == 0 && t != 0) ? 1 : 0;
-                    mnv.x = __int_as_float(__float_as_int(mnv.x) + wrapped), mnv.y = __int_as_float(__float_as_int(mnv.y) + wrapped);
-                    mnv.z = __int_as_float(__float_as_int(mnv.z) + wrapped), mnv.w = __int_as_float(__float_as_int(mnv.w) + wrapped);
-                }
-                float cm[RF_RC] = {mnv.x, mnv.y, mnv.z, mnv.w};  // running column minima, continued from the handed-over state
-#pragma unroll
-                for (int j = 0; j < RF_RQ; j += 2) {
-                    float d[2][4];
+    
+            } else {
+                // Software-pipelined form: the packed distance evaluations of row pair p+1 (FMA pipe) are issued next to
+                // the minima / rotation bookkeeping of row pair p (ALU pipe); warp-level barriers between the four stages
+                // of a rotation keep ptxas from sinking all ALU work behind all FMA work (which leaves one pipe idle
+                // per phase).  Arithmetic and comparison order per row / column are unchanged.
+                auto dist_pair = [&](int j, const RFGroup &c, float (&d)[2][4]) {
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const f32x2 px = pack2(qx[j + u], qx[j + u]), py = pack2(qy[j + u], qy[j + u]), pz = pack2(qz[j + u], qz[j + u]);
-                        unpack2(sqdist_exact2(px, py, pz, cur.x01, cur.y01, cur.z01), d[u][0], d[u][1]);
-                        unpack2(sqdist_exact2(px, py, pz, cur.x23, cur.y23, cur.z23), d[u][2], d[u][3]);
+                        unpack2(sqdist_exact2(px, py, pz, c.x01, c.y01, c.z01), d[u][0], d[u][1]);
+                        unpack2(sqdist_exact2(px, py, pz, c.x23, c.y23, c.z23), d[u][2], d[u][3]);
+                    }
+                };
+                auto fold_pair = [&](int j, const float (&d)[2][4], int t, float (&cm)[RF_RC]) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
                         const float old = best[j + u];
                         float nb = min3(old, d[u][0], d[u][1]);
                         nb = min3(nb, d[u][2], d[u][3]);
@@ -200,18 +260,57 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
                     }
 #pragma unroll
                     for (int i = 0; i < RF_RC; ++i) cm[i] = min3(cm[i], d[0][i], d[1][i]);
+                };
+                float dA[2][4], dB[2][4];
+                dist_pair(0, cur, dA);
+#pragma unroll 2
+                for (int t = 0; t < ((DBG & 1) ? 2 : 32); ++t) {
+                    const int gn = (g + 1) & 31;
+                    const RFGroup nxt = rf_load_group(cols_p, gn);
+                    float4 mnv = *reinterpret_cast<const float4 *>(wmn + g * RF_RC);
+                    int4 rtv = *reinterpret_cast<const int4 *>(wrot + g * RF_RC);
+                    {
+                        const int wrapped = (t == lane + 1) ? 1 : 0;
+#pragma unroll
+                        for (int j = 0; j < RF_RQ; ++j) best[j] = __int_as_float(__float_as_int(best[j]) + wrapped);
+                    }
+                    {
+                        const int wrapped = (lane == 0 && t != 0) ? 1 : 0;
+                        mnv.x = __int_as_float(__float_as_int(mnv.x) + wrapped), mnv.y = __int_as_float(__float_as_int(mnv.y) + wrapped);
+                        mnv.z = __int_as_float(__float_as_int(mnv.z) + wrapped), mnv.w = __int_as_float(__float_as_int(mnv.w) + wrapped);
+                    }
+                    float cm[RF_RC] = {mnv.x, mnv.y, mnv.z, mnv.w};
+                    dist_pair(2, cur, dB);
+                    fold_pair(0, dA, t, cm);
+                    if (PIPE == 1) __syncwarp();
+                    dist_pair(4, cur, dA);
+                    fold_pair(2, dB, t, cm);
+                    if (PIPE == 1) __syncwarp();
+                    dist_pair(6, cur, dB);
+                    fold_pair(4, dA, t, cm);
+                    if (PIPE == 1) __syncwarp();
+                    dist_pair(0, nxt, dA);   // first pair of the NEXT rotation (unused after the last one)
+                    fold_pair(6, dB, t, cm);
+                    rtv.x = (cm[0] < mnv.x) ? t : rtv.x, rtv.y = (cm[1] < mnv.y) ? t : rtv.y;
+                    rtv.z = (cm[2] < mnv.z) ? t : rtv.z, rtv.w = (cm[3] < mnv.w) ? t : rtv.w;
+                    mnv = make_float4(cm[0], cm[1], cm[2], cm[3]);
+                    *reinterpret_cast<float4 *>(wmn + g * RF_RC) = mnv;
+                    *reinterpret_cast<int4 *>(wrot + g * RF_RC) = rtv;
+                    __syncwarp();
+                    cur = nxt;
+                    g = gn;
                 }
-                rtv.x = (cm[0] < mnv.x) ? t : rtv.x, rtv.y = (cm[1] < mnv.y) ? t : rtv.y;
-                rtv.z = (cm[2] < mnv.z) ? t : rtv.z, rtv.w = (cm[3] < mnv.w) ? t : rtv.w;
-                mnv = make_float4(cm[0], cm[1], cm[2], cm[3]);
-                *reinterpret_cast<float4 *>(wmn + g * RF_RC) = mnv;
-                *reinterpret_cast<int4 *>(wrot + g * RF_RC) = rtv;
-                __syncwarp();
-                cur = nxt;
-                g = gn;
             }
 
+            if (DBG & 2) {  // timing experiment only: no re-evaluation, one dummy key per lane
+                float sm = 0.f; int sr = 0;
+#pragma unroll
+                for (int j = 0; j < RF_RQ; ++j) sm += best[j], sr += rot[j];
+                atomicMax(a.rowkey + (size_t)cloud * n + row0 + lrow0, ((u64)__float_as_uint(sm) << 32) | (unsigned)sr);
+            } else {
             // ---- rows: exact value, then the lowest column index of the winning group with d == value ----
+            // (branch-free: the 8 re-evaluations are independent so that their loads and FMA chains overlap)
+            u64 rkey[RF_RQ];
 #pragma unroll
             for (int j = 0; j < RF_RQ; ++j) {
                 float bv = best[j];
@@ -223,13 +322,16 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
                 const float d1 = sqdist_exact(qx[j], qy[j], qz[j], v0.y, v0.w, v1.y);
                 const float d2 = sqdist_exact(qx[j], qy[j], qz[j], v1.z, v2.x, v2.z);
                 const int k = (d0 == bv) ? 0 : (d1 == bv) ? 1 : (d2 == bv) ? 2 : 3;
-                const int row = row0 + lrow0 + j;
-                if (row < n) {
-                    const u64 key = ((u64)__float_as_uint(bv) << 32) | (unsigned)(cbase + gw * RF_RC + k);
-                    atomicMax(a.rowkey + (size_t)cloud * n + row, ~key);
-                }
+                rkey[j] = ~(((u64)__float_as_uint(bv) << 32) | (unsigned)(cbase + gw * RF_RC + k));
             }
-            // ---- columns: lane L finalises group L ----
+            {
+                const int nvalid = n - (row0 + lrow0);            // real rows of this lane (may be <= 0 or >= 8)
+                u64 *rk = a.rowkey + (size_t)cloud * n + row0 + lrow0;
+#pragma unroll
+                for (int j = 0; j < RF_RQ; ++j)
+                    if (j < nvalid) atomicMax(rk + j, rkey[j]);
+            }
+            // ---- columns: lane L finalises group L (padding columns included: their keys are never merged) ----
             {
                 const float4 *cp = reinterpret_cast<const float4 *>(cols_p + lane * 12);
                 const float4 v0 = cp[0], v1 = cp[1], v2 = cp[2];
@@ -239,29 +341,31 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
                 const int4 rtf = *reinterpret_cast<const int4 *>(wrot + lane * RF_RC);
                 const float mns[RF_RC] = {mnf.x, mnf.y, mnf.z, mnf.w};
                 const int rts[RF_RC] = {rtf.x, rtf.y, rtf.z, rtf.w};
+                u64 ckey[RF_RC];
 #pragma unroll
                 for (int i = 0; i < RF_RC; ++i) {
-                    const int lc = lane * RF_RC + i;  // round-local column
-                    if (lc < ncols) {
-                        float cv = mns[i];
-                        if (lane <= 30 && rts[i] <= lane) cv = bump_down(cv);  // bumped when lane 0 picked it up, never replaced
-                        const int vl = (31 - lane + rts[i]) & 31;              // lane whose rows produced the minimum
-                        const float4 *rp = reinterpret_cast<const float4 *>(rows_s + (wrow0 + vl * RF_RQ) * 3);  // 8 rows, 96 B
-                        float rv[24];
+                    float cv = mns[i];
+                    if (lane <= 30 && rts[i] <= lane) cv = bump_down(cv);  // bumped when lane 0 picked it up, never replaced
+                    const int vl = (31 - lane + rts[i]) & 31;              // lane whose rows produced the minimum
+                    const float4 *rp = reinterpret_cast<const float4 *>(rows_s + (wrow0 + vl * RF_RQ) * 3);  // 8 rows, 96 B
+                    float rv[24];
 #pragma unroll
-                        for (int q4 = 0; q4 < 6; ++q4) {
-                            const float4 t4 = rp[q4];
-                            rv[4 * q4 + 0] = t4.x, rv[4 * q4 + 1] = t4.y, rv[4 * q4 + 2] = t4.z, rv[4 * q4 + 3] = t4.w;
-                        }
-                        int k = RF_RQ - 1;
-#pragma unroll
-                        for (int q = RF_RQ - 2; q >= 0; --q) {
-                            const float dq = sqdist_exact(rv[3 * q], rv[3 * q + 1], rv[3 * q + 2], cxs[i], cys[i], czs[i]);
-                            k = (dq == cv) ? q : k;
-                        }
-                        wcolkey[warp][lc] = ((u64)__float_as_uint(cv) << 32) | (unsigned)(row0 + wrow0 + vl * RF_RQ + k);
+                    for (int q4 = 0; q4 < 6; ++q4) {
+                        const float4 t4 = rp[q4];
+                        rv[4 * q4 + 0] = t4.x, rv[4 * q4 + 1] = t4.y, rv[4 * q4 + 2] = t4.z, rv[4 * q4 + 3] = t4.w;
                     }
+                    int k = RF_RQ - 1;
+#pragma unroll
+                    for (int q = RF_RQ - 2; q >= 0; --q) {
+                        const float dq = sqdist_exact(rv[3 * q], rv[3 * q + 1], rv[3 * q + 2], cxs[i], cys[i], czs[i]);
+                        k = (dq == cv) ? q : k;
+                    }
+                    ckey[i] = ((u64)__float_as_uint(cv) << 32) | (unsigned)(row0 + wrow0 + vl * RF_RQ + k);
                 }
+                ulonglong2 *ck = reinterpret_cast<ulonglong2 *>(&wcolkey[warp][lane * RF_RC]);
+                ck[0] = make_ulonglong2(ckey[0], ckey[1]);
+                ck[1] = make_ulonglong2(ckey[2], ckey[3]);
+            }
             }
         }  // warp_active
         __syncthreads();
@@ -270,6 +374,13 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
 #pragma unroll
             for (int w = 1; w < RF_WARPS; ++w) key = wcolkey[w][tid] < key ? wcolkey[w][tid] : key;
             atomicMax(a.colkey + (size_t)cloud * m + cbase + tid, ~key);
+        }
+        if (more) {
+            if (nb_bytes) {
+                mbar_wait(&mbar, phase);
+                phase ^= 1;
+            }
+            __syncthreads();                             // next columns visible, wcolkey / cols_p consumed
         }
     }
 }
@@ -415,13 +526,13 @@ __device__ __forceinline__ void rf_inverse_radix(const RingNNArgs &a, unsigned i
 //   the radix fallback re-uses count.. as its two composite buffers (2*big <= 3*big).
 constexpr int RF_BUCKET_MAX = 48;
 
-__device__ __forceinline__ void rf_build_inverse(const RingNNArgs &a, unsigned int *smem_u, int cloud, bool dir2, int tid) {
+// `perm` [cnt], `begin` [ntgt] and `end` [ntgt] (begin and end contiguous) may live in global OR shared memory.
+__device__ __forceinline__ void rf_build_inverse(const RingNNArgs &a, unsigned int *smem_u, bool dir2, int tid, int *perm,
+                                                 int *begin, int *end) {
     __shared__ int scan_warp[RF_MERGE_THREADS / 32];
     __shared__ int max_bucket;
     const int cnt = dir2 ? a.m : a.n;      // sources: the points whose nearest neighbour was searched
     const int ntgt = dir2 ? a.n : a.m;     // targets: the points they can map to
-    int *inv = (dir2 ? a.inv2 : a.inv1) + (size_t)cloud * (cnt + 2 * ntgt);
-    int *perm = inv, *begin = inv + cnt, *end = begin + ntgt;
     if (!a.inv_fast) {  // big clouds: bitonic sort of the composites the caller wrote into the buffer
         rf_inverse_bitonic(a, smem_u, nullptr, cnt, ntgt, perm, begin, end, tid);
         return;
@@ -514,36 +625,10 @@ __device__ __forceinline__ float rf_block_sum(float v, float *warp_part, int tid
     return s;  // valid in thread 0
 }
 
-template <bool INVERT>
-__global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const RingNNArgs a) {
-    extern __shared__ __align__(16) unsigned int sortbuf[];  // INVERT: [sort_n] composites
-    __shared__ float warp_part[RF_MERGE_THREADS / 32];
-    __shared__ int flag;
-    const int tid = threadIdx.x;
-    const int cloud = blockIdx.x >> 1;
-    const bool dir2 = blockIdx.x & 1;
-    const int cnt = dir2 ? a.m : a.n;
-    u64 *src = (dir2 ? a.colkey : a.rowkey) + (size_t)cloud * cnt;
-    float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
-    int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
-    // Phase 1 only READS the keys: the device-scope fences of the loss tickets below then have no stores of this SM to
-    // drain (a fence issued after the 3 stores per element costs ~10 us).  Phase 2 (unpack_store) writes the outputs.
-    auto unpack_store = [&]() {
-        for (int e = tid; e < cnt; e += RF_MERGE_THREADS) {
-            const u64 key = ~__ldcg(src + e);
-            src[e] = 0ull;
-            dist[e] = __uint_as_float((unsigned)(key >> 32));
-            idx[e] = (int)(unsigned)(key & 0xffffffffu);
-            if (INVERT) sortbuf[e] = a.inv_fast ? (unsigned)(key & 0xffffffffu) : (((unsigned)(key & 0xffffffffu) << a.sort_shift) | (unsigned)e);
-        }
-        if (INVERT) rf_build_inverse(a, sortbuf, cloud, dir2, tid);
-    };
-    if (a.loss == nullptr) {
-        unpack_store();
-        return;
-    }
-    float v = 0.f;
-    for (int e = tid; e < cnt; e += RF_MERGE_THREADS) v += __uint_as_float((unsigned)((~__ldcg(src + e)) >> 32));  // fixed order
+// Deterministic loss: per-block partial -> two-level tickets (groups of RF_GROUP blocks, then groups), folded in block /
+// group order by the last arriver.  Call with all threads of the block; `v` = this thread's partial (fixed order).
+__device__ __forceinline__ void rf_loss_fold(const RingNNArgs &a, float v, float *warp_part, int *flag_p, int tid) {
+    int &flag = *flag_p;
     const float s = rf_block_sum(v, warp_part, tid);
     const int group = blockIdx.x / RF_GROUP, ngroups = (gridDim.x + RF_GROUP - 1) / RF_GROUP;
     const int gfirst = group * RF_GROUP, gcount = min(RF_GROUP, (int)gridDim.x - gfirst);
@@ -590,7 +675,183 @@ __global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const 
             }
         }
     }
+}
+
+template <bool INVERT>
+__global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const RingNNArgs a) {
+    extern __shared__ __align__(16) unsigned int sortbuf[];  // INVERT: [sort_n] composites
+    __shared__ float warp_part[RF_MERGE_THREADS / 32];
+    __shared__ int flag;
+    const int tid = threadIdx.x;
+    const int cloud = blockIdx.x >> 1;
+    const bool dir2 = blockIdx.x & 1;
+    const int cnt = dir2 ? a.m : a.n;
+    u64 *src = (dir2 ? a.colkey : a.rowkey) + (size_t)cloud * cnt;
+    float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
+    int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
+    // Phase 1 only READS the keys: the device-scope fences of the loss tickets below then have no stores of this SM to
+    // drain (a fence issued after the 3 stores per element costs ~10 us).  Phase 2 (unpack_store) writes the outputs.
+    auto unpack_store = [&]() {
+        for (int e = tid; e < cnt; e += RF_MERGE_THREADS) {
+            const u64 key = ~__ldcg(src + e);
+            src[e] = 0ull;
+            dist[e] = __uint_as_float((unsigned)(key >> 32));
+            idx[e] = (int)(unsigned)(key & 0xffffffffu);
+            if (INVERT) sortbuf[e] = a.inv_fast ? (unsigned)(key & 0xffffffffu) : (((unsigned)(key & 0xffffffffu) << a.sort_shift) | (unsigned)e);
+        }
+        if (INVERT) {
+            const int ntgt = dir2 ? a.n : a.m;
+            int *inv = (dir2 ? a.inv2 : a.inv1) + (size_t)cloud * (cnt + 2 * ntgt);
+            rf_build_inverse(a, sortbuf, dir2, tid, inv, inv + cnt, inv + cnt + ntgt);
+        }
+    };
+    if (a.loss == nullptr) {
+        unpack_store();
+        return;
+    }
+    float v = 0.f;
+    for (int e = tid; e < cnt; e += RF_MERGE_THREADS) v += __uint_as_float((unsigned)((~__ldcg(src + e)) >> 32));  // fixed order
+    rf_loss_fold(a, v, warp_part, &flag, tid);
     unpack_store();
+}
+
+// ---- fused tail of the training step: unpack + loss + inverse maps + BOTH gradients in one kernel -----------------
+// A cluster of two CTAs per cloud.  CTA `dir2 = rank` decodes the keys of its direction (dist / idx outputs, loss
+// partial), builds the inverse of that index map IN SHARED MEMORY and computes the gradient of the TARGET side:
+//     rank 0: rows -> columns (idx1), buckets over the columns,  grad_xyz2[k] = 2g[(b_k - a_idx2[k]) + sum_{i: idx1[i]=k} (b_k - a_i)]
+//     rank 1: columns -> rows (idx2), buckets over the rows,     grad_xyz1[i] = 2g[(a_i - b_idx1[i]) + sum_{k: idx2[k]=i} (a_i - b_k)]
+// (nndistance.cu:143-151).  The "own" term needs the OTHER direction's index, which the CTA reads from the other key array
+// itself; a cluster barrier orders those reads before the owner zero-restores its keys.  Both clouds' points are staged into
+// shared memory by bulk-TMA BEFORE griddepcontrol.wait, i.e. under the tail of the ring kernel when the launch is
+// programmatic (PDL); buckets, permutation and points are then read from shared memory only.  Summation order and
+// arithmetic are those of nn_grad_gather_kernel (ascending source index; buckets above GATHER_COOP warp-cooperatively),
+// so the gradients are bit-identical to the three-kernel path.
+struct RingFinishArgs {
+    const float *g;          // device scalar: upstream gradient of the loss
+    float *grad1, *grad2;    // [b,n,3], [b,m,3]
+};
+constexpr int GATHER_COOP_F = 32;  // == GATHER_COOP of nn_grad_gather_kernel (same summation tree)
+
+// shared memory (bytes) of the fused tail; 0 if the shape does not fit (caller falls back to the three-kernel path)
+static size_t rf_finish_smem_bytes(int n, int m) {
+    const size_t big = (size_t)(n > m ? n : m);
+    if (big > 8192) return 0;
+    size_t ints = 4 * big + RX_WARPS * RX_BINS + RX_BINS;  // sort area + radix rank table
+    ints += 4 * big;                                       // perm | begin | end | idxT (each <= big)
+    size_t bytes = ints * 4;
+    bytes = (bytes + 15) & ~(size_t)15;
+    bytes += (((size_t)n * 12 + 15) & ~(size_t)15) + (((size_t)m * 12 + 15) & ~(size_t)15);
+    return bytes <= 227 * 1024 ? bytes : 0;
+}
+
+__global__ void __launch_bounds__(RF_MERGE_THREADS, 1) nn_ring_finish_kernel(const RingNNArgs a, const RingFinishArgs f) {
+    extern __shared__ __align__(16) unsigned int fsm[];
+    __shared__ float warp_part[RF_MERGE_THREADS / 32];
+    __shared__ int flag;
+    __shared__ __align__(8) uint64_t mbar;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cloud = blockIdx.x >> 1;
+    const bool dir2 = blockIdx.x & 1;       // == rank in the cluster
+    const int cnt = dir2 ? a.m : a.n;       // sources of this direction
+    const int ntgt = dir2 ? a.n : a.m;      // targets (the side whose gradient this CTA produces)
+    const int big = a.n > a.m ? a.n : a.m;
+    unsigned int *sortarea = fsm;                                   // keys | count | cursor | pbuf, then the radix table
+    int *perm_s = reinterpret_cast<int *>(fsm + 4 * (size_t)big + RX_WARPS * RX_BINS + RX_BINS);
+    int *begin_s = perm_s + big, *end_s = begin_s + ntgt;           // begin/end contiguous (rf_build_inverse contract)
+    int *idxT_s = perm_s + 3 * (size_t)big;
+    size_t off = ((8 * (size_t)big + RX_WARPS * RX_BINS + RX_BINS) * 4 + 15) & ~(size_t)15;
+    float *T_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(fsm) + off);
+    off += ((size_t)ntgt * 12 + 15) & ~(size_t)15;
+    float *S_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(fsm) + off);
+    const float *__restrict__ Tg = (dir2 ? a.set1 : a.set2) + (size_t)cloud * ntgt * 3;
+    const float *__restrict__ Sg = (dir2 ? a.set2 : a.set1) + (size_t)cloud * cnt * 3;
+
+    // ---- prologue (independent of the ring kernel's results): both clouds into shared memory ----
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    const uint32_t tb = rf_bulk_bytes(Tg, ntgt), sb = rf_bulk_bytes(Sg, cnt);
+    if (tid == 0 && tb + sb) {
+        fence_proxy_async();
+        mbar_expect_tx(&mbar, tb + sb);
+        if (tb) bulk_g2s(T_s, Tg, tb, &mbar);
+        if (sb) bulk_g2s(S_s, Sg, sb, &mbar);
+    }
+    rf_stage_tail(T_s, Tg, ntgt, ntgt, 0.f, tb, tid, RF_MERGE_THREADS);
+    rf_stage_tail(S_s, Sg, cnt, cnt, 0.f, sb, tid, RF_MERGE_THREADS);
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the ring kernel's keys are complete and visible
+
+    // ---- keys: own direction (distance + index), other direction (index of every target point) ----
+    u64 *src = (dir2 ? a.colkey : a.rowkey) + (size_t)cloud * cnt;
+    const u64 *oth = (dir2 ? a.rowkey : a.colkey) + (size_t)cloud * ntgt;
+    float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
+    int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
+    unsigned int *keys_s = sortarea, *dtmp_s = sortarea + 3 * (size_t)big;  // distances parked in the (still unused) pbuf region
+    float v = 0.f;
+    for (int e = tid; e < cnt; e += RF_MERGE_THREADS) {
+        const u64 key = ~__ldcg(src + e);
+        keys_s[e] = (unsigned)(key & 0xffffffffu);
+        dtmp_s[e] = (unsigned)(key >> 32);
+        v += __uint_as_float((unsigned)(key >> 32));  // fixed order (same as nn_ring_unpack_kernel)
+    }
+    for (int k = tid; k < ntgt; k += RF_MERGE_THREADS) idxT_s[k] = (int)(unsigned)((~__ldcg(oth + k)) & 0xffffffffu);
+    // loss tickets first: nothing of this SM is in flight yet, so their fences are cheap
+    if (a.loss != nullptr) rf_loss_fold(a, v, warp_part, &flag, tid);
+    // both CTAs of the cluster have read both key arrays -> the owner may zero-restore its array
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    for (int e = tid; e < cnt; e += RF_MERGE_THREADS) {
+        src[e] = 0ull;
+        dist[e] = __uint_as_float(dtmp_s[e]);
+        idx[e] = (int)keys_s[e];
+    }
+    __syncthreads();  // dtmp consumed before the sort re-uses the region
+    rf_build_inverse(a, sortarea, dir2, tid, perm_s, begin_s, end_s);
+    if (tb + sb) mbar_wait(&mbar, 0);
+    __syncthreads();  // inverse complete, points visible
+
+    // ---- gradient of the target side: thread per point, buckets from shared memory ----
+    const float gs = __ldg(f.g) * 2.f;
+    float *G = (dir2 ? f.grad1 : f.grad2) + (size_t)cloud * ntgt * 3;
+    for (int base = 0; base < ntgt; base += RF_MERGE_THREADS) {  // block-uniform trip count
+        const int k = base + tid;
+        const bool valid = k < ntgt;
+        int pb = 0, pe = 0;
+        float px = 0.f, py = 0.f, pz = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+        if (valid) {
+            pb = begin_s[k], pe = end_s[k];
+            px = T_s[3 * k + 0], py = T_s[3 * k + 1], pz = T_s[3 * k + 2];
+            const int j = min(max(idxT_s[k], 0), cnt - 1);
+            ax = gs * (px - S_s[3 * j + 0]);
+            ay = gs * (py - S_s[3 * j + 1]);
+            az = gs * (pz - S_s[3 * j + 2]);
+        }
+        const bool bigb = valid && (pe - pb) > GATHER_COOP_F;
+        if (valid && !bigb) {
+            for (int p = pb; p < pe; ++p) {  // ascending source index: fixed summation order
+                const int e = perm_s[p];
+                ax += -(gs * (S_s[3 * e + 0] - px));
+                ay += -(gs * (S_s[3 * e + 1] - py));
+                az += -(gs * (S_s[3 * e + 2] - pz));
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, bigb);
+        while (todo) {  // big buckets: the whole warp, lane-strided ascending + fixed shuffle tree
+            const int srcl = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int b0 = __shfl_sync(0xffffffffu, pb, srcl), b1 = __shfl_sync(0xffffffffu, pe, srcl);
+            const float qx = __shfl_sync(0xffffffffu, px, srcl), qy = __shfl_sync(0xffffffffu, py, srcl), qz = __shfl_sync(0xffffffffu, pz, srcl);
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            for (int p = b0 + lane; p < b1; p += 32) {
+                const int e = perm_s[p];
+                sx += -(gs * (S_s[3 * e + 0] - qx));
+                sy += -(gs * (S_s[3 * e + 1] - qy));
+                sz += -(gs * (S_s[3 * e + 2] - qz));
+            }
+            sx = warp_sum(sx), sy = warp_sum(sy), sz = warp_sum(sz);
+            if (lane == srcl) ax += sx, ay += sy, az += sz;
+        }
+        if (valid) G[3 * k + 0] = ax, G[3 * k + 1] = ay, G[3 * k + 2] = az;
+    }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -639,8 +900,28 @@ bool nn_ring_inverse_supported(int n, int m) {
     return big <= 32768;  // composite (target << shift | source) in 30 bits, sort buffer <= 128 KB
 }
 
+bool nn_ring_step_supported(int n, int m) { return n > 0 && m > 0 && rf_finish_smem_bytes(n, m) != 0; }
+
+static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
+                               int *idx2, float *loss, int *inv1, int *inv2, const float *step_g, float *step_grad1,
+                               float *step_grad2, void *workspace, cudaStream_t stream);
+
 int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
                            int *idx2, float *loss, int *inv1, int *inv2, void *workspace, cudaStream_t stream) {
+    return nn_ring_launch_impl(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, inv1, inv2, nullptr, nullptr, nullptr, workspace,
+                               stream);
+}
+
+// forward + backward of the fused loss in two kernels (ring + fused tail); requires nn_ring_step_supported(n, m)
+int nn_ring_step_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_loss, float *dist1, int *idx1,
+                        float *dist2, int *idx2, float *loss, float *grad1, float *grad2, void *workspace, cudaStream_t stream) {
+    return nn_ring_launch_impl(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, nullptr, nullptr, grad_loss, grad1, grad2,
+                               workspace, stream);
+}
+
+static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
+                               int *idx2, float *loss, int *inv1, int *inv2, const float *step_g, float *step_grad1,
+                               float *step_grad2, void *workspace, cudaStream_t stream) {
     RingNNArgs a = {};
     const RFLayout L = rf_layout(b, n, m);
     unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
@@ -664,9 +945,41 @@ int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *
     }
     if (variant == 1) nn_ring_kernel<5><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     else if (variant == 2) nn_ring_kernel<6><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    else if (variant == 3) nn_ring_kernel<3><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    else if (variant == 20) nn_ring_kernel<4, 0, 1><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    else if (variant == 21) nn_ring_kernel<4, 0, 2><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    else if (variant == 22) nn_ring_kernel<4, 2, 1><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    else if (variant == 10) nn_ring_kernel<4, 1><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    else if (variant == 11) nn_ring_kernel<4, 2><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    else if (variant == 12) nn_ring_kernel<4, 3><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     else nn_ring_kernel<4><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     HP_LAUNCH_CHECK("nn_ring_kernel");
-    if (inv1 != nullptr && inv2 != nullptr) {
+    if (step_g != nullptr) {
+        const size_t smem = rf_finish_smem_bytes(n, m);
+        HP_REQUIRE(smem != 0, "nn ring step: clouds too large for the fused tail (n=%d m=%d)", n, m);
+        const int big = n > m ? n : m;
+        a.sort_n = 1 << ceil_log2(big);
+        a.sort_shift = ceil_log2(big);
+        a.inv_fast = 1;
+        RingFinishArgs f;
+        f.g = step_g, f.grad1 = step_grad1, f.grad2 = step_grad2;
+        static SmemAttrCache attr;
+        HP_CUDA(ensure_dynamic_smem(nn_ring_finish_kernel, smem, attr));
+        static int pdl = -1;
+        if (pdl < 0) {
+            const char *e = getenv("HP_NO_PDL");
+            pdl = (e && atoi(e)) ? 0 : 1;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)ugrid), cfg.blockDim = dim3(RF_MERGE_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+        cudaLaunchAttribute attrs[2];
+        attrs[0].id = cudaLaunchAttributeClusterDimension;
+        attrs[0].val.clusterDim.x = 2, attrs[0].val.clusterDim.y = 1, attrs[0].val.clusterDim.z = 1;
+        attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attrs, cfg.numAttrs = pdl ? 2 : 1;
+        HP_CUDA(cudaLaunchKernelEx(&cfg, nn_ring_finish_kernel, a, f));
+    } else if (inv1 != nullptr && inv2 != nullptr) {
         HP_REQUIRE(nn_ring_inverse_supported(n, m), "nn ring forward: clouds too large for the in-kernel inverse (n=%d m=%d)", n, m);
         a.inv1 = inv1, a.inv2 = inv2;
         const int big = n > m ? n : m;
@@ -683,7 +996,7 @@ int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *
     } else {
         nn_ring_unpack_kernel<false><<<(unsigned)ugrid, RF_MERGE_THREADS, 0, stream>>>(a);
     }
-    HP_LAUNCH_CHECK("nn_ring_unpack_kernel");
+    HP_LAUNCH_CHECK("nn_ring_unpack_kernel / nn_ring_finish_kernel");
     return HP_OK;
 }
 

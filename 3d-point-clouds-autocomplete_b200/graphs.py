@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import torch
 
-from .chamfer import chamfer_backward, chamfer_forward
+from .chamfer import chamfer_step, chamfer_step_supported
 from .target_network import target_network_backward, target_network_forward, target_network_num_weights
 
 
@@ -50,13 +50,12 @@ class ChamferStepGraph:
             self._one = torch.ones((), device=self.device)
 
             def step():
-                loss, d1, i1, d2, i2, inv = chamfer_forward(self.xyz1, self.xyz2, want_inverse=True)
-                g1, g2 = chamfer_backward(self.xyz1, self.xyz2, i1, i2, self._one, inv)
-                return loss, d1, i1, d2, i2, g1, g2
+                return chamfer_step(self.xyz1, self.xyz2, self._one)
 
             self.graph, outs, self._stream = _capture(step, self.device)
             self.loss, self.dist1, self.idx1, self.dist2, self.idx2, self.grad_xyz1, self.grad_xyz2 = outs
-            self.launches_per_replay = 3  # ring forward + unpack + backward
+            # ring forward + fused tail (unpack, loss, inverse maps, both gradients); big clouds: ring + unpack + gather
+            self.launches_per_replay = 2 if chamfer_step_supported(batch, n, m) else 3
 
             self.host_graph = None
             if with_host_io:
@@ -71,8 +70,7 @@ class ChamferStepGraph:
                 def host_step():
                     self.xyz1.copy_(self.xyz1_host, non_blocking=True)
                     self.xyz2.copy_(self.xyz2_host, non_blocking=True)
-                    loss, _d1, i1, _d2, i2, inv = chamfer_forward(self.xyz1, self.xyz2, want_inverse=True)
-                    g1, g2 = chamfer_backward(self.xyz1, self.xyz2, i1, i2, self._one, inv)
+                    loss, _d1, _i1, _d2, _i2, g1, g2 = chamfer_step(self.xyz1, self.xyz2, self._one)
                     self.loss_host.copy_(loss, non_blocking=True)
                     self.grad_xyz1_host.copy_(g1, non_blocking=True)
                     self.grad_xyz2_host.copy_(g2, non_blocking=True)
@@ -133,8 +131,8 @@ class HotPathStepGraph:
         loss = loss_coef * ChamferLoss(gt, rec)                            (core/epoch_loops.py:25-26)
         d loss / d weights                                                  (what autograd hands the hypernetwork)
 
-    as one CUDA graph: fused TargetNetwork forward -> ring Chamfer forward -> gather Chamfer backward -> fused
-    TargetNetwork backward.  Static inputs: ``weights`` [B,W], ``points`` [B,N,3], ``gt`` [B,N,3]; outputs refreshed in
+    as one CUDA graph: fused TargetNetwork forward -> ring Chamfer forward -> fused Chamfer tail (unpack + loss + both
+    gradients) -> fused TargetNetwork backward.  Static inputs: ``weights`` [B,W], ``points`` [B,N,3], ``gt`` [B,N,3]; outputs refreshed in
     place: ``rec`` [B,N,3], ``loss`` [1] (unscaled Chamfer sum), ``grad_weights`` [B,W]."""
 
     def __init__(self, batch: int, n: int, layer_out_channels, use_bias: bool, device, loss_coef: float = 0.05):
@@ -149,13 +147,12 @@ class HotPathStepGraph:
 
             def step():
                 rec = target_network_forward(self.weights, self.points, loc, use_bias, False)
-                loss, _d1, i1, _d2, i2, inv = chamfer_forward(self.gt, rec, want_inverse=True)
-                _g_gt, g_rec = chamfer_backward(self.gt, rec, i1, i2, self._coef, inv)
+                loss, _d1, _i1, _d2, _i2, _g_gt, g_rec = chamfer_step(self.gt, rec, self._coef)
                 gw, _ = target_network_backward(self.weights, self.points, g_rec, loc, use_bias, False)
                 return rec, loss, gw
 
             self.graph, (self.rec, self.loss, self.grad_weights), self._stream = _capture(step, self.device)
-            self.launches_per_replay = 5
+            self.launches_per_replay = 4 if chamfer_step_supported(batch, n, n) else 5
 
     def replay(self):
         self.graph.replay()

@@ -120,6 +120,18 @@ HP_API int hp_chamfer_forward_inv(int b, int n, const float *xyz1, int m, const 
 HP_API int hp_chamfer_backward_inv(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1,
                             const int *idx2, const int *inv1, const int *inv2, const float *grad_loss,
                             float *grad_xyz1, float *grad_xyz2, void *stream);
+/* One training step of the fused loss in TWO kernels: loss = ChamferLoss(xyz1, xyz2) (losses/champfer_loss.py:11-17)
+ * and its gradients for the upstream scalar grad_loss[0] (device memory, known before the forward is enqueued -- e.g. the
+ * trainer's constant loss coefficient, core/epoch_loops.py:25-26).  The ring kernel is followed by a single tail kernel
+ * (launched programmatically dependent, so its prologue overlaps the ring kernel's tail) that decodes distances and
+ * indices, reduces the loss in a fixed order, inverts both index maps in shared memory and gathers both gradients.
+ * Outputs are bit-identical to hp_chamfer_forward_inv + hp_chamfer_backward_inv.  hp_chamfer_step_supported returns 0
+ * when the clouds do not fit the tail kernel's shared memory (about 4000 points per cloud).  Workspace as for
+ * hp_chamfer_forward. */
+HP_API int hp_chamfer_step_supported(int b, int n, int m);
+HP_API int hp_chamfer_step(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_loss,
+                    float *dist1, int *idx1, float *dist2, int *idx2, float *loss, float *grad_xyz1,
+                    float *grad_xyz2, void *workspace, size_t workspace_bytes, void *stream);
 /* hp_nndistancegrad (per-point upstream gradients, nn_distance.py:28-39) as the same gather over inverse maps from
  * hp_chamfer_forward_inv (whose `loss` may be NULL when only distances and indices are wanted). */
 HP_API int hp_nndistancegrad_inv(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,

@@ -355,3 +355,72 @@ def test_random_shapes_sweep_vs_oracle(hp, oracle):
         np.testing.assert_allclose(cd.grad.cpu().numpy(), ogb, rtol=1e-5, atol=1e-6, err_msg=str((b, n, m, kind)))
         ref_loss = float(od1.sum(dtype=np.float64) + od2.sum(dtype=np.float64))
         assert abs(float(loss.detach()) - ref_loss) <= 1e-5 * max(abs(ref_loss), 1e-12)
+
+
+@pytest.mark.parametrize("b,n,m,kind", [(3, 700, 1100, "uniform"), (32, 2048, 2048, "uniform"), (2, 1500, 300, "ties"),
+                                        (1, 1, 7, "uniform"), (2, 7, 1, "uniform"), (2, 64, 64, "zero"), (2, 2048, 2048, "zero"),
+                                        (2, 2048, 2048, "skewed"), (3, 1023, 2049, "lattice"), (2, 4097, 4100, "uniform"),
+                                        (1, 9000, 300, "uniform")])
+def test_fused_step_equals_three_kernel_path_and_oracle(hp, oracle, b, n, m, kind):
+    """chamfer_step (ring kernel + ONE tail kernel: unpack, loss, inverse maps in shared memory, both gradients) must give the
+    same bits as chamfer_forward(want_inverse=True) + chamfer_backward, repeatedly (the workspace returns to zero), and match
+    the oracle.  The last shape does not fit the tail kernel's shared memory and takes the three-kernel path."""
+    g = torch.Generator().manual_seed(3 * n + m)
+    if kind == "ties":
+        a = torch.randint(0, 3, (b, n, 3), generator=g).float() / 2
+        c = torch.randint(0, 3, (b, m, 3), generator=g).float() / 2
+    elif kind == "zero":
+        a = torch.zeros(b, n, 3)
+        c = torch.rand(b, m, 3, generator=g)
+    elif kind == "skewed":
+        a = torch.rand(b, n, 3, generator=g) - 0.5
+        c = (torch.rand(b, m, 3, generator=g) - 0.5) * 0.05
+    elif kind == "lattice":
+        a, c = _clouds((b, n, 3), (b, m, 3), "lattice", seed=n)
+    else:
+        a, c = torch.rand(b, n, 3, generator=g) - 0.5, torch.rand(b, m, 3, generator=g) - 0.5
+    ad, cd = a.to(DEV), c.to(DEV)
+    gl = torch.tensor(0.7, device=DEV)
+    assert hp.chamfer_step_supported(b, n, m) == (max(n, m) <= 4000)  # shared-memory bound of the tail kernel
+    loss0, e1, j1, e2, j2, inv = hp.chamfer_forward(ad, cd, want_inverse=True)
+    ha, hb = hp.chamfer_backward(ad, cd, j1, j2, gl, inv)
+    for rep in range(3):
+        loss, d1, i1, d2, i2, ga, gb = hp.chamfer_step(ad, cd, gl)
+        assert torch.equal(i1, j1) and torch.equal(i2, j2) and torch.equal(d1, e1) and torch.equal(d2, e2), rep
+        assert torch.equal(loss, loss0), (rep, float(loss), float(loss0))
+        assert torch.equal(ga, ha) and torch.equal(gb, hb), rep
+    # the three-kernel path still works on the same (zero-restored) workspace
+    loss1, f1, k1, f2, k2 = hp.chamfer_forward(ad, cd)
+    assert torch.equal(loss1, loss0) and torch.equal(k1, j1) and torch.equal(k2, j2)
+    od1, oi1, od2, oi2 = oracle.nn_distance(a.numpy(), c.numpy())
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+    oga, ogb = oracle.nn_distance_grad(a.numpy(), c.numpy(), oi1, oi2, np.full((b, n), 0.7, np.float32), np.full((b, m), 0.7, np.float32))
+    big_buckets = max(int(torch.bincount(i1.flatten().long()).max()), int(torch.bincount(i2.flatten().long()).max())) > 32
+    rtol = 1e-4 if big_buckets else 1e-5  # thousands of fp32 terms per sum in the degenerate cases
+    np.testing.assert_allclose(ga.cpu().numpy(), oga, rtol=rtol, atol=1e-6)
+    np.testing.assert_allclose(gb.cpu().numpy(), ogb, rtol=rtol, atol=1e-6)
+    ref_loss = float(od1.sum(dtype=np.float64) + od2.sum(dtype=np.float64))
+    assert abs(float(loss) - ref_loss) <= 1e-5 * max(abs(ref_loss), 1e-12)
+
+
+def test_fused_step_unaligned_views_and_graph(hp):
+    """Clouds whose base addresses are not 16-byte aligned (bulk-TMA falls back to plain loads) and the captured graph
+    (programmatic dependent launch inside a CUDA graph) give the same bits as the eager three-kernel path."""
+    g = torch.Generator().manual_seed(77)
+    buf_a = (torch.rand(2 * 1001 * 3 + 1, generator=g) - 0.5).to(DEV)
+    buf_c = (torch.rand(2 * 515 * 3 + 1, generator=g) - 0.5).to(DEV)
+    a, c = buf_a[1:].view(2, 1001, 3), buf_c[1:].view(2, 515, 3)
+    gl = torch.tensor(1.0, device=DEV)
+    loss0, e1, j1, e2, j2, inv = hp.chamfer_forward(a.clone(), c.clone(), want_inverse=True)
+    ha, hb = hp.chamfer_backward(a.clone(), c.clone(), j1, j2, gl, inv)
+    loss, d1, i1, d2, i2, ga, gb = hp.chamfer_step(a, c, gl)
+    assert torch.equal(loss, loss0) and torch.equal(i1, j1) and torch.equal(i2, j2) and torch.equal(ga, ha) and torch.equal(gb, hb)
+    step = hp.ChamferStepGraph(2, 1001, 515, DEV)
+    step.xyz1.copy_(a)
+    step.xyz2.copy_(c)
+    for _ in range(3):
+        step.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(step.loss, loss0) and torch.equal(step.grad_xyz1, ha) and torch.equal(step.grad_xyz2, hb)
+    assert torch.equal(step.idx1, j1) and torch.equal(step.dist2, e2)
