@@ -630,6 +630,30 @@ __device__ __forceinline__ float rf_block_sum(float v, float *warp_part, int tid
 __device__ __forceinline__ void rf_loss_fold(const RingNNArgs &a, float v, float *warp_part, int *flag_p, int tid) {
     int &flag = *flag_p;
     const float s = rf_block_sum(v, warp_part, tid);
+    if (gridDim.x <= RF_MERGE_THREADS) {
+        // up to 1024 blocks: ONE ticket; the last arriver folds all partials with the fixed block_sum tree (thread i holds
+        // block i's partial).  One fence + one atomic on everybody's path, one more fence + load for the last block.
+        if (tid == 0) {
+            a.losspart[blockIdx.x] = s;
+            __threadfence();
+            flag = (atomicAdd(a.counters, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (flag) {  // block-uniform
+            __threadfence();
+            float t = 0.f;
+            if (tid < (int)gridDim.x) {
+                t = __ldcg(a.losspart + tid);
+                a.losspart[tid] = 0.f;  // the whole workspace returns to zero (its layout moves with the shape)
+            }
+            const float tot = rf_block_sum(t, warp_part, tid);
+            if (tid == 0) {
+                a.loss[0] = tot;
+                a.counters[0] = 0u;
+            }
+        }
+        return;
+    }
     const int group = blockIdx.x / RF_GROUP, ngroups = (gridDim.x + RF_GROUP - 1) / RF_GROUP;
     const int gfirst = group * RF_GROUP, gcount = min(RF_GROUP, (int)gridDim.x - gfirst);
     if (tid == 0) {
@@ -776,23 +800,28 @@ __global__ void __launch_bounds__(RF_MERGE_THREADS, 1) nn_ring_finish_kernel(con
         if (tb) bulk_g2s(T_s, Tg, tb, &mbar);
         if (sb) bulk_g2s(S_s, Sg, sb, &mbar);
     }
-    rf_stage_tail(T_s, Tg, ntgt, ntgt, 0.f, tb, tid, RF_MERGE_THREADS);
-    rf_stage_tail(S_s, Sg, cnt, cnt, 0.f, sb, tid, RF_MERGE_THREADS);
+    if (tb != (uint32_t)ntgt * 12u) rf_stage_tail(T_s, Tg, ntgt, ntgt, 0.f, tb, tid, RF_MERGE_THREADS);  // uniform; rare
+    if (sb != (uint32_t)cnt * 12u) rf_stage_tail(S_s, Sg, cnt, cnt, 0.f, sb, tid, RF_MERGE_THREADS);
+    unsigned int *keys_s = sortarea, *dtmp_s = sortarea + 3 * (size_t)big;  // distances parked in the (still unused) pbuf region
+    int *count = reinterpret_cast<int *>(sortarea) + big, *cursor = count + big, *pbuf = cursor + big;
+    for (int i = tid; i < ntgt; i += RF_MERGE_THREADS) count[i] = 0;
+    __syncthreads();
 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the ring kernel's keys are complete and visible
 
-    // ---- keys: own direction (distance + index), other direction (index of every target point) ----
+    // ---- keys: own direction (distance + index, histogram of the targets), other direction (index of every target point) ----
     u64 *src = (dir2 ? a.colkey : a.rowkey) + (size_t)cloud * cnt;
     const u64 *oth = (dir2 ? a.rowkey : a.colkey) + (size_t)cloud * ntgt;
     float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
     int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
-    unsigned int *keys_s = sortarea, *dtmp_s = sortarea + 3 * (size_t)big;  // distances parked in the (still unused) pbuf region
     float v = 0.f;
     for (int e = tid; e < cnt; e += RF_MERGE_THREADS) {
         const u64 key = ~__ldcg(src + e);
-        keys_s[e] = (unsigned)(key & 0xffffffffu);
+        const unsigned tgt = (unsigned)(key & 0xffffffffu);
+        keys_s[e] = tgt;
         dtmp_s[e] = (unsigned)(key >> 32);
         v += __uint_as_float((unsigned)(key >> 32));  // fixed order (same as nn_ring_unpack_kernel)
+        atomicAdd(&count[min(tgt, (unsigned)(ntgt - 1))], 1);
     }
     for (int k = tid; k < ntgt; k += RF_MERGE_THREADS) idxT_s[k] = (int)(unsigned)((~__ldcg(oth + k)) & 0xffffffffu);
     // loss tickets first: nothing of this SM is in flight yet, so their fences are cheap
@@ -804,14 +833,103 @@ __global__ void __launch_bounds__(RF_MERGE_THREADS, 1) nn_ring_finish_kernel(con
         dist[e] = __uint_as_float(dtmp_s[e]);
         idx[e] = (int)keys_s[e];
     }
-    __syncthreads();  // dtmp consumed before the sort re-uses the region
+    __syncthreads();  // histogram complete; dtmp consumed before the placement re-uses the region
+
+    // ---- exclusive scan of the histogram (contiguous chunk per thread, warp scan, scan of the warp totals) + largest bucket ----
+    __shared__ int scan_warp_f[RF_MERGE_THREADS / 32];
+    __shared__ int max_bucket_f;
+    const int per = (ntgt + RF_MERGE_THREADS - 1) / RF_MERGE_THREADS;
+    const int lo = min(ntgt, tid * per), hi = min(ntgt, lo + per);
+    int local = 0, lmax = 0;
+    for (int i = lo; i < hi; ++i) local += count[i], lmax = max(lmax, count[i]);
+    int inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    lmax = __reduce_max_sync(0xffffffffu, lmax);
+    if (lane == 31) scan_warp_f[tid >> 5] = inc;
+    if (tid == 0) max_bucket_f = 0;
+    __syncthreads();
+    if (tid < 32) {
+        const int w = scan_warp_f[tid];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, winc, o);
+            if (tid >= o) winc += u;
+        }
+        scan_warp_f[tid] = winc - w;  // exclusive prefix of the warp totals
+    }
+    if (lane == 0 && lmax > 0) atomicMax(&max_bucket_f, lmax);
+    __syncthreads();
+    const bool lean = max_bucket_f <= GATHER_COOP_F;  // block-uniform
+
+    const float gs = __ldg(f.g) * 2.f;
+    float *G = (dir2 ? f.grad1 : f.grad2) + (size_t)cloud * ntgt * 3;
+    if (lean) {
+        // ---- benign assignment (no bucket above GATHER_COOP): placement in arrival order, the gradient thread orders its
+        //      (tiny) bucket itself -- a 4-element sorting network, or ascending selection for 5..32 entries ----
+        {
+            int run = scan_warp_f[tid >> 5] + inc - local;
+            for (int i = lo; i < hi; ++i) {
+                const int c = count[i];
+                count[i] = run;   // begin
+                cursor[i] = run;  // becomes end after the placement
+                run += c;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < cnt; e += RF_MERGE_THREADS) pbuf[atomicAdd(&cursor[min(keys_s[e], (unsigned)(ntgt - 1))], 1)] = e;
+        if (tb + sb) mbar_wait(&mbar, 0);
+        __syncthreads();  // buckets complete, points visible
+        for (int k = tid; k < ntgt; k += RF_MERGE_THREADS) {
+            const int b0 = count[k], sz = cursor[k] - b0;
+            const float px = T_s[3 * k + 0], py = T_s[3 * k + 1], pz = T_s[3 * k + 2];
+            const int j = min(max(idxT_s[k], 0), cnt - 1);
+            float ax = gs * (px - S_s[3 * j + 0]);
+            float ay = gs * (py - S_s[3 * j + 1]);
+            float az = gs * (pz - S_s[3 * j + 2]);
+            auto acc = [&](int e) {
+                ax += -(gs * (S_s[3 * e + 0] - px));
+                ay += -(gs * (S_s[3 * e + 1] - py));
+                az += -(gs * (S_s[3 * e + 2] - pz));
+            };
+            if (sz <= 4) {
+                int e0 = sz > 0 ? pbuf[b0] : 0x7fffffff, e1 = sz > 1 ? pbuf[b0 + 1] : 0x7fffffff;
+                int e2 = sz > 2 ? pbuf[b0 + 2] : 0x7fffffff, e3 = sz > 3 ? pbuf[b0 + 3] : 0x7fffffff;
+                int t;
+                t = min(e0, e1), e1 = max(e0, e1), e0 = t;
+                t = min(e2, e3), e3 = max(e2, e3), e2 = t;
+                t = min(e0, e2), e2 = max(e0, e2), e0 = t;
+                t = min(e1, e3), e3 = max(e1, e3), e1 = t;
+                t = min(e1, e2), e2 = max(e1, e2), e1 = t;
+                if (sz > 0) acc(e0);
+                if (sz > 1) acc(e1);
+                if (sz > 2) acc(e2);
+                if (sz > 3) acc(e3);
+            } else {
+                int prev = -1;
+                for (int it = 0; it < sz; ++it) {  // ascending selection: sources are distinct
+                    int cur = 0x7fffffff;
+                    for (int p = b0; p < b0 + sz; ++p) {
+                        const int e = pbuf[p];
+                        cur = (e > prev && e < cur) ? e : cur;
+                    }
+                    acc(cur);
+                    prev = cur;
+                }
+            }
+            G[3 * k + 0] = ax, G[3 * k + 1] = ay, G[3 * k + 2] = az;
+        }
+        return;
+    }
+
+    // ---- skewed assignment: data-independent stable sort (rf_build_inverse), buckets above GATHER_COOP warp-cooperatively ----
     rf_build_inverse(a, sortarea, dir2, tid, perm_s, begin_s, end_s);
     if (tb + sb) mbar_wait(&mbar, 0);
     __syncthreads();  // inverse complete, points visible
-
-    // ---- gradient of the target side: thread per point, buckets from shared memory ----
-    const float gs = __ldg(f.g) * 2.f;
-    float *G = (dir2 ? f.grad1 : f.grad2) + (size_t)cloud * ntgt * 3;
     for (int base = 0; base < ntgt; base += RF_MERGE_THREADS) {  // block-uniform trip count
         const int k = base + tid;
         const bool valid = k < ntgt;

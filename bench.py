@@ -200,7 +200,7 @@ def _other_paths(torch, hp, dev, fp32_peak, mufu_peak, flush, stream, barrier):
     hpg.weights.copy_(tng.weights)
     ms = statistics.mean(_events_timed(torch, hpg.replay, 20, 3, flush, stream, barrier))
     out["c4_hot_path_step_B64_N2048"] = {
-        "ms": ms, "what": "fused TargetNetwork fwd -> Chamfer fwd (ring) -> Chamfer bwd (gather) -> TargetNetwork bwd, one CUDA graph "
+        "ms": ms, "what": "fused TargetNetwork fwd -> Chamfer ring kernel -> Chamfer tail (loss + both gradients) -> TargetNetwork bwd, one CUDA graph "
                           "(config C4 without encoder / hypernetwork)",
         "algorithmic_tflops": ((37440.0 + 74688.0) * tb * tn + 16.0 * tb * tn * tn) / ms / 1e9}
     # the reference's op sequence for the same hot path on this GPU: per-sample torch loop (model/full_model.py:70-74,
@@ -321,8 +321,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # The step, captured once as a CUDA graph (the repo's public API for launch-bound steps, graphs.py):
-    # forward (both directions + loss: ring kernel + unpack) and backward (both gradients).
+    # The step, captured once as a CUDA graph (the repo's public API for launch-bound steps, graphs.py): the ring kernel
+    # (all-pairs distances, both directions) + ONE tail kernel (distances/indices, loss, inverse maps, both gradients).
     step = hp.ChamferStepGraph(B, N, M, dev, with_host_io=True)
     step.xyz1.copy_(a_h.to(dev))
     step.xyz2.copy_(b_h.to(dev))
@@ -435,7 +435,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_s * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": _config({"launch": "step captured once as a CUDA graph (ChamferStepGraph), one replay per step"}),
+            "config": _config({"launch": "step captured once as a CUDA graph (ChamferStepGraph: nn_ring_kernel + nn_ring_finish_kernel, "
+                                        "the second launched programmatically dependent), one replay per step"}),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": step.d2h_bytes,
                     "ms_per_step": pipe_ms,
@@ -447,7 +448,7 @@ def run_ours(args):
                     "unpipelined_api": "ChamferStepGraph.run_from_host: the same copies and step serialised in one graph"},
             "eager_api": {"ms_per_step": statistics.mean(eager_ms), "value": PAIRS_PER_STEP / (statistics.mean(eager_ms) * 1e-3),
                           "note": "ChamferLoss()(preds, gts); loss.backward() through torch autograd, no graph: CPU launch path bound"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": step.launches_per_replay * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "other_paths": other,

@@ -360,11 +360,12 @@ def test_random_shapes_sweep_vs_oracle(hp, oracle):
 @pytest.mark.parametrize("b,n,m,kind", [(3, 700, 1100, "uniform"), (32, 2048, 2048, "uniform"), (2, 1500, 300, "ties"),
                                         (1, 1, 7, "uniform"), (2, 7, 1, "uniform"), (2, 64, 64, "zero"), (2, 2048, 2048, "zero"),
                                         (2, 2048, 2048, "skewed"), (3, 1023, 2049, "lattice"), (2, 4097, 4100, "uniform"),
-                                        (1, 9000, 300, "uniform")])
+                                        (1, 9000, 300, "uniform"), (600, 16, 24, "uniform")])
 def test_fused_step_equals_three_kernel_path_and_oracle(hp, oracle, b, n, m, kind):
     """chamfer_step (ring kernel + ONE tail kernel: unpack, loss, inverse maps in shared memory, both gradients) must give the
     same bits as chamfer_forward(want_inverse=True) + chamfer_backward, repeatedly (the workspace returns to zero), and match
-    the oracle.  The last shape does not fit the tail kernel's shared memory and takes the three-kernel path."""
+    the oracle.  (1, 9000, 300) does not fit the tail kernel's shared memory and takes the three-kernel path; batch 600 is
+    above 1024 blocks, where the loss is folded through two ticket levels instead of one."""
     g = torch.Generator().manual_seed(3 * n + m)
     if kind == "ties":
         a = torch.randint(0, 3, (b, n, 3), generator=g).float() / 2
