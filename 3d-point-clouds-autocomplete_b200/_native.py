@@ -55,6 +55,7 @@ SIGNATURES = {
     "hp_target_network_backward": (_int, [_int, _int, _int, ctypes.POINTER(_int), _int, _vp, _vp, _ll, _vp, _int, _vp, _vp,
                                           _vp, _sz, _vp]),
     "hp_pairwise_cd": (_int, [_int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
+    "hp_pairwise_cd_pairs": (_int, [_ll, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_measure_peak": (_int, [_int, _int, ctypes.POINTER(ctypes.c_double), _vp]),
 }
 

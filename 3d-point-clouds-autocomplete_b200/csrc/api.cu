@@ -247,11 +247,12 @@ extern "C" const char *hp_last_error_message(void) { return g_err; }
 
 extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *stream_v) {
     HP_REQUIRE(rate_host != nullptr, "hp_measure_peak: null result pointer");
-    HP_REQUIRE(kind >= 0 && kind <= 9 && iters > 0, "hp_measure_peak: bad kind/iters (%d, %d)", kind, iters);
+    HP_REQUIRE(kind >= 0 && kind <= 12 && iters > 0, "hp_measure_peak: bad kind/iters (%d, %d)", kind, iters);
     cudaStream_t stream = (cudaStream_t)stream_v;
     float *sink = nullptr;
     HP_CUDA(cudaMalloc(&sink, sizeof(float)));  // measurement helper only: not on the product path
-    const int blocks = kind >= 7 ? sm_count() * 4 : sm_count() * 8, threads = kind >= 7 ? 128 : 256;
+    // kinds 10 / 11 / 12: kind 9 with 3 / 2 / 1 warps per scheduler instead of 4 (how the issue rate holds up in a thin tail)
+    const int blocks = kind >= 10 ? sm_count() * (13 - kind) : kind >= 7 ? sm_count() * 4 : sm_count() * 8, threads = kind >= 7 ? 128 : 256;
     cudaEvent_t e0, e1;
     HP_CUDA(cudaEventCreate(&e0));
     HP_CUDA(cudaEventCreate(&e1));
@@ -267,7 +268,7 @@ extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *str
             case 6: peak_mma_tf32_kernel<<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
             case 7: ring_pattern_kernel<7><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
             case 8: ring_pattern_kernel<8><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
-            case 9: ring_pattern_kernel<9><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
+            case 9: case 10: case 11: case 12: ring_pattern_kernel<9><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
             default: peak_kernel<5><<<blocks, threads, 0, stream>>>(iters, 1.0f, sink); break;
         }
         HP_CUDA(cudaEventRecord(e1, stream));
@@ -289,7 +290,7 @@ extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *str
         case 3: per_thread_iter = 1024 * 2 * 8.0; break;   // 1024 candidates x 2 queries x 8 algorithmic FLOP
         case 6: per_thread_iter = 8 * 2.0 * 16 * 8 * 8 / 32.0; break;
         case 7: per_thread_iter = 32 * 112.0; break;       // packed FMA-pipe instructions per lane
-        case 8: case 9: per_thread_iter = 32 * 96.0; break;  // 8 mma per warp-iteration, 2048 FLOP each, per thread
+        case 8: case 9: case 10: case 11: case 12: per_thread_iter = 32 * 96.0; break;  // 8 mma per warp-iteration, 2048 FLOP each, per thread
         default: per_thread_iter = 1024 * 4 * 8.0; break;  // 1024 candidates x 4 queries x 8 algorithmic FLOP
     }
     *rate_host = threads_total * per_thread_iter * (double)iters / ((double)best_ms * 1e-3);

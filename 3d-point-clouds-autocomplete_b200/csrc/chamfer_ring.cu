@@ -124,8 +124,9 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
             if (rb) bulk_g2s(rows_s, rsrc, rb, &mbar);
             if (cb) bulk_g2s(cols_raw, csrc, cb, &mbar);
         }
-        rf_stage_tail(rows_s, rsrc, nrows, RF_ROWS, RF_PAD_ROW, rb, tid, RF_WARPS * 32);
-        rf_stage_tail(cols_raw, csrc, ncols0, RF_COLS, RF_PAD_COL, cb, tid, RF_WARPS * 32);
+        // block-uniform: nothing to do when the bulk copies cover whole, unpadded tiles (the common case)
+        if (rb != (uint32_t)RF_ROWS * 12u) rf_stage_tail(rows_s, rsrc, nrows, RF_ROWS, RF_PAD_ROW, rb, tid, RF_WARPS * 32);
+        if (cb != (uint32_t)RF_COLS * 12u) rf_stage_tail(cols_raw, csrc, ncols0, RF_COLS, RF_PAD_COL, cb, tid, RF_WARPS * 32);
         if (rb + cb) {
             mbar_wait(&mbar, phase);
             phase ^= 1;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
                 mbar_expect_tx(&mbar, nb_bytes);
                 bulk_g2s(cols_raw, csrc, nb_bytes, &mbar);
             }
-            rf_stage_tail(cols_raw, csrc, ncols_n, RF_COLS, RF_PAD_COL, nb_bytes, tid, RF_WARPS * 32);
+            if (nb_bytes != (uint32_t)RF_COLS * 12u) rf_stage_tail(cols_raw, csrc, ncols_n, RF_COLS, RF_PAD_COL, nb_bytes, tid, RF_WARPS * 32);
         }
         if (warp_active) {
             // lane L meets column group (31 - L + t) mod 32 at rotation t: ascending with one wrap (at t = L+1);

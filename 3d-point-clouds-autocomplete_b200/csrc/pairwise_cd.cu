@@ -71,7 +71,7 @@ __device__ __forceinline__ void ring_round(const float (&qx)[RING_RQ], const flo
 
 __global__ void __launch_bounds__(PCD_WARPS * 32, 2)
     pairwise_cd_kernel(int nb, int n, int m, const float *__restrict__ first, const float *__restrict__ second,
-                       int row_begin, float *__restrict__ cd) {
+                       int row_begin, const int *__restrict__ pair_r, const int *__restrict__ pair_s, float *__restrict__ cd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *stage = reinterpret_cast<float *>(smem_raw);                        // [PCD_CHUNK*3] cloud-s chunk, AoS
     unsigned int *colmin = reinterpret_cast<unsigned int *>(stage + PCD_CHUNK * 3);  // [m] float bits
@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(PCD_WARPS * 32, 2)
     __shared__ float part[2][PCD_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r = row_begin + (int)(blockIdx.x / nb), s = (int)(blockIdx.x % nb);
+    // cloud pair of this CTA: entry blockIdx.x of an explicit pair list, or (row, column) of a row block of the full matrix
+    const int r = pair_r ? __ldg(pair_r + blockIdx.x) : row_begin + (int)(blockIdx.x / nb);
+    const int s = pair_s ? __ldg(pair_s + blockIdx.x) : (int)(blockIdx.x % nb);
     const float *__restrict__ A = first + (size_t)r * n * 3;
     const float *__restrict__ Bp = second + (size_t)s * m * 3;
 
@@ -169,6 +171,9 @@ __global__ void __launch_bounds__(PCD_WARPS * 32, 2)
 
 using namespace hp;
 
+// one cache for both entry points: the attribute belongs to the kernel, not to the caller
+static SmemAttrCache g_pcd_smem_attr;
+
 extern "C" int hp_pairwise_cd(int na, int nb, int n, int m, const float *first, const float *second, int row_begin,
                               int row_end, float *cd, void *stream) {
     HP_REQUIRE(na >= 0 && nb >= 0 && n >= 0 && m >= 0, "hp_pairwise_cd: negative size");
@@ -184,9 +189,27 @@ extern "C" int hp_pairwise_cd(int na, int nb, int n, int m, const float *first, 
         set_error("hp_pairwise_cd: m=%d column points need %zu bytes of shared memory (limit 200 KB)", m, smem);
         return HP_ERR_UNSUPPORTED;
     }
-    static SmemAttrCache attr;
-    HP_CUDA(ensure_dynamic_smem(pairwise_cd_kernel, smem, attr));
-    pairwise_cd_kernel<<<(unsigned)pairs, PCD_WARPS * 32, smem, (cudaStream_t)stream>>>(nb, n, m, first, second, row_begin, cd);
+    HP_CUDA(ensure_dynamic_smem(pairwise_cd_kernel, smem, g_pcd_smem_attr));
+    pairwise_cd_kernel<<<(unsigned)pairs, PCD_WARPS * 32, smem, (cudaStream_t)stream>>>(nb, n, m, first, second, row_begin, nullptr,
+                                                                                       nullptr, cd);
     HP_LAUNCH_CHECK("pairwise_cd_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_pairwise_cd_pairs(long long npairs, int n, int m, const float *first, const float *second, const int *pair_r,
+                                    const int *pair_s, float *cd, void *stream) {
+    HP_REQUIRE(npairs >= 0 && n >= 0 && m >= 0, "hp_pairwise_cd_pairs: negative size");
+    if (npairs == 0) return HP_OK;
+    HP_REQUIRE(n > 0 && m > 0, "hp_pairwise_cd_pairs: empty clouds (n=%d m=%d)", n, m);
+    HP_REQUIRE(first && second && pair_r && pair_s && cd, "hp_pairwise_cd_pairs: null pointer");
+    HP_REQUIRE(npairs <= 0x7fffffffLL, "hp_pairwise_cd_pairs: %lld cloud pairs in one call; split the list", npairs);
+    const size_t smem = (size_t)PCD_CHUNK * 3 * sizeof(float) + (size_t)m * sizeof(unsigned int);
+    if (smem > 200 * 1024) {
+        set_error("hp_pairwise_cd_pairs: m=%d column points need %zu bytes of shared memory (limit 200 KB)", m, smem);
+        return HP_ERR_UNSUPPORTED;
+    }
+    HP_CUDA(ensure_dynamic_smem(pairwise_cd_kernel, smem, g_pcd_smem_attr));
+    pairwise_cd_kernel<<<(unsigned)npairs, PCD_WARPS * 32, smem, (cudaStream_t)stream>>>(1, n, m, first, second, 0, pair_r, pair_s, cd);
+    HP_LAUNCH_CHECK("pairwise_cd_kernel (pair list)");
     return HP_OK;
 }

@@ -96,6 +96,42 @@ def col_min_merged(block: torch.Tensor, row_begin: int, n_rows: int, group=None)
     return best.values, I.gather(0, first_rank.unsqueeze(0)).squeeze(0)
 
 
+def shard_pairs(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Chunk [p0, p1) of `rank` out of `total` equal-cost work items (cloud pairs): equal ceil-sized chunks."""
+    per = (total + world - 1) // world
+    return min(total, rank * per), min(total, (rank + 1) * per)
+
+
+def upper_triangle_pairs(n: int, p0: int, p1: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(r, s), r < s, of entries p0..p1-1 of the strict upper triangle of an [n, n] matrix in row-major order
+    (row r starts at offset r(2n-r-1)/2), as int32 tensors -- closed form, nothing of size n^2 is built."""
+    p = torch.arange(p0, p1, dtype=torch.int64, device=device)
+    if p.numel() == 0:
+        z = torch.empty((0,), dtype=torch.int32, device=device)
+        return z, z.clone()
+    t = 2 * n - 1
+    r = ((t - torch.sqrt((t * t - 8 * p).to(torch.float64))) / 2).floor().to(torch.int64).clamp_(0, max(n - 2, 0))
+    off = lambda q: q * (2 * n - q - 1) // 2  # noqa: E731  (pairs before row q)
+    r = torch.where(off(r + 1) <= p, r + 1, r)   # float rounding can be off by one either way
+    r = torch.where(off(r) > p, r - 1, r)
+    sidx = p - off(r) + r + 1
+    return r.to(torch.int32), sidx.to(torch.int32)
+
+
+def nearest_other_from_pair_values(n: int, r: torch.Tensor, sidx: torch.Tensor, v: torch.Tensor, group=None) -> torch.Tensor:
+    """Column minima of a SYMMETRIC [n, n] matrix with +inf on the diagonal, from any partition of its strict upper
+    triangle: this rank holds v[p] = M[r[p], s[p]] (r < s).  min_r M[r, c] over r != c is the minimum of the triangle's
+    column c and row c, so one scatter-min by s, one by r and an all_reduce(MIN) give the full vector on every rank
+    (min is exact and order independent: identical for every world size)."""
+    out = torch.full((n,), INF, dtype=v.dtype, device=v.device)
+    if v.numel() > 0:
+        out.scatter_reduce_(0, sidx.to(torch.int64), v, reduce="amin", include_self=True)
+        out.scatter_reduce_(0, r.to(torch.int64), v, reduce="amin", include_self=True)
+    if _rank_world(group)[1] > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.MIN, group=group)
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # the heavy part: row blocks of the cloud-distance matrices (kernels)
 # --------------------------------------------------------------------------------------
@@ -118,6 +154,46 @@ def pairwise_cd(first: torch.Tensor, second: torch.Tensor, row_begin: int = 0, r
                                     out[rb - row_begin:].data_ptr(), stream)
             _native.check(rc, "hp_pairwise_cd")
     return out
+
+
+def pairwise_cd_pairs(first: torch.Tensor, second: torch.Tensor, r_idx: torch.Tensor, s_idx: torch.Tensor) -> torch.Tensor:
+    """cd[p] = CD(first[r_idx[p]], second[s_idx[p]]) for an explicit list of cloud pairs (int32 device tensors)."""
+    check_points(first, "first")
+    check_points(second, "second")
+    check_same_device(first, second)
+    if r_idx.shape != s_idx.shape or r_idx.dim() != 1:
+        raise RuntimeError("pairwise_cd_pairs: r_idx and s_idx must be 1-D tensors of equal length")
+    npairs = r_idx.numel()
+    out = torch.empty((npairs,), dtype=torch.float32, device=first.device)
+    if npairs == 0:
+        return out
+    if int(r_idx.min()) < 0 or int(r_idx.max()) >= first.size(0) or int(s_idx.min()) < 0 or int(s_idx.max()) >= second.size(0):
+        raise RuntimeError("pairwise_cd_pairs: cloud index out of range")
+    r32 = r_idx.to(device=first.device, dtype=torch.int32).contiguous()
+    s32 = s_idx.to(device=first.device, dtype=torch.int32).contiguous()
+    lib = _native.load()
+    step = 1 << 30
+    with on_device_of(first) as stream:
+        for p0 in range(0, npairs, step):
+            cnt = min(step, npairs - p0)
+            rc = lib.hp_pairwise_cd_pairs(cnt, first.size(1), second.size(1), first.data_ptr(), second.data_ptr(),
+                                          r32[p0:].data_ptr(), s32[p0:].data_ptr(), out[p0:].data_ptr(), stream)
+            _native.check(rc, "hp_pairwise_cd_pairs")
+    return out
+
+
+def nearest_other_cd(pcs: torch.Tensor, group=None) -> torch.Tensor:
+    """For every cloud of `pcs` the Chamfer distance to its nearest OTHER cloud of the same set: the column minima of
+    M_xx + inf*I that the 1-NN two-sample test needs (knn, utils/metrics.py:162-170).  CD(a, b) == CD(b, a), so only
+    the strict upper triangle is evaluated (half the work of the full matrix); its pair list, not its rows, is what is
+    split across the ranks (equal pair counts = equal work)."""
+    pcs = pcs.contiguous()
+    n = pcs.size(0)
+    rank, world = _rank_world(group)
+    p0, p1 = shard_pairs(n * (n - 1) // 2, rank, world)
+    r, sidx = upper_triangle_pairs(n, p0, p1, pcs.device)
+    v = pairwise_cd_pairs(pcs, pcs, r, sidx)
+    return nearest_other_from_pair_values(n, r, sidx, v, group)
 
 
 def pairwise_emd(first: torch.Tensor, second: torch.Tensor, row_begin: int = 0, row_end: Optional[int] = None,
@@ -173,12 +249,12 @@ def earth_mover_distance(sample_pcs, ref_pcs, batch_size=None):
 
 
 def _pairwise_EMD_CD_(sample_pcs, ref_pcs, batch_size=None, chamfer_loss=None, rows: Optional[Tuple[int, int]] = None,
-                      with_emd: bool = True):
+                      with_emd: bool = True, with_cd: bool = True):
     """All-pairs matrices [N_first(rows), N_second]; `batch_size` and `chamfer_loss` are accepted for
     signature compatibility (utils/metrics.py:121) and ignored: nothing is materialised per chunk."""
     first, second = sample_pcs.contiguous(), ref_pcs.contiguous()
     rb, re_ = rows if rows is not None else (0, first.size(0))
-    all_cd = pairwise_cd(first, second, rb, re_)
+    all_cd = pairwise_cd(first, second, rb, re_) if with_cd else None
     all_emd = pairwise_emd(first, second, rb, re_) if with_emd else None
     return all_cd, all_emd
 
@@ -255,11 +331,17 @@ def knn_from_blocks(Mxx_blk, Mxy_blk, Myy_blk, x_begin: int, y_begin: int, n0: i
     xy_row_v, _ = row_min_gathered(Mxy_blk, n0, group)          # nearest y for every x
     xy_col_v, _ = col_min_merged(Mxy_blk, x_begin, n0, group)  # nearest x for every y
     yy_v, _ = col_min_merged(Myy_blk, y_begin, n1, group)      # nearest other y for every y
+    return knn1_from_nearest(xx_v, xy_row_v, xy_col_v, yy_v)
+
+
+def knn1_from_nearest(xx_v: torch.Tensor, xy_row_v: torch.Tensor, xy_col_v: torch.Tensor, yy_v: torch.Tensor):
+    """1-NN two-sample statistics from the four nearest-neighbour distance vectors: for every x its nearest other x
+    (xx_v) and nearest y (xy_row_v), for every y its nearest x (xy_col_v) and nearest other y (yy_v)."""
     # stacked row order is x first, then y: on ties the lower stacked index (an x) wins
-    pred_x = (xx_v <= xy_row_v).to(Mxy_blk.dtype)   # 1 = nearest neighbour is an x (label 1)
-    pred_y = (xy_col_v <= yy_v).to(Mxy_blk.dtype)
+    pred_x = (xx_v <= xy_row_v).to(xy_row_v.dtype)   # 1 = nearest neighbour is an x (label 1)
+    pred_y = (xy_col_v <= yy_v).to(xy_row_v.dtype)
     pred = torch.cat((pred_x, pred_y))
-    label = torch.cat((torch.ones(n0), torch.zeros(n1))).to(Mxy_blk)
+    label = torch.cat((torch.ones(xx_v.numel()), torch.zeros(yy_v.numel()))).to(xy_row_v)
     return _two_sample_stats(pred, label)
 
 
@@ -280,11 +362,16 @@ def compute_all_metrics(sample_pcs, ref_pcs, batch_size=None, chamfer_loss=None,
         results.update({"%s-EMD" % k: v for k, v in mmd_cov_from_block(M_rs_emd, rb, n_ref, group).items()})
     if one_nn:
         sb, se = shard_rows(n_smp, rank, world)
-        M_rr_cd, M_rr_emd = _pairwise_EMD_CD_(ref_pcs, ref_pcs, batch_size, chamfer_loss, rows=(rb, re_), with_emd=with_emd)
-        M_ss_cd, M_ss_emd = _pairwise_EMD_CD_(sample_pcs, sample_pcs, batch_size, chamfer_loss, rows=(sb, se), with_emd=with_emd)
-        one = knn_from_blocks(M_rr_cd, M_rs_cd, M_ss_cd, rb, sb, n_ref, n_smp, 1, False, group)
+        # CD is symmetric: M_rr and M_ss enter only through "nearest other cloud of the same set", which comes from the strict
+        # upper triangle (half the pairs), sharded by pair count
+        xx_v, yy_v = nearest_other_cd(ref_pcs, group), nearest_other_cd(sample_pcs, group)
+        xy_row_v, _ = row_min_gathered(M_rs_cd, n_ref, group)
+        xy_col_v, _ = col_min_merged(M_rs_cd, rb, n_ref, group)
+        one = knn1_from_nearest(xx_v, xy_row_v, xy_col_v, yy_v)
         results.update({"1-NN-CD-%s" % k: v for k, v in one.items() if "acc" in k})
-        if with_emd:
+        if with_emd:  # the auction is not symmetric in its arguments: full matrices, like the reference
+            _, M_rr_emd = _pairwise_EMD_CD_(ref_pcs, ref_pcs, batch_size, chamfer_loss, rows=(rb, re_), with_emd=True, with_cd=False)
+            _, M_ss_emd = _pairwise_EMD_CD_(sample_pcs, sample_pcs, batch_size, chamfer_loss, rows=(sb, se), with_emd=True, with_cd=False)
             one = knn_from_blocks(M_rr_emd, M_rs_emd, M_ss_emd, rb, sb, n_ref, n_smp, 1, False, group)
             results.update({"1-NN-EMD-%s" % k: v for k, v in one.items() if "acc" in k})
     return results

@@ -219,6 +219,13 @@ HP_API int hp_target_network_backward(int b, int n, int n_layers, const int *dim
 HP_API int hp_pairwise_cd(int na, int nb, int n, int m, const float *first, const float *second,
                    int row_begin, int row_end, float *cd, void *stream);
 
+/* The same cloud distance for an explicit list of cloud pairs: cd[p] = CD(first[pair_r[p]], second[pair_s[p]]),
+ * pair_r / pair_s device int32 [npairs] (indices are not range-checked).  Used for the SYMMETRIC matrices of the
+ * 1-NN two-sample test (knn, utils/metrics.py:162-191: M_xx and M_yy compare a set with itself), where only the
+ * strict upper triangle is evaluated and the pair list is what gets sharded across GPUs. */
+HP_API int hp_pairwise_cd_pairs(long long npairs, int n, int m, const float *first, const float *second,
+                         const int *pair_r, const int *pair_s, float *cd, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * Measurement helpers (used by bench.py for the roofline denominators; not on the path)
  * ---------------------------------------------------------------------------------- */

@@ -41,6 +41,30 @@ def test_pairwise_cd_row_blocks_are_bit_identical(hp):
     torch.testing.assert_close(full, swapped.t(), rtol=1e-6, atol=0)
 
 
+def test_pairwise_cd_pair_list_and_symmetric_nearest_other(hp):
+    """hp_pairwise_cd_pairs gives the bits of the matrix kernel for the same cloud pairs; nearest_other_cd (strict upper
+    triangle only) equals the column minima of the full self-distance matrix up to the order of the two means."""
+    a, b = _sets(9, 6, 300, 257, seed=12)
+    ad, bd = a.to(DEV), b.to(DEV)
+    full = hp.pairwise_cd(ad, bd)
+    g = torch.Generator().manual_seed(1)
+    r = torch.randint(0, 9, (40,), generator=g, dtype=torch.int32).to(DEV)
+    s_ = torch.randint(0, 6, (40,), generator=g, dtype=torch.int32).to(DEV)
+    got = hp.metrics.pairwise_cd_pairs(ad, bd, r, s_)
+    assert torch.equal(got, full[r.long(), s_.long()])
+    assert hp.metrics.pairwise_cd_pairs(ad, bd, r[:0], s_[:0]).numel() == 0
+    with pytest.raises(RuntimeError):
+        hp.metrics.pairwise_cd_pairs(ad, bd, r, s_ + 6)
+    self_full = hp.pairwise_cd(ad, ad)
+    want = (self_full + torch.diag(torch.full((9,), float("inf"), device=DEV))).min(0).values
+    near = hp.metrics.nearest_other_cd(ad)
+    torch.testing.assert_close(near, want, rtol=1e-6, atol=0)
+    upper = torch.triu_indices(9, 9, 1).to(DEV)
+    assert torch.equal(hp.metrics.pairwise_cd_pairs(ad, ad, upper[0].int(), upper[1].int()), self_full[upper[0], upper[1]])
+    one = hp.metrics.nearest_other_cd(ad[:1])
+    assert one.shape == (1,) and torch.isinf(one).all()
+
+
 def test_pairwise_cd_vs_reference_expansion_form(hp, oracle):
     """vs the reference's own dist_chamfer arithmetic (expansion form, torch port): 1e-5 relative."""
     a, b = _sets(3, 3, 1024, 1024, seed=5)

@@ -57,6 +57,36 @@ def test_shard_rows_partition(hp):
             assert max(e - b for b, e in blocks) <= (n + world - 1) // world
 
 
+def test_upper_triangle_pairs_and_nearest_other(hp):
+    """Closed-form pair list of the strict upper triangle; nearest-other vector from any chunking of it equals the
+    column minima of the symmetric matrix with an infinite diagonal."""
+    M = hp.metrics
+    for n in (0, 1, 2, 3, 7, 100, 1000):
+        tot = n * (n - 1) // 2
+        r, s_ = M.upper_triangle_pairs(n, 0, tot, "cpu")
+        tr = torch.triu_indices(n, n, 1)
+        assert r.dtype == torch.int32 and torch.equal(r.long(), tr[0]) and torch.equal(s_.long(), tr[1]), n
+        for world in (1, 2, 3, 8):
+            chunks = [M.shard_pairs(tot, k, world) for k in range(world)]
+            assert [i for b, e in chunks for i in range(b, e)] == list(range(tot))
+            assert max(e - b for b, e in chunks) <= (tot + world - 1) // world
+    r, s_ = M.upper_triangle_pairs(200000, 200000 * 199999 // 2 - 2, 200000 * 199999 // 2, "cpu")  # far beyond float32 precision
+    assert r.tolist() == [199997, 199998] and s_.tolist() == [199999, 199999]
+    gen = torch.Generator().manual_seed(3)
+    for n in (2, 9, 40):
+        A = torch.randint(0, 4, (n, n), generator=gen).float()  # small integers: ties
+        A = torch.maximum(A, A.t())
+        want = (A + torch.diag(torch.full((n,), float("inf")))).min(0).values
+        tot = n * (n - 1) // 2
+        parts = []
+        for k in range(3):
+            p0, p1 = M.shard_pairs(tot, k, 3)
+            r, s_ = M.upper_triangle_pairs(n, p0, p1, "cpu")
+            parts.append(M.nearest_other_from_pair_values(n, r, s_, A[r.long(), s_.long()]))
+        assert torch.equal(torch.stack(parts).min(0).values, want)
+    assert M.nearest_other_from_pair_values(1, *M.upper_triangle_pairs(1, 0, 0, "cpu"), torch.empty(0)).tolist() == [float("inf")]
+
+
 def _worker(rank, world, port, path, n_ref, n_smp):
     sys.path.insert(0, REPO)
     import importlib
@@ -74,6 +104,15 @@ def _worker(rank, world, port, path, n_ref, n_smp):
                             rb, sb, n_ref, n_smp, 1, False, None)
     out = {k: float(v) for k, v in res.items()}
     out.update({"knn_" + k: float(v) for k, v in one.items()})
+    # the symmetric formulation used by compute_all_metrics: pair lists of the upper triangles instead of row blocks
+    near = []
+    for key, n in (("S_rr", n_ref), ("S_ss", n_smp)):
+        p0, p1 = M.shard_pairs(n * (n - 1) // 2, rank, world)
+        r, s_ = M.upper_triangle_pairs(n, p0, p1, "cpu")
+        near.append(M.nearest_other_from_pair_values(n, r, s_, d[key][r.long(), s_.long()], None))
+    xy_row, _ = M.row_min_gathered(d["M_rs"][rb:re_].contiguous(), n_ref, None)
+    xy_col, _ = M.col_min_merged(d["M_rs"][rb:re_].contiguous(), rb, n_ref, None)
+    out.update({"sym_" + k: float(v) for k, v in M.knn1_from_nearest(near[0], xy_row, xy_col, near[1]).items()})
     torch.save(out, f"{path}.rank{rank}")
     dist.barrier()
     dist.destroy_process_group()
@@ -86,10 +125,12 @@ def test_world_size_2_gloo_equals_single_process(hp, tmp_path, n_ref, n_smp):
     d = {"M_rs": torch.randint(0, 5, (n_ref, n_smp), generator=gen).float(),
          "M_rr": torch.randint(0, 5, (n_ref, n_ref), generator=gen).float(),
          "M_ss": torch.randint(0, 5, (n_smp, n_smp), generator=gen).float()}
+    d["S_rr"], d["S_ss"] = torch.maximum(d["M_rr"], d["M_rr"].t()), torch.maximum(d["M_ss"], d["M_ss"].t())  # symmetric
     path = str(tmp_path / "mats.pt")
     torch.save(d, path)
     single = {k: float(v) for k, v in hp.metrics.mmd_cov_from_block(d["M_rs"], 0, n_ref, None).items()}
     single.update({"knn_" + k: float(v) for k, v in hp.metrics.knn(d["M_rr"], d["M_rs"], d["M_ss"], 1).items()})
+    single.update({"sym_" + k: float(v) for k, v in hp.metrics.knn(d["S_rr"], d["M_rs"], d["S_ss"], 1).items()})
     mp.spawn(_worker, args=(2, _free_port(), path, n_ref, n_smp), nprocs=2, join=True)
     for rank in range(2):
         got = torch.load(f"{path}.rank{rank}")

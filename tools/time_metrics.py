@@ -26,3 +26,12 @@ ms = e0.elapsed_time(e1)
 pairs = NR * NS * P * P
 print(f"pairwise_cd {NR}x{NS}x{P}^2: {ms:.2f} ms -> {pairs / ms / 1e9:.2f} T unordered pairs/s; "
       f"algorithmic 16 FLOP/unordered pair = {16 * pairs / ms / 1e9:.1f} TFLOP/s = {16 * pairs / (ms * 1e-3) / peak:.3f} of measured FP32 peak {peak / 1e12:.1f}")
+# the CD half of compute_all_metrics with 1-NNA (ref-vs-sample matrix + upper triangles of the two self-distance matrices)
+hp.compute_all_metrics(smp[:64], ref[:64], with_emd=False, one_nn=True)
+torch.cuda.synchronize()
+e0.record()
+res = hp.compute_all_metrics(smp, ref, with_emd=False, one_nn=True)
+vals = {k: float(v) for k, v in res.items()}
+e1.record()
+torch.cuda.synchronize()
+print(f"compute_all_metrics CD + 1-NNA {NS} vs {NR}: {e0.elapsed_time(e1):.1f} ms", {k: round(v, 5) for k, v in vals.items()})
