@@ -16,6 +16,9 @@ for (b, n, m) in [(2, 300, 257), (1, 1100, 130)]:
     loss.backward()
     d1, d2 = hp.nn_distance(a, c)
     (d1.sum() + 2 * d2.sum()).backward()
+    hp.chamfer_step(a.detach(), c.detach(), torch.tensor(0.5, device=dev))  # ring forward + fused tail (cluster of 2, PDL)
+    skew = (c.detach() * 0.02).contiguous()                                  # skewed assignment: radix path of the fused tail
+    hp.chamfer_step(a.detach(), skew, torch.tensor(0.5, device=dev))
     e1, i1, e2, i2 = hp.NNDistance(a.detach(), c.detach())
     hp.NNDistanceGrad(a.detach(), c.detach(), i1, i2, torch.ones_like(e1), torch.ones_like(e2))  # sorting backward
 w = (torch.randn(3, 19011, generator=g) * 0.15).to(dev).requires_grad_(True)
