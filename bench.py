@@ -6,7 +6,7 @@
 Workload (BASELINE.json configs[1], named in `config.workload`): Chamfer nearest-neighbour
 distance forward + backward, B=32, N=M=2048, fp32, synthetic clouds ~ U[-0.5,0.5]^3.
 One "step" = Chamfer forward (both directions + loss) + backward (both gradients), captured once as a CUDA
-graph (ChamferStepGraph) and replayed: ring kernel + unpack + backward kernel.
+graph (ChamferStepGraph) and replayed: ring kernel + one fused tail kernel (loss, inverse maps, both gradients).
 metric = ordered (query, candidate) point pairs evaluated per second = 2*B*N*M / t_step.
 
 One JSON line on stdout (rank 0).  Keys follow the driver contract; in addition
