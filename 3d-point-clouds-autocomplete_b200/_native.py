@@ -56,6 +56,7 @@ SIGNATURES = {
                                           _vp, _sz, _vp]),
     "hp_pairwise_cd": (_int, [_int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "hp_pairwise_cd_pairs": (_int, [_ll, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hp_measure_chamfer_ring_only": (_int, [_int, _int, _vp, _int, _vp, _vp, _sz, _vp]),
     "hp_measure_peak": (_int, [_int, _int, ctypes.POINTER(ctypes.c_double), _vp]),
 }
 

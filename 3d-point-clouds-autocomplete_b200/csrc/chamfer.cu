@@ -447,6 +447,7 @@ int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *
                            int *idx2, float *loss, int *inv1, int *inv2, void *workspace, cudaStream_t stream);
 bool nn_ring_inverse_supported(int n, int m);
 bool nn_ring_step_supported(int n, int m);
+int nn_ring_only_launch(int b, int n, const float *xyz1, int m, const float *xyz2, void *workspace, cudaStream_t stream);
 int nn_ring_step_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_loss, float *dist1, int *idx1,
                         float *dist2, int *idx2, float *loss, float *grad1, float *grad2, void *workspace, cudaStream_t stream);
 int nn_ring_backward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,
@@ -651,6 +652,15 @@ extern "C" int hp_chamfer_backward_inv(int b, int n, const float *xyz1, int m, c
                "hp_chamfer_backward_inv: null pointer");
     return nn_ring_backward_launch(b, n, xyz1, m, xyz2, idx1, idx2, inv1, inv2, grad_loss, nullptr, nullptr, grad_xyz1,
                                    grad_xyz2, (cudaStream_t)stream);
+}
+
+extern "C" int hp_measure_chamfer_ring_only(int b, int n, const float *xyz1, int m, const float *xyz2, void *workspace,
+                                            size_t workspace_bytes, void *stream) {
+    HP_REQUIRE(b > 0 && n > 0 && m > 0 && xyz1 && xyz2, "hp_measure_chamfer_ring_only: bad arguments");
+    HP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 &&
+                   workspace_bytes >= hp_chamfer_workspace_bytes(b, n, m),
+               "hp_measure_chamfer_ring_only: workspace null, misaligned or too small");
+    return nn_ring_only_launch(b, n, xyz1, m, xyz2, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int hp_chamfer_step_supported(int b, int n, int m) {

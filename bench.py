@@ -356,8 +356,16 @@ def run_ours(args):
     peak_mufu = native.measure_peak(2, 8192, stream.cuda_stream)
     fp32_peak = max(peak_ffma, peak_ffma2)
 
+    # the dominant kernel alone (nn_ring_kernel), on a private workspace that is discarded afterwards
+    ring_ws = torch.zeros(native.load().hp_chamfer_workspace_bytes(B, N, M), dtype=torch.uint8, device=dev)
+
+    def ring_only():
+        native.check(native.load().hp_measure_chamfer_ring_only(B, N, step.xyz1.data_ptr(), M, step.xyz2.data_ptr(), ring_ws.data_ptr(),
+                                                                ring_ws.numel(), stream.cuda_stream), "hp_measure_chamfer_ring_only")
+
     with ClockSampler(local_rank) as clocks:
         step_ms = _events_timed(torch, step.replay, args.steps, args.warmup, flush, stream, barrier)
+        ring_ms = _events_timed(torch, ring_only, args.steps, 3, flush, stream, barrier)
         fwd_ms = _events_timed(torch, fwd_graph.replay, args.steps, 3, flush, stream, barrier)
         bwd_ms = _events_timed(torch, bwd_graph.replay, args.steps, 3, flush, stream, barrier)
     e2e_ms = _events_timed(torch, step.run_from_host, max(20, args.steps // 2), 3, flush, stream, barrier)
@@ -411,22 +419,28 @@ def run_ours(args):
             peaks_file = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        ring_avg_s = statistics.mean(ring_ms) * 1e-3
         roofline = {
-            "bound": "fp32", "kernel": "nn_ring_kernel (+ nn_ring_unpack_kernel): Chamfer forward, both directions + loss",
-            "achieved": achieved, "peak": fp32_peak / 1e12,
-            "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12),
+            "bound": "fp32", "kernel": "nn_ring_kernel: all-pairs squared distances + argmin, both directions (the dominant kernel of the step)",
+            "achieved": (PAIRS_PER_STEP * FLOP_PER_PAIR) / ring_avg_s / 1e12, "peak": fp32_peak / 1e12,
+            "unit": "TFLOP/s", "frac": (PAIRS_PER_STEP * FLOP_PER_PAIR) / ring_avg_s / fp32_peak,
             "traffic": NCU_RING_DRAM_BYTES,
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of nn_ring_kernel, ncu --set full capture "
-                              "profiles/r01_ncu_full_nn_ring.txt (inputs are 1.5 MiB; results stay in L2 for the unpack kernel)",
+                              "profiles/r01_ncu_full_nn_ring.txt (inputs are 1.5 MiB; results stay in L2 for the tail kernel)",
             "peak_source": "hp_measure_peak: register-resident FFMA/FFMA2 chains on all SMs, measured live in this run "
                            "(MEASURED_PEAKS.json has no FP32 entry; K=3 keeps the path off the tensor cores); "
                            "nominal 148*128*2*1.965 GHz = 74.4",
             "algorithmic_flop_per_launch": PAIRS_PER_STEP * FLOP_PER_PAIR,
             "executed_flop_per_launch": PAIRS_PER_STEP * FLOP_PER_PAIR // 2,
             "note": "algorithmic = 8 FLOP per ORDERED (query,candidate) pair (SURVEY 8d); the ring kernel evaluates each "
-                    "unordered pair once for both directions, so executed FLOP = half",
-            "kernel_ms": statistics.mean(fwd_ms), "bwd_kernel_ms": statistics.mean(bwd_ms),
+                    "unordered pair once for both directions, so executed FLOP = half.  The kernel is bound by instruction "
+                    "issue (packed fp32x2 ops hold the issue port for two cycles; DESIGN.md 4.1), not by a pipe.",
+            "kernel_ms": statistics.mean(ring_ms),
+            "forward_ms": statistics.mean(fwd_ms), "forward_frac": achieved / (fp32_peak / 1e12),
+            "forward_what": "nn_ring_kernel + nn_ring_unpack_kernel: everything nn_distance returns (distances, indices, loss)",
+            "bwd_kernel_ms": statistics.mean(bwd_ms),
             "fwd+bwd_frac": (PAIRS_PER_STEP * FLOP_PER_PAIR) / step_avg_s / fp32_peak,
+            "fwd+bwd_what": "the whole step (value): nn_ring_kernel + nn_ring_finish_kernel",
             "peak_ffma_tflops": peak_ffma / 1e12, "peak_ffma2_tflops": peak_ffma2 / 1e12, "peak_mufu_tex2": peak_mufu / 1e12,
             "hbm_peak_gbs_measured": peaks_file.get("hbm_gbs"),
         }
@@ -453,7 +467,7 @@ def run_ours(args):
                     "unpipelined_api": "ChamferStepGraph.run_from_host: the same copies and step serialised in one graph"},
             "eager_api": {"ms_per_step": statistics.mean(eager_ms), "value": PAIRS_PER_STEP / (statistics.mean(eager_ms) * 1e-3),
                           "note": "ChamferLoss()(preds, gts); loss.backward() through torch autograd, no graph: CPU launch path bound"},
-            "gpu_launches": step.launches_per_replay * args.steps,
+            "gpu_launches": step.launches_per_replay * args.steps,  # timed `value` region only
             "roofline": roofline,
             "cpu_baseline": cpu,
             "other_paths": other,

@@ -234,6 +234,11 @@ HP_API int hp_pairwise_cd_pairs(long long npairs, int n, int m, const float *fir
  * on every SM and returns the achieved rate in *rate (FLOP/s for kinds 0-1, ex2/s for kind 2),
  * timed with CUDA events on `stream` (synchronises). */
 HP_API int hp_measure_peak(int kind, int iters, double *rate_host, void *stream);
+/* Launches ONLY the dominant kernel of the Chamfer step (nn_ring_kernel: all-pairs distances, both directions, keys into the
+ * workspace) so that bench.py can time it alone with CUDA events.  The keys are left in `workspace` (zero-filled on entry,
+ * hp_chamfer_workspace_bytes): use a private workspace and discard it afterwards. */
+HP_API int hp_measure_chamfer_ring_only(int b, int n, const float *xyz1, int m, const float *xyz2, void *workspace,
+                                 size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }
