@@ -14,8 +14,8 @@ from .emd import (ApproxMatch, MatchCost, MatchCostFunction, MatchCostGrad, appr
                   match_cost)
 
 from . import target_network  # noqa: F401
-from .target_network import (TargetNetwork, generate_points, generate_points_batched, target_network_backward,  # noqa: F401
-                             target_network_forward, target_network_num_weights)
+from .target_network import (TargetNetwork, generate_points, generate_points_batched, reconstruct_batch,  # noqa: F401
+                             target_network_backward, target_network_forward, target_network_num_weights)
 from . import graphs  # noqa: F401
 from .graphs import ChamferHostPipeline, ChamferStepGraph, HotPathStepGraph, TargetNetworkStepGraph  # noqa: F401
 

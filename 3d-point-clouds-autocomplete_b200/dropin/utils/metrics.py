@@ -1,7 +1,7 @@
 """Drop-in for the reference's utils/metrics.py.
 
 The hot-path functions (MMD / COV / 1-NNA over all-pairs CD and EMD matrices) come from the B200 implementation.
-Everything else the reference module defines (JSD, average precision, ...: CPU code outside the hot path, which
+JSD runs its nearest-grid-centre search on the NN kernel.  Everything else the reference module defines (CPU code outside the hot path, which
 callers such as core/experiments.py:19 import from the same module) is taken from the reference's own file when it
 is found further down sys.path, so `from utils.metrics import compute_all_metrics, jsd_between_point_cloud_sets`
 keeps working.  That file's `from utils.pytorch_structural_losses... import match_cost / nn_distance` resolve to the
@@ -46,3 +46,8 @@ _pairwise_EMD_CD_ = _m._pairwise_EMD_CD_
 knn = _m.knn
 mmd_cov = _m.mmd_cov
 compute_all_metrics = _m.compute_all_metrics
+# JSD (utils/metrics.py:243-359): nearest grid centre of every point through the NN kernel instead of a CPU KD-tree
+unit_cube_grid_point_cloud = _m.unit_cube_grid_point_cloud
+entropy_of_occupancy_grid = _m.entropy_of_occupancy_grid
+jensen_shannon_divergence = _m.jensen_shannon_divergence
+jsd_between_point_cloud_sets = _m.jsd_between_point_cloud_sets

@@ -22,12 +22,13 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import _native
 from ._glue import check_points, check_same_device, on_device_of
-from .chamfer import ChamferLoss
+from .chamfer import ChamferLoss, NNDistance
 from .emd import emd_cost_pairs, match_cost
 
 INF = float("inf")
@@ -375,3 +376,75 @@ def compute_all_metrics(sample_pcs, ref_pcs, batch_size=None, chamfer_loss=None,
             one = knn_from_blocks(M_rr_emd, M_rs_emd, M_ss_emd, rb, sb, n_ref, n_smp, 1, False, group)
             results.update({"1-NN-EMD-%s" % k: v for k, v in one.items() if "acc" in k})
     return results
+
+
+# --------------------------------------------------------------------------------------
+# JSD between two sets of clouds (utils/metrics.py:243-359): occupancy-grid histograms through the NN kernel
+# --------------------------------------------------------------------------------------
+def unit_cube_grid_point_cloud(resolution: int, clip_sphere: bool = False):
+    """utils/metrics.py:243-262: centres of the resolution^3 cells of the unit cube (float32 of the float64 expression
+    ``i * spacing - 0.5``, like the reference's element-wise fill), optionally only those within the 0.5-sphere."""
+    spacing = 1.0 / float(resolution - 1)
+    axis = (np.arange(resolution, dtype=np.float64) * spacing - 0.5).astype(np.float32)
+    grid = np.stack(np.meshgrid(axis, axis, axis, indexing="ij"), axis=-1)
+    if clip_sphere:
+        grid = grid.reshape(-1, 3)
+        grid = grid[np.linalg.norm(grid, axis=1) <= 0.5]
+    return grid, spacing
+
+
+def _as_cloud_tensor(pcs, device=None) -> torch.Tensor:
+    t = torch.as_tensor(np.asarray(pcs, dtype=np.float32)) if not torch.is_tensor(pcs) else pcs.to(torch.float32)
+    if device is not None:
+        t = t.to(device)
+    elif not t.is_cuda:
+        t = t.cuda()
+    return t.contiguous()
+
+
+def entropy_of_occupancy_grid(pclouds, grid_resolution: int, in_sphere: bool = False, verbose: bool = False):
+    """utils/metrics.py:279-320 -> (mean Bernoulli entropy of the cell-activation variables, per-cell point counts).
+
+    The reference asks a scikit-learn KD-tree for the nearest grid centre of every point, cloud by cloud; here all
+    S*R points of the set meet all grid centres in ONE launch of the nearest-neighbour ring kernel (the same exact fp32
+    distance and lowest-index tie rule as nn_distance); counts are a bincount of the returned indices."""
+    pc = _as_cloud_tensor(pclouds)
+    s_, r_ = pc.shape[0], pc.shape[1]
+    grid_np, _ = unit_cube_grid_point_cloud(grid_resolution, in_sphere)
+    grid = torch.from_numpy(np.ascontiguousarray(grid_np.reshape(-1, 3))).to(pc.device)
+    ncell = grid.shape[0]
+    _, idx, _, _ = NNDistance(pc.reshape(1, s_ * r_, 3), grid.unsqueeze(0))
+    idx = idx.view(s_, r_).long()
+    counters = torch.bincount(idx.reshape(-1), minlength=ncell).to(torch.float64)
+    hit = torch.zeros((s_, ncell), dtype=torch.float64, device=pc.device)
+    hit.scatter_(1, idx, 1.0)                       # a cell counts once per cloud (np.unique, :306)
+    p = hit.sum(0) / float(s_)
+    p = p[p > 0]
+    q = 1.0 - p
+    ent = -(p * torch.log(p)) - torch.where(q > 0, q * torch.log(torch.where(q > 0, q, torch.ones_like(q))), torch.zeros_like(q))
+    return float(ent.sum()) / ncell, counters.cpu().numpy()
+
+
+def jensen_shannon_divergence(P, Q) -> float:
+    """utils/metrics.py:323-340, base-2 entropies of the normalised histograms (float64)."""
+    P = np.asarray(P, dtype=np.float64)
+    Q = np.asarray(Q, dtype=np.float64)
+    if np.any(P < 0) or np.any(Q < 0):
+        raise ValueError('Negative values.')
+    if len(P) != len(Q):
+        raise ValueError('Non equal size.')
+    P_, Q_ = P / np.sum(P), Q / np.sum(Q)
+
+    def h2(a):
+        a = a[a > 0]
+        return float(-(a * np.log2(a)).sum())
+
+    return h2((P_ + Q_) / 2.0) - (h2(P_) + h2(Q_)) / 2.0
+
+
+def jsd_between_point_cloud_sets(sample_pcs, ref_pcs, resolution: int = 28) -> float:
+    """utils/metrics.py:265-276: JSD between the occupancy-grid histograms of two sets of clouds (grid clipped to the
+    0.5-sphere).  Inputs: [S, R, 3] numpy arrays or tensors."""
+    sample_counts = entropy_of_occupancy_grid(sample_pcs, resolution, True)[1]
+    ref_counts = entropy_of_occupancy_grid(ref_pcs, resolution, True)[1]
+    return jensen_shannon_divergence(sample_counts, ref_counts)

@@ -210,3 +210,22 @@ def generate_points_batched(config, epoch, batch: int, size, normalize_points=No
     for j in range(batch):
         out[j] = generate_points(config, epoch, size, normalize_points)
     return out
+
+
+def reconstruct_batch(target_network_config, point_generator_config, weights: torch.Tensor, n_points: int, epoch: int,
+                      device=None, points: torch.Tensor = None) -> torch.Tensor:
+    """The body of the per-sample loop of ``FullModel.forward`` (model/full_model.py:67-74) for the whole batch:
+
+        for j, w in enumerate(target_networks_weights):
+            reconstruction[j] = TargetNetwork(cfg, w)(generate_points(...).to(device)).T
+
+    becomes: draw the B input clouds on the host in the reference's order (same global CPU RNG consumption,
+    SURVEY Q7), ONE pinned H2D copy, one fused kernel that writes the trainer's [B, 3, N] layout directly.
+    ``weights`` [B, W] is the hypernetwork output (gradients flow back to it); ``points`` overrides the sampling."""
+    device = weights.device if device is None else torch.device(device)
+    b = weights.size(0)
+    if points is None:
+        points = generate_points_batched(point_generator_config, epoch, b, (n_points, 3), pin=weights.is_cuda)
+    points = points.to(device, non_blocking=True)
+    return target_network_forward(weights, points, list(target_network_config['layer_out_channels']),
+                                  bool(target_network_config['use_bias']), True)

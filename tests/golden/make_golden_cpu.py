@@ -117,5 +117,49 @@ tm = (torch.rand(5, 200, 3, generator=g) - 0.5).numpy()
 out["tm_pcs"] = tm
 out["tm_cd"] = np.array([[compute_trimesh_chamfer(tm[j], tm[k]) for k in range(5)] for j in range(5)])
 
+# 7. the reference's FullModel.forward end to end on CPU (model/full_model.py:54-80, HyperPocket mode, the 3D-EPN sample
+#    config): hypernetwork output and reconstruction of a seeded batch, for the batched replacement of the per-sample loop
+import json  # noqa: E402
+
+from model.full_model import FullModel as RefFullModel  # noqa: E402
+
+cfg = json.load(open(os.path.join(REF, "settings", "config_3depn_airplane.json.sample")))
+torch.manual_seed(1856)
+fm = RefFullModel(cfg["full_model"])
+fm.eval()
+fm_B, fm_NE, fm_NM, fm_NG, fm_epoch = 3, 80, 48, 128, 37
+existing = torch.rand(fm_B, fm_NE, 3, generator=g) - 0.5
+missing = torch.rand(fm_B, fm_NM, 3, generator=g) - 0.5
+captured = {}
+
+
+def _after_hypernetwork(mod, inp, o):
+    captured["w"] = o.detach().clone()
+    torch.manual_seed(99)  # re-seed between the hypernetwork and the per-sample loop (the encoders draw from the same global
+    # RNG): the test re-applies this seed before drawing the target-network input clouds
+
+
+hook = fm.hyper_network.register_forward_hook(_after_hypernetwork)
+with torch.no_grad():
+    rec = fm(existing.clone(), missing.clone(), [fm_B, fm_NG, 3], fm_epoch, "cpu")
+hook.remove()
+assert rec.shape == (fm_B, 3, fm_NG) and captured["w"].shape == (fm_B, 19011)
+out.update(fm_weights=captured["w"].numpy(), fm_rec=rec.numpy(), fm_meta=np.array([fm_B, fm_NG, fm_epoch, 99]))
+
+# 8. JSD between two sets of clouds (utils/metrics.py:243-359; scikit-learn KD-tree on the occupancy grid)
+def _ball(n_clouds, n_pts, scale):
+    v = torch.randn(n_clouds, n_pts, 3, generator=g)
+    v = v / v.norm(dim=2, keepdim=True) * torch.rand(n_clouds, n_pts, 1, generator=g) ** (1 / 3) * 0.5
+    return (v * torch.tensor(scale)).numpy().astype(np.float32)
+
+jsd_smp, jsd_ref = _ball(6, 256, [1.0, 0.6, 0.9]), _ball(5, 256, [0.8, 1.0, 0.7])
+out.update(jsd_smp=jsd_smp, jsd_ref=jsd_ref)
+for res in (8, 28):
+    out[f"jsd_r{res}"] = np.float64(ref_metrics.jsd_between_point_cloud_sets(jsd_smp, jsd_ref, res))
+    ent, cnt = ref_metrics.entropy_of_occupancy_grid(jsd_smp, res, True)
+    out[f"jsd_ent_r{res}"], out[f"jsd_cnt_r{res}"] = np.float64(ent), cnt.astype(np.float32)
+grid_c, spacing = ref_metrics.unit_cube_grid_point_cloud(8, True)
+out.update(jsd_grid8=grid_c, jsd_spacing8=np.float64(spacing))
+
 np.savez_compressed(os.path.join(HERE, "cpu_reference.npz"), **out)
 print("wrote", os.path.join(HERE, "cpu_reference.npz"), {k: v.shape for k, v in out.items()})

@@ -111,3 +111,21 @@ def test_dist_chamfer_and_emd_approx(hp):
     a2, b2 = _sets(2, 2, 128, 128, seed=4)
     e = hp.metrics.emd_approx(a2.to(DEV), b2.to(DEV))
     torch.testing.assert_close(e, hp.match_cost(a2.to(DEV), b2.to(DEV)) / 128.0)
+
+
+def test_jsd_vs_reference_golden(hp, golden_cpu):
+    """jsd_between_point_cloud_sets / entropy_of_occupancy_grid (utils/metrics.py:265-320) with the nearest grid centre of every
+    point found by the NN ring kernel, against the reference's scikit-learn KD-tree implementation (golden vectors)."""
+    g = golden_cpu
+    for res in (8, 28):
+        ent, cnt = hp.metrics.entropy_of_occupancy_grid(g["jsd_smp"], res, True)
+        assert np.array_equal(cnt, g[f"jsd_cnt_r{res}"].astype(np.float64)), res
+        assert ent == pytest.approx(float(g[f"jsd_ent_r{res}"]), rel=1e-9)
+        jsd = hp.metrics.jsd_between_point_cloud_sets(g["jsd_smp"], torch.from_numpy(g["jsd_ref"]).to(DEV), res)
+        assert jsd == pytest.approx(float(g[f"jsd_r{res}"]), rel=1e-9)
+    # C5-sized set: 1000 clouds x 2048 points against the 28^3 grid in one launch; identical sets have zero divergence
+    big = (torch.rand(1000, 2048, 3, generator=torch.Generator().manual_seed(0)) - 0.5).to(DEV) * 0.55
+    ent, cnt = hp.metrics.entropy_of_occupancy_grid(big, 28, True)
+    assert cnt.sum() == 1000 * 2048 and 0.0 < ent < 1.0
+    assert abs(hp.metrics.jsd_between_point_cloud_sets(big[:500], big[:500])) < 1e-12
+    assert hp.metrics.jsd_between_point_cloud_sets(big[:500], big[500:] * 0.5) > 0.1

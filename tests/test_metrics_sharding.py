@@ -162,3 +162,24 @@ def test_knn_general_k_matches_reference_golden_semantics():
     s1 = m.knn(Mxx, Mxy, Myy, 1)
     M1 = np.array([(label[np.argmin(M[:, c])]) for c in range(n0 + n1)], float)
     assert float(s1["acc"]) == np.mean(M1 == label).astype(np.float32)
+
+
+def test_jsd_host_pieces_match_reference_golden(hp, golden_cpu):
+    """Grid construction and the JSD formula (utils/metrics.py:243-262,323-340) against values produced by the reference's own
+    functions; the nearest-grid-centre search itself (NN kernel) is checked on the GPU in tests/test_metrics_gpu.py."""
+    g = golden_cpu
+    M = hp.metrics
+    grid, spacing = M.unit_cube_grid_point_cloud(8, True)
+    assert grid.dtype == np.float32 and np.array_equal(grid, g["jsd_grid8"]) and spacing == float(g["jsd_spacing8"])
+    assert M.unit_cube_grid_point_cloud(5, False)[0].shape == (5, 5, 5, 3)
+    for res in (8, 28):
+        cells = M.unit_cube_grid_point_cloud(res, True)[0].astype(np.float64)
+        def counts(pcs):  # brute-force float64 nearest centre
+            pts = pcs.reshape(-1, 3).astype(np.float64)
+            idx = ((pts[:, None, :] - cells[None, :, :]) ** 2).sum(-1).argmin(1)
+            return np.bincount(idx, minlength=len(cells)).astype(np.float64)
+        c_smp, c_ref = counts(g["jsd_smp"]), counts(g["jsd_ref"])
+        assert np.array_equal(c_smp, g[f"jsd_cnt_r{res}"].astype(np.float64))
+        assert M.jensen_shannon_divergence(c_smp, c_ref) == pytest.approx(float(g[f"jsd_r{res}"]), rel=1e-9)
+    with pytest.raises(ValueError):
+        M.jensen_shannon_divergence(np.array([1.0, -1.0]), np.array([1.0, 1.0]))

@@ -146,3 +146,19 @@ def test_trimesh_chamfer_restatement_matches_reference_kdtree(oracle, golden_cpu
     for j in range(5):
         for k in range(5):
             assert oracle.trimesh_chamfer(pcs[j], pcs[k]) == pytest.approx(float(golden_cpu["tm_cd"][j, k]), rel=1e-9, abs=1e-15)
+
+
+def test_oracle_reproduces_reference_full_model_loop(hp, oracle, golden_cpu):
+    """The per-sample loop of the reference's FullModel.forward (model/full_model.py:67-74), run on CPU by the golden script:
+    re-drawing the input clouds in the same order from the same seed and applying the oracle MLP to the recorded hypernetwork
+    output gives the recorded reconstruction (host-side sampling order + weight layout pinned without a GPU)."""
+    import torch
+
+    g = golden_cpu
+    B, N, epoch, seed = (int(v) for v in g["fm_meta"])
+    pcfg = {"target_network_input": {"constant": False, "normalization": {"enable": True, "type": "progressive", "epoch": 100}}}
+    torch.manual_seed(seed)
+    pts = hp.generate_points_batched(pcfg, epoch, B, (N, 3), pin=False)
+    y = oracle.target_network_forward(g["fm_weights"], pts.numpy(), [32, 64, 128, 64], True)
+    err = np.abs(np.transpose(y, (0, 2, 1)) - g["fm_rec"]).max() / np.abs(g["fm_rec"]).max()
+    assert err < 1e-6, err
