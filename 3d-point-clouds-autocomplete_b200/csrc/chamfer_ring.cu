@@ -4,12 +4,14 @@
 // 2*B*N*M distance evaluations.  d(a_i, b_j) is bit-symmetric under the library's one association
 // fma(dz,dz,fma(dx,dx,dy*dy)), so here every UNORDERED pair is evaluated once and feeds both directions:
 //
-//   * a lane keeps 8 points of set 1 ("rows") and 4 points of set 2 ("columns") in registers; 32 times per
-//     round the 8x4 distances are evaluated (FADD2/FMUL2/FFMA2, 96 packed ops), folded into the lane's 8 row
-//     minima and into the 4 column minima that TRAVEL WITH the column points, and the column registers move
-//     one lane up the warp (SHFL).  No shared-memory traffic in the hot loop; the FMA pipe is the bound.
+//   * a lane keeps 8 points of set 1 ("rows") in registers; the 128 columns of a round sit in shared memory as 32 packed
+//     groups of 4.  32 times per round a lane evaluates its 8 rows against one group (FADD2/FMUL2/FFMA2, 96 packed ops),
+//     folds the 8x4 distances into its 8 row minima and into the group's 4 column minima, and the group's STATE (minima +
+//     rotation of last improvement) is handed to the next lane through shared memory (LDS.128 / STS.128 + __syncwarp).
+//     The loop is bound by instruction ISSUE: a packed fp32x2 op holds the issue port for two cycles, everything else for
+//     one -- 2*96 + 88 = 280 slots per rotation (hp_measure_peak kinds 7-12).
 //   * indices: per row / per column only the ROTATION in which the minimum last improved is tracked
-//     (FSETP+SEL per row per rotation, issued in the shadow of the FMA pipe); afterwards the 4 columns
+//     (FSETP+SEL per row per rotation: 24 of the 280 issue slots); afterwards the 4 columns
 //     (8 rows) met in that rotation are re-evaluated with bit-identical arithmetic and the lowest index with
 //     d == min is taken.
 //   * ties: the reference keeps the LOWEST index among equal distances (nndistance.cu:32-64,117-125).  A lane
@@ -18,9 +20,11 @@
 //     integer bits: d >= 0), which makes "strict <" behave like "<=" for the post-wrap (lower-index) groups
 //     only; the bump is removed afterwards if nothing replaced it.  Same for columns, which wrap when they
 //     pass from lane 31 to lane 0.  Result: bit-exact distances and reference-exact indices.
-//   * a CTA (4 warps) owns 1024 rows x R*128 columns of one cloud; per-CTA (distance,index) candidates are
-//     written as 64-bit keys (float bits << 32 | index: integer order == (distance, index) order) and folded
-//     by nn_ring_unpack_kernel, which also reduces the fused loss in a fixed order.
+//   * a CTA (4 warps) owns 1024 rows x R*128 columns of one cloud; per-CTA (distance,index) candidates are merged with
+//     64-bit atomicMax on ~(float bits << 32 | index) keys (integer order == (distance, index) order) in a zero-restored
+//     workspace.  The keys are consumed either by nn_ring_finish_kernel (training step: distances, indices, loss, inverse
+//     index maps in shared memory and BOTH gradients in one kernel, launched programmatically dependent) or by
+//     nn_ring_unpack_kernel (+ nn_grad_gather_kernel later), when the upstream gradient is not known yet.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -86,7 +90,8 @@ __device__ __forceinline__ RFGroup rf_load_group(const float *cols_p, int g) {
     return r;
 }
 
-template <int MINB, int DBG = 0, int PIPE = 0>
+// DBG: timing experiments only (HP_RING_VARIANT 10/11/12): bit 0 = two rotations instead of 32, bit 1 = no rescans
+template <int MINB, int DBG = 0>
 __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const RingNNArgs a) {
     __shared__ __align__(128) float rows_s[RF_ROWS * 3];
     __shared__ __align__(128) float cols_raw[RF_COLS * 3];
@@ -192,67 +197,31 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
             for (int j = 0; j < RF_RQ; ++j) best[j] = __int_as_float(0x7f800000), rot[j] = 0;
             int g = 31 - lane;
             RFGroup cur = rf_load_group(cols_p, g);
-            if (PIPE == 0) {
 #pragma unroll 2
-                for (int t = 0; t < ((DBG & 1) ? 2 : 32); ++t) {
-                    const int gn = (g + 1) & 31;
-                    const RFGroup nxt = rf_load_group(cols_p, gn);  // prefetch the next rotation's columns
-                    float4 mnv = *reinterpret_cast<const float4 *>(wmn + g * RF_RC);
-                    int4 rtv = *reinterpret_cast<const int4 *>(wrot + g * RF_RC);
-                    {   // at t == lane+1 this lane's column groups wrap to index 0: later groups must win ties (+1 ulp)
-                        const int wrapped = (t == lane + 1) ? 1 : 0;
-    #pragma unroll
-                        for (int j = 0; j < RF_RQ; ++j) best[j] = __int_as_float(__float_as_int(best[j]) + wrapped);
-                    }
-                    {   // lane 0 (t >= 1) picks up columns last seen by lane 31: they wrap to the lowest rows (+1 ulp)
-                        const int wrapped = (lane == 0 && t != 0) ? 1 : 0;
-                        mnv.x = __int_as_float(__float_as_int(mnv.x) + wrapped), mnv.y = __int_as_float(__float_as_int(mnv.y) + wrapped);
-                        mnv.z = __int_as_float(__float_as_int(mnv.z) + wrapped), mnv.w = __int_as_float(__float_as_int(mnv.w) + wrapped);
-                    }
-                    float cm[RF_RC] = {mnv.x, mnv.y, mnv.z, mnv.w};  // running column minima, continued from the handed-over state
-    #pragma unroll
-                    for (int j = 0; j < RF_RQ; j += 2) {
-                        float d[2][4];
-    #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const f32x2 px = pack2(qx[j + u], qx[j + u]), py = pack2(qy[j + u], qy[j + u]), pz = pack2(qz[j + u], qz[j + u]);
-                            unpack2(sqdist_exact2(px, py, pz, cur.x01, cur.y01, cur.z01), d[u][0], d[u][1]);
-                            unpack2(sqdist_exact2(px, py, pz, cur.x23, cur.y23, cur.z23), d[u][2], d[u][3]);
-                            const float old = best[j + u];
-                            float nb = min3(old, d[u][0], d[u][1]);
-                            nb = min3(nb, d[u][2], d[u][3]);
-                            best[j + u] = nb;
-                            rot[j + u] = (nb < old) ? t : rot[j + u];
-                        }
-    #pragma unroll
-                        for (int i = 0; i < RF_RC; ++i) cm[i] = min3(cm[i], d[0][i], d[1][i]);
-                    }
-                    rtv.x = (cm[0] < mnv.x) ? t : rtv.x, rtv.y = (cm[1] < mnv.y) ? t : rtv.y;
-                    rtv.z = (cm[2] < mnv.z) ? t : rtv.z, rtv.w = (cm[3] < mnv.w) ? t : rtv.w;
-                    mnv = make_float4(cm[0], cm[1], cm[2], cm[3]);
-                    *reinterpret_cast<float4 *>(wmn + g * RF_RC) = mnv;
-                    *reinterpret_cast<int4 *>(wrot + g * RF_RC) = rtv;
-                    __syncwarp();
-                    cur = nxt;
-                    g = gn;
+            for (int t = 0; t < ((DBG & 1) ? 2 : 32); ++t) {
+                const int gn = (g + 1) & 31;
+                const RFGroup nxt = rf_load_group(cols_p, gn);  // prefetch the next rotation's columns
+                float4 mnv = *reinterpret_cast<const float4 *>(wmn + g * RF_RC);
+                int4 rtv = *reinterpret_cast<const int4 *>(wrot + g * RF_RC);
+                {   // at t == lane+1 this lane's column groups wrap to index 0: later groups must win ties (+1 ulp)
+                    const int wrapped = (t == lane + 1) ? 1 : 0;
+#pragma unroll
+                    for (int j = 0; j < RF_RQ; ++j) best[j] = __int_as_float(__float_as_int(best[j]) + wrapped);
                 }
-    
-            } else {
-                // Software-pipelined form: the packed distance evaluations of row pair p+1 (FMA pipe) are issued next to
-                // the minima / rotation bookkeeping of row pair p (ALU pipe); warp-level barriers between the four stages
-                // of a rotation keep ptxas from sinking all ALU work behind all FMA work (which leaves one pipe idle
-                // per phase).  Arithmetic and comparison order per row / column are unchanged.
-                auto dist_pair = [&](int j, const RFGroup &c, float (&d)[2][4]) {
+                {   // lane 0 (t >= 1) picks up columns last seen by lane 31: they wrap to the lowest rows (+1 ulp)
+                    const int wrapped = (lane == 0 && t != 0) ? 1 : 0;
+                    mnv.x = __int_as_float(__float_as_int(mnv.x) + wrapped), mnv.y = __int_as_float(__float_as_int(mnv.y) + wrapped);
+                    mnv.z = __int_as_float(__float_as_int(mnv.z) + wrapped), mnv.w = __int_as_float(__float_as_int(mnv.w) + wrapped);
+                }
+                float cm[RF_RC] = {mnv.x, mnv.y, mnv.z, mnv.w};  // running column minima, continued from the handed-over state
+#pragma unroll
+                for (int j = 0; j < RF_RQ; j += 2) {
+                    float d[2][4];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const f32x2 px = pack2(qx[j + u], qx[j + u]), py = pack2(qy[j + u], qy[j + u]), pz = pack2(qz[j + u], qz[j + u]);
-                        unpack2(sqdist_exact2(px, py, pz, c.x01, c.y01, c.z01), d[u][0], d[u][1]);
-                        unpack2(sqdist_exact2(px, py, pz, c.x23, c.y23, c.z23), d[u][2], d[u][3]);
-                    }
-                };
-                auto fold_pair = [&](int j, const float (&d)[2][4], int t, float (&cm)[RF_RC]) {
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                        unpack2(sqdist_exact2(px, py, pz, cur.x01, cur.y01, cur.z01), d[u][0], d[u][1]);
+                        unpack2(sqdist_exact2(px, py, pz, cur.x23, cur.y23, cur.z23), d[u][2], d[u][3]);
                         const float old = best[j + u];
                         float nb = min3(old, d[u][0], d[u][1]);
                         nb = min3(nb, d[u][2], d[u][3]);
@@ -261,47 +230,17 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
                     }
 #pragma unroll
                     for (int i = 0; i < RF_RC; ++i) cm[i] = min3(cm[i], d[0][i], d[1][i]);
-                };
-                float dA[2][4], dB[2][4];
-                dist_pair(0, cur, dA);
-#pragma unroll 2
-                for (int t = 0; t < ((DBG & 1) ? 2 : 32); ++t) {
-                    const int gn = (g + 1) & 31;
-                    const RFGroup nxt = rf_load_group(cols_p, gn);
-                    float4 mnv = *reinterpret_cast<const float4 *>(wmn + g * RF_RC);
-                    int4 rtv = *reinterpret_cast<const int4 *>(wrot + g * RF_RC);
-                    {
-                        const int wrapped = (t == lane + 1) ? 1 : 0;
-#pragma unroll
-                        for (int j = 0; j < RF_RQ; ++j) best[j] = __int_as_float(__float_as_int(best[j]) + wrapped);
-                    }
-                    {
-                        const int wrapped = (lane == 0 && t != 0) ? 1 : 0;
-                        mnv.x = __int_as_float(__float_as_int(mnv.x) + wrapped), mnv.y = __int_as_float(__float_as_int(mnv.y) + wrapped);
-                        mnv.z = __int_as_float(__float_as_int(mnv.z) + wrapped), mnv.w = __int_as_float(__float_as_int(mnv.w) + wrapped);
-                    }
-                    float cm[RF_RC] = {mnv.x, mnv.y, mnv.z, mnv.w};
-                    dist_pair(2, cur, dB);
-                    fold_pair(0, dA, t, cm);
-                    if (PIPE == 1) __syncwarp();
-                    dist_pair(4, cur, dA);
-                    fold_pair(2, dB, t, cm);
-                    if (PIPE == 1) __syncwarp();
-                    dist_pair(6, cur, dB);
-                    fold_pair(4, dA, t, cm);
-                    if (PIPE == 1) __syncwarp();
-                    dist_pair(0, nxt, dA);   // first pair of the NEXT rotation (unused after the last one)
-                    fold_pair(6, dB, t, cm);
-                    rtv.x = (cm[0] < mnv.x) ? t : rtv.x, rtv.y = (cm[1] < mnv.y) ? t : rtv.y;
-                    rtv.z = (cm[2] < mnv.z) ? t : rtv.z, rtv.w = (cm[3] < mnv.w) ? t : rtv.w;
-                    mnv = make_float4(cm[0], cm[1], cm[2], cm[3]);
-                    *reinterpret_cast<float4 *>(wmn + g * RF_RC) = mnv;
-                    *reinterpret_cast<int4 *>(wrot + g * RF_RC) = rtv;
-                    __syncwarp();
-                    cur = nxt;
-                    g = gn;
                 }
+                rtv.x = (cm[0] < mnv.x) ? t : rtv.x, rtv.y = (cm[1] < mnv.y) ? t : rtv.y;
+                rtv.z = (cm[2] < mnv.z) ? t : rtv.z, rtv.w = (cm[3] < mnv.w) ? t : rtv.w;
+                mnv = make_float4(cm[0], cm[1], cm[2], cm[3]);
+                *reinterpret_cast<float4 *>(wmn + g * RF_RC) = mnv;
+                *reinterpret_cast<int4 *>(wrot + g * RF_RC) = rtv;
+                __syncwarp();
+                cur = nxt;
+                g = gn;
             }
+
 
             if (DBG & 2) {  // timing experiment only: no re-evaluation, one dummy key per lane
                 float sm = 0.f; int sr = 0;
@@ -1071,9 +1010,6 @@ static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const flo
     if (variant == 1) nn_ring_kernel<5><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     else if (variant == 2) nn_ring_kernel<6><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     else if (variant == 3) nn_ring_kernel<3><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
-    else if (variant == 20) nn_ring_kernel<4, 0, 1><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
-    else if (variant == 21) nn_ring_kernel<4, 0, 2><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
-    else if (variant == 22) nn_ring_kernel<4, 2, 1><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     else if (variant == 10) nn_ring_kernel<4, 1><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     else if (variant == 11) nn_ring_kernel<4, 2><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     else if (variant == 12) nn_ring_kernel<4, 3><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);

@@ -39,7 +39,7 @@ if REPO not in sys.path:
 B, N, M = 32, 2048, 2048
 PAIRS_PER_STEP = 2 * B * N * M  # ordered (query, candidate) evaluations, both directions
 FLOP_PER_PAIR = 8  # 3 sub, 3 mul, 2 add
-NCU_RING_DRAM_BYTES = 2657024  # profiles/r01_ncu_full_nn_ring.txt (per launch)
+NCU_RING_DRAM_BYTES = 2658816  # profiles/r01_ncu_full_nn_ring.txt (dram__bytes_read.sum + dram__bytes_write.sum, per launch)
 METRIC = "chamfer_point_pairs_per_s"
 UNIT = "pairs/s"
 WORKLOAD = f"chamfer_nn_distance_fwd+bwd_B{B}_N{N}_M{M}_fp32"

@@ -425,3 +425,24 @@ def test_fused_step_unaligned_views_and_graph(hp):
     torch.cuda.synchronize()
     assert torch.equal(step.loss, loss0) and torch.equal(step.grad_xyz1, ha) and torch.equal(step.grad_xyz2, hb)
     assert torch.equal(step.idx1, j1) and torch.equal(step.dist2, e2)
+
+
+def test_fused_step_random_shapes_sweep(hp):
+    """Seeded sweep over awkward shapes (around the 128-column round, the 256-row warp block, the 1024-row CTA chunk and the
+    1024-thread tail kernel; unequal and tiny clouds; lattice inputs with massive ties): the fused step must reproduce the
+    three-kernel path bit for bit, and leave the workspace reusable."""
+    rng = np.random.default_rng(77)
+    specials = [1, 2, 3, 5, 31, 32, 33, 127, 128, 129, 255, 256, 257, 1023, 1024, 1025, 1500, 2047, 2048, 2049, 3000, 3999]
+    gl = torch.tensor(-1.25, device=DEV)
+    for it in range(20):
+        b = int(rng.integers(1, 6))
+        n, m = int(rng.choice(specials)), int(rng.choice(specials))
+        kind = ["uniform", "lattice"][it % 2]
+        a, c = _clouds((b, n, 3), (b, m, 3), kind, seed=500 + it)
+        ad, cd = a.to(DEV), c.to(DEV)
+        loss0, e1, j1, e2, j2, inv = hp.chamfer_forward(ad, cd, want_inverse=True)
+        ha, hb = hp.chamfer_backward(ad, cd, j1, j2, gl, inv)
+        loss, d1, i1, d2, i2, ga, gb = hp.chamfer_step(ad, cd, gl)
+        tag = (b, n, m, kind)
+        assert torch.equal(i1, j1) and torch.equal(i2, j2) and torch.equal(d1, e1) and torch.equal(d2, e2), tag
+        assert torch.equal(loss, loss0) and torch.equal(ga, ha) and torch.equal(gb, hb), tag
