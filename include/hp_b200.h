@@ -229,10 +229,11 @@ HP_API int hp_pairwise_cd_pairs(long long npairs, int n, int m, const float *fir
 /* ------------------------------------------------------------------------------------
  * Measurement helpers (used by bench.py for the roofline denominators; not on the path)
  * ---------------------------------------------------------------------------------- */
-/* Runs a register-resident FFMA (kind 0), packed FFMA2 (kind 1) or MUFU.EX2 (kind 2) chain, or the
- * Chamfer inner-loop instruction mix (kinds 3-5, see csrc/api.cu),
- * on every SM and returns the achieved rate in *rate (FLOP/s for kinds 0-1, ex2/s for kind 2),
- * timed with CUDA events on `stream` (synchronises). */
+/* Runs a register-resident FFMA (kind 0), packed FFMA2 (kind 1) or MUFU.EX2 (kind 2) chain, the Chamfer inner-loop
+ * instruction mix (kinds 3-5), legacy mma.sync TF32 (kind 6), or a register-only replica of the ring kernel's rotation
+ * (kinds 7-12: FMA-pipe ops only / + FMNMX3 / + FSETP,SEL bookkeeping / the latter with 3, 2, 1 warps per scheduler; see
+ * csrc/api.cu and DESIGN.md 4.1) on every SM and returns the achieved rate in *rate (FLOP/s for kinds 0-1 and 3-6, ex2/s
+ * for kind 2, packed instructions per lane per second for kinds 7-12), timed with CUDA events on `stream` (synchronises). */
 HP_API int hp_measure_peak(int kind, int iters, double *rate_host, void *stream);
 /* Launches ONLY the dominant kernel of the Chamfer step (nn_ring_kernel: all-pairs distances, both directions, keys into the
  * workspace) so that bench.py can time it alone with CUDA events.  The keys are left in `workspace` (zero-filled on entry,
