@@ -113,6 +113,19 @@ def test_dist_chamfer_and_emd_approx(hp):
     torch.testing.assert_close(e, hp.match_cost(a2.to(DEV), b2.to(DEV)) / 128.0)
 
 
+def test_jsd_vs_oracle_on_seeded_sets(hp, oracle):
+    """Fresh seeded sets (not the golden inputs): the NN-kernel occupancy counts equal the oracle's exhaustive float64 search."""
+    g = torch.Generator().manual_seed(21)
+    smp = ((torch.rand(7, 300, 3, generator=g) - 0.5) * 0.57).numpy()
+    ref = ((torch.rand(4, 500, 3, generator=g) - 0.5) * 0.5).numpy()
+    for res in (5, 16):
+        cnt = hp.metrics.entropy_of_occupancy_grid(smp, res, True)[1]
+        ocnt = oracle.occupancy_counts(smp, res)
+        assert np.abs(cnt - ocnt).sum() <= 2, res   # a point within fp32 rounding of a cell boundary may fall either way
+        got = hp.metrics.jsd_between_point_cloud_sets(smp, ref, res)
+        assert got == pytest.approx(oracle.jsd_between_point_cloud_sets(smp, ref, res), rel=1e-4, abs=1e-7)
+
+
 def test_jsd_vs_reference_golden(hp, golden_cpu):
     """jsd_between_point_cloud_sets / entropy_of_occupancy_grid (utils/metrics.py:265-320) with the nearest grid centre of every
     point found by the NN ring kernel, against the reference's scikit-learn KD-tree implementation (golden vectors)."""

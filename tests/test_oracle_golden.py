@@ -162,3 +162,14 @@ def test_oracle_reproduces_reference_full_model_loop(hp, oracle, golden_cpu):
     y = oracle.target_network_forward(g["fm_weights"], pts.numpy(), [32, 64, 128, 64], True)
     err = np.abs(np.transpose(y, (0, 2, 1)) - g["fm_rec"]).max() / np.abs(g["fm_rec"]).max()
     assert err < 1e-6, err
+
+
+def test_jsd_restatement_matches_reference(oracle, golden_cpu):
+    """Occupancy-grid JSD (utils/metrics.py:243-359) restated with an exhaustive float64 nearest-centre search against the values
+    the reference's scikit-learn implementation produced."""
+    g = golden_cpu
+    assert np.array_equal(oracle.unit_cube_grid(8, True), g["jsd_grid8"])
+    for res in (8, 28):
+        assert np.array_equal(oracle.occupancy_counts(g["jsd_smp"], res), g[f"jsd_cnt_r{res}"].astype(np.float64))
+        got = oracle.jsd_between_point_cloud_sets(g["jsd_smp"], g["jsd_ref"], res)
+        assert abs(got - float(g[f"jsd_r{res}"])) <= 1e-9 * abs(float(g[f"jsd_r{res}"]))
