@@ -7,8 +7,8 @@ shim at the repository root.  ``dropin/`` mirrors the reference's import paths
 ``utils.metrics``) for use on ``sys.path`` ahead of the reference tree.
 """
 from . import _native  # noqa: F401
-from .chamfer import (ChamferLoss, NNDistance, NNDistanceFunction, NNDistanceGrad, chamfer_backward,  # noqa: F401
-                      chamfer_forward, chamfer_step, chamfer_step_supported, nn_distance)
+from .chamfer import (ChamferLoss, NNDistance, NNDistanceFunction, NNDistanceGrad, batch_pairwise_dist,  # noqa: F401
+                      chamfer_backward, chamfer_forward, chamfer_step, chamfer_step_supported, nn_distance)
 
 from .emd import (ApproxMatch, MatchCost, MatchCostFunction, MatchCostGrad, approx_match, emd_cost_pairs,  # noqa: F401
                   match_cost)
@@ -17,7 +17,10 @@ from . import target_network  # noqa: F401
 from .target_network import (TargetNetwork, generate_points, generate_points_batched, reconstruct_batch,  # noqa: F401
                              target_network_backward, target_network_forward, target_network_num_weights)
 from . import graphs  # noqa: F401
-from .graphs import ChamferHostPipeline, ChamferStepGraph, HotPathStepGraph, TargetNetworkStepGraph  # noqa: F401
+from .graphs import (ChamferHostPipeline, ChamferStepGraph, FullModelStepGraph, HotPathStepGraph,  # noqa: F401
+                     TargetNetworkStepGraph)
+from . import hyper_network  # noqa: F401
+from .hyper_network import FusedHyperNetworkHead, fuse_hypernetwork_head  # noqa: F401
 
 from . import metrics  # noqa: F401
 from .metrics import compute_all_metrics, pairwise_cd, pairwise_emd  # noqa: F401

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import contextlib
+import threading
 from typing import Dict, Tuple
 
 import torch
@@ -42,14 +43,56 @@ def on_device_of(t: torch.Tensor):
 
 
 _workspaces: Dict[Tuple[int, int, str], torch.Tensor] = {}
+_owners = threading.local()
+
+
+@contextlib.contextmanager
+def workspace_owner(store: dict):
+    """While active (on this thread), ``zeroed_workspace`` hands out buffers that live in ``store`` instead of the shared
+    per-stream cache.  CUDA-graph captures run under it with a dict the graph object keeps: the raw pointers baked into
+    the graph stay valid for the graph's lifetime, and two graphs never share (and race on) one workspace, whatever stream
+    handle PyTorch recycles for their capture."""
+    stack = getattr(_owners, "stack", None)
+    if stack is None:
+        stack = _owners.stack = []
+    stack.append(store)
+    try:
+        yield store
+    finally:
+        stack.pop()
 
 
 def zeroed_workspace(device: torch.device, stream: int, nbytes: int, tag: str) -> torch.Tensor:
-    """A per-(device, stream, tag) scratch buffer that kernels keep zero-restored between calls."""
+    """A scratch buffer that kernels keep zero-restored between calls: per (device, stream, tag) from a shared cache, or
+    per (device, tag) from the active ``workspace_owner`` store."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
+    stack = getattr(_owners, "stack", None)
+    if stack:
+        store, key = stack[-1], (idx, tag)
+        ws = store.get(key)
+        if ws is None or ws.numel() < nbytes:
+            if ws is not None:
+                store.setdefault("_retired", []).append(ws)  # an earlier capture may still point at it
+            ws = torch.zeros(max(int(nbytes), 4096), dtype=torch.uint8, device=device)
+            store[key] = ws
+        return ws
     key = (idx, int(stream), tag)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(int(nbytes), 4096), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+def check_with_workspace(rc: int, what: str, ws: torch.Tensor) -> None:
+    """_native.check for calls whose kernels leave state in a zero-restored workspace: if the call failed part-way (e.g.
+    the ring kernel ran but the tail launch was refused), stale keys would poison every later call, so the workspace is
+    cleared (stream-ordered) before the error is raised."""
+    if rc != 0:
+        try:
+            ws.zero_()
+        except Exception:
+            pass
+    from . import _native
+
+    _native.check(rc, what)

@@ -33,6 +33,7 @@ SIGNATURES = {
     "hp_nndistance": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_nndistance_ws": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hp_nndistancegrad": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hp_batch_pairwise_dist": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp]),
     "hp_chamfer_workspace_bytes": (_sz, [_int, _int, _int]),
     "hp_chamfer_forward": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hp_chamfer_backward": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -56,9 +57,16 @@ SIGNATURES = {
                                           _vp, _sz, _vp]),
     "hp_pairwise_cd": (_int, [_int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "hp_pairwise_cd_pairs": (_int, [_ll, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+# include/hp_b200_bench.h: measurement helpers of libhp_b200_bench.so (bench.py / tools only; never on the product path)
+BENCH_LIB_PATH = os.path.join(_PKG_DIR, "lib", "libhp_b200_bench.so")
+BENCH_SIGNATURES = {
     "hp_measure_chamfer_ring_only": (_int, [_int, _int, _vp, _int, _vp, _vp, _sz, _vp]),
     "hp_measure_peak": (_int, [_int, _int, ctypes.POINTER(ctypes.c_double), _vp]),
+    "hp_measure_set_trace": (_int, [_vp]),
 }
+_bench_lib = None
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -93,7 +101,32 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed: {kind} (code {rc}): {msg}")
 
 
+def load_bench() -> ctypes.CDLL:
+    """Load libhp_b200_bench.so (the product sources + measurement helpers, built with -DHP_BENCH_BUILD)."""
+    global _bench_lib
+    if _bench_lib is not None:
+        return _bench_lib
+    with _lock:
+        if _bench_lib is None:
+            if not os.path.exists(BENCH_LIB_PATH):
+                raise NativeLibraryMissing(f"{BENCH_LIB_PATH} is missing (build it with __graft_entry__.build())")
+            lib = ctypes.CDLL(BENCH_LIB_PATH)
+            for name, (res, args) in {**SIGNATURES, **BENCH_SIGNATURES}.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _bench_lib = lib
+    return _bench_lib
+
+
+def check_bench(rc: int, what: str) -> None:
+    if rc != HP_OK:
+        lib = load_bench()
+        raise RuntimeError(f"{what} failed: {lib.hp_error_string(rc).decode()} (code {rc}): "
+                           f"{lib.hp_last_error_message().decode(errors='replace')}")
+
+
 def measure_peak(kind: int, iters: int = 4096, stream: int = 0) -> float:
     out = ctypes.c_double(0.0)
-    check(load().hp_measure_peak(kind, iters, ctypes.byref(out), stream), "hp_measure_peak")
+    check_bench(load_bench().hp_measure_peak(kind, iters, ctypes.byref(out), stream), "hp_measure_peak")
     return out.value

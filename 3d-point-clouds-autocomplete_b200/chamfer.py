@@ -15,7 +15,7 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from . import _native
-from ._glue import check_points, check_same_device, on_device_of, zeroed_workspace
+from ._glue import check_points, check_same_device, check_with_workspace, on_device_of, zeroed_workspace
 
 _STRICT_BATCH = os.environ.get("HP_STRICT_BATCH", "0") == "1"
 
@@ -48,7 +48,7 @@ def NNDistance(set_d: torch.Tensor, set_q: torch.Tensor):
         ws = zeroed_workspace(dev, stream, nbytes, "chamfer")
         rc = lib.hp_nndistance_ws(b, n, set_d.data_ptr(), m, set_q.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
                                   dist2.data_ptr(), idx2.data_ptr(), ws.data_ptr(), ws.numel(), stream)
-    _native.check(rc, "hp_nndistance_ws")
+    check_with_workspace(rc, "hp_nndistance_ws", ws)
     return [dist1, idx1, dist2, idx2]
 
 
@@ -101,7 +101,7 @@ class NNDistanceFunction(Function):
                 rc = lib.hp_chamfer_forward_inv(b, n, seta.data_ptr(), m, setb.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
                                                 dist2.data_ptr(), idx2.data_ptr(), None, inv[0].data_ptr(), inv[1].data_ptr(),
                                                 ws.data_ptr(), ws.numel(), stream)
-            _native.check(rc, "hp_chamfer_forward_inv")
+            check_with_workspace(rc, "hp_chamfer_forward_inv", ws)
         else:
             dist1, idx1, dist2, idx2 = NNDistance(seta, setb)
         ctx.save_for_backward(seta, setb)
@@ -163,12 +163,12 @@ def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, want_inverse: bool =
             rc = lib.hp_chamfer_forward_inv(b, n, xyz1.data_ptr(), m, xyz2.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
                                             dist2.data_ptr(), idx2.data_ptr(), loss.data_ptr(), inv[0].data_ptr(),
                                             inv[1].data_ptr(), ws.data_ptr(), ws.numel(), stream)
-            _native.check(rc, "hp_chamfer_forward_inv")
+            check_with_workspace(rc, "hp_chamfer_forward_inv", ws)
         else:
             rc = lib.hp_chamfer_forward(b, n, xyz1.data_ptr(), m, xyz2.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
                                         dist2.data_ptr(), idx2.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws.numel(),
                                         stream)
-            _native.check(rc, "hp_chamfer_forward")
+            check_with_workspace(rc, "hp_chamfer_forward", ws)
     if want_inverse:
         return loss, dist1, idx1, dist2, idx2, inv
     return loss, dist1, idx1, dist2, idx2
@@ -236,11 +236,13 @@ def chamfer_step(xyz1: torch.Tensor, xyz2: torch.Tensor, grad_loss: torch.Tensor
         rc = lib.hp_chamfer_step(b, n, xyz1.data_ptr(), m, xyz2.data_ptr(), g.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
                                  dist2.data_ptr(), idx2.data_ptr(), loss.data_ptr(), grad1.data_ptr(), grad2.data_ptr(),
                                  ws.data_ptr(), ws.numel(), stream)
-        _native.check(rc, "hp_chamfer_step")
+        check_with_workspace(rc, "hp_chamfer_step", ws)
     return loss, dist1, idx1, dist2, idx2, grad1, grad2
 
 
 class _ChamferLossFunction(Function):
+    """Forward kernels now, backward kernels later (three launches in total): used when the fused step is unavailable."""
+
     @staticmethod
     def forward(ctx, xyz1, xyz2):
         loss, _d1, idx1, _d2, idx2, inv = chamfer_forward(xyz1, xyz2, want_inverse=True)
@@ -253,6 +255,35 @@ class _ChamferLossFunction(Function):
         xyz1, xyz2 = ctx.saved_tensors
         g1, g2 = chamfer_backward(xyz1, xyz2, ctx.idx1, ctx.idx2, grad_loss, ctx.inv)
         return g1, g2
+
+
+_ones = {}
+
+
+def _device_one(device: torch.device) -> torch.Tensor:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    t = _ones.get(key)
+    if t is None:
+        t = _ones[key] = torch.ones((), dtype=torch.float32, device=device)
+    return t
+
+
+class _ChamferLossFusedFunction(Function):
+    """The training-step form: when a gradient will be asked for, the forward runs the fused two-kernel step (ring kernel +
+    sectioned tail) for an upstream gradient of one -- loss AND both gradients -- and the backward only scales them by the
+    actual upstream gradient (the trainer's loss_coef and mean, core/epoch_loops.py:25-26).  Two launches instead of three,
+    and nothing but two small multiplies left on the backward path."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        loss, _d1, _i1, _d2, _i2, g1, g2 = chamfer_step(xyz1, xyz2, _device_one(xyz1.device))
+        ctx.save_for_backward(g1, g2)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        g1, g2 = ctx.saved_tensors
+        return g1 * grad_loss, g2 * grad_loss
 
 
 class ChamferLoss(nn.Module):
@@ -276,11 +307,30 @@ class ChamferLoss(nn.Module):
     def forward(self, preds, gts):
         if not (preds.is_cuda and gts.is_cuda):
             raise RuntimeError("ChamferLoss (B200) needs CUDA tensors; there is no CPU fallback")
-        return _ChamferLossFunction.apply(gts.contiguous(), preds.contiguous())
+        xyz1, xyz2 = gts.contiguous(), preds.contiguous()
+        needs_grad = torch.is_grad_enabled() and (xyz1.requires_grad or xyz2.requires_grad)
+        if needs_grad and xyz1.dim() == 3 and xyz2.dim() == 3 and xyz1.size(0) == xyz2.size(0) and xyz1.size(0) > 0 \
+                and chamfer_step_supported(xyz1.size(0), xyz1.size(1), xyz2.size(1)):
+            return _ChamferLossFusedFunction.apply(xyz1, xyz2)
+        return _ChamferLossFunction.apply(xyz1, xyz2)
 
     def batch_pairwise_dist(self, x, y):
-        """P[b,i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  (champfer_loss.py:19-35), [B,Nx,Ny]."""
-        sq_x = (x * x).sum(dim=2)
-        sq_y = (y * y).sum(dim=2)
-        cross = torch.bmm(x, y.transpose(2, 1))
-        return sq_x.unsqueeze(2) + sq_y.unsqueeze(1) - 2 * cross
+        """P[b,i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  (champfer_loss.py:19-35), [B,Nx,Ny], one kernel (no bmm, no Gram
+        matrices).  Forward only, like every use in the reference (utils/metrics.py:82 under no_grad)."""
+        return batch_pairwise_dist(x, y)
+
+
+def batch_pairwise_dist(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """The reference's expansion-form distance matrix (losses/champfer_loss.py:19-35) through hp_batch_pairwise_dist."""
+    x, y = x.detach().contiguous(), y.detach().contiguous()
+    check_points(x, "x")
+    check_points(y, "y")
+    check_same_device(x, y)
+    if x.size(0) != y.size(0):
+        raise RuntimeError(f"batch_pairwise_dist: batch mismatch ({x.size(0)} vs {y.size(0)})")
+    b, nx, ny = x.size(0), x.size(1), y.size(1)
+    P = torch.empty((b, nx, ny), dtype=torch.float32, device=x.device)
+    with on_device_of(x) as stream:
+        rc = _native.load().hp_batch_pairwise_dist(b, nx, ny, x.data_ptr(), y.data_ptr(), P.data_ptr(), stream)
+    _native.check(rc, "hp_batch_pairwise_dist")
+    return P

@@ -1,4 +1,5 @@
-// api.cu -- error plumbing, device queries and the roofline-denominator microbenchmarks.
+// api.cu -- error plumbing and device queries; in the bench library (HP_BENCH_BUILD) also the roofline-denominator
+// microbenchmarks (hp_measure_peak).  The product library contains no measurement code.
 #include <stdarg.h>
 #include <string.h>
 
@@ -33,6 +34,7 @@ int sm_count() {
     return cached[dev];
 }
 
+#ifdef HP_BENCH_BUILD
 // ---- microbenchmarks: what the FP32 / MUFU pipes of this very GPU deliver right now --------
 // kind 0: scalar FFMA, 16 independent chains/thread            -> 2 FLOP per FFMA
 // kind 1: packed FFMA2 (fma.rn.f32x2), 8 independent chains    -> 4 FLOP per FFMA2
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(128, 4) ring_pattern_kernel(int iters, float s
     for (int i = 0; i < 4; ++i) s += cm[i] + (float)crot[i];
     if (s == 123.456f) sink[0] = s;
 }
+#endif  // HP_BENCH_BUILD
 
 }  // namespace hp
 
@@ -245,7 +248,8 @@ extern "C" const char *hp_error_string(int code) {
 
 extern "C" const char *hp_last_error_message(void) { return g_err; }
 
-extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *stream_v) {
+#ifdef HP_BENCH_BUILD
+extern "C" HP_API int hp_measure_peak(int kind, int iters, double *rate_host, void *stream_v) {
     HP_REQUIRE(rate_host != nullptr, "hp_measure_peak: null result pointer");
     HP_REQUIRE(kind >= 0 && kind <= 12 && iters > 0, "hp_measure_peak: bad kind/iters (%d, %d)", kind, iters);
     cudaStream_t stream = (cudaStream_t)stream_v;
@@ -296,3 +300,4 @@ extern "C" int hp_measure_peak(int kind, int iters, double *rate_host, void *str
     *rate_host = threads_total * per_thread_iter * (double)iters / ((double)best_ms * 1e-3);
     return HP_OK;
 }
+#endif  // HP_BENCH_BUILD

@@ -447,31 +447,39 @@ int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *
                            int *idx2, float *loss, int *inv1, int *inv2, void *workspace, cudaStream_t stream);
 bool nn_ring_inverse_supported(int n, int m);
 bool nn_ring_step_supported(int n, int m);
+#ifdef HP_BENCH_BUILD
+int nn_ring_set_trace(void *dev_ptr);
 int nn_ring_only_launch(int b, int n, const float *xyz1, int m, const float *xyz2, void *workspace, cudaStream_t stream);
+#endif
 int nn_ring_step_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_loss, float *dist1, int *idx1,
                         float *dist2, int *idx2, float *loss, float *grad1, float *grad2, void *workspace, cudaStream_t stream);
 int nn_ring_backward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,
                             const int *inv1, const int *inv2, const float *grad_loss, const float *grad_dist1,
                             const float *grad_dist2, float *grad1, float *grad2, cudaStream_t stream);
 
-// HP_NN_RING=0 selects the first-generation ordered-pair kernel (kept for A/B measurements and as the
-// workspace-free path of hp_nndistance).
+// The first-generation ordered-pair kernel stays as the fallback of hp_nndistance when no stream-ordered workspace can be had;
+// the bench library (HP_BENCH_BUILD) can select it with HP_NN_RING=0 for A/B measurements.
 static bool use_ring() {
+#ifdef HP_BENCH_BUILD
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("HP_NN_RING");
         v = (e && atoi(e) == 0) ? 0 : 1;
     }
     return v == 1;
+#else
+    return true;
+#endif
 }
 
 // ---- host side ---------------------------------------------------------------------------
 constexpr int FWD_MIN_QT = 32;  // smallest query tile of any variant (sizes the loss workspace)
 constexpr int GRAD_THREADS = 1024;
 
-// Forward tile variants (threads per CTA, queries per thread).  HP_NN_VARIANT selects one at run time for
-// tuning; the default is the best measured on B200 at B=32, N=M=2048.
+// Forward tile variants (threads per CTA, queries per thread) of the ordered-pair kernel; the bench library can select one
+// with HP_NN_VARIANT, the product build uses the best measured on B200 at B=32, N=M=2048.
 static int fwd_variant() {
+#ifdef HP_BENCH_BUILD
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("HP_NN_VARIANT");
@@ -479,6 +487,9 @@ static int fwd_variant() {
         if (v < 0 || v > 8) v = 0;
     }
     return v;
+#else
+    return 0;
+#endif
 }
 
 template <int THREADS, int RQ, int MC>
@@ -509,6 +520,7 @@ static int nn_forward_launch(int b, int n, const float *xyz1, int m, const float
     a.counter = reinterpret_cast<unsigned int *>(workspace);
     a.partial = workspace ? reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(workspace) + 8) : nullptr;
     switch (fwd_variant()) {
+#ifdef HP_BENCH_BUILD
         case 1: return nn_forward_launch_t<128, 2, 2048>(a, stream);
         case 2: return nn_forward_launch_t<64, 2, 1024>(a, stream);
         case 3: return nn_forward_launch_t<256, 1, 2048>(a, stream);
@@ -517,6 +529,7 @@ static int nn_forward_launch(int b, int n, const float *xyz1, int m, const float
         case 6: return nn_forward_launch_t<128, 4, 2048>(a, stream);
         case 7: return nn_forward_launch_t<32, 4, 512>(a, stream);
         case 8: return nn_forward_launch_t<32, 8, 512>(a, stream);
+#endif
         default: return nn_forward_launch_t<128, 1, 2048>(a, stream);
     }
 }
@@ -524,7 +537,21 @@ static int nn_forward_launch(int b, int n, const float *xyz1, int m, const float
 static int nn_backward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const float *g1, const int *idx1,
                               const float *g2, const int *idx2, float *grad1, float *grad2, int scalar_grad,
                               cudaStream_t stream) {
+    // shared memory (ints) of one (cloud, side) CTA: keys[no] perm[no] start[np+1] cnt[nseg][np] -- sized for the worse of the
+    // two sides, with as many placement segments (<= one per warp) as fit; clouds that do not fit even one segment
+    // (n + m above HP_NNGRAD_SMEM_POINTS, or very unbalanced pairs such as 16384 x 2048) take the atomicAdd kernel below.
+    const size_t budget = (size_t)200 * 1024 / sizeof(int);
+    auto side_ints = [](size_t np, size_t no, size_t nseg) { return 2 * no + np + 1 + nseg * np; };
+    int nseg = 0;
     if ((long long)n + m <= HP_NNGRAD_SMEM_POINTS) {
+        for (int s = GRAD_THREADS / 32; s >= 1; --s) {
+            if (side_ints(n, m, s) <= budget && side_ints(m, n, s) <= budget) {
+                nseg = s;
+                break;
+            }
+        }
+    }
+    if (nseg >= 1) {
         NNGradArgs a;
         a.set[0] = xyz1, a.set[1] = xyz2;
         a.idx[0] = idx1, a.idx[1] = idx2;
@@ -533,13 +560,8 @@ static int nn_backward_launch(int b, int n, const float *xyz1, int m, const floa
         a.npts[0] = n, a.npts[1] = m;
         a.b = b;
         a.scalar_grad = scalar_grad;
-        // shared memory (ints): keys[no] perm[no] start[np+1] cnt[nseg][np]; nseg placement warps as it fits
-        const size_t big = (size_t)(n > m ? n : m);
-        const size_t fixed = (size_t)2 * big + big + 1;
-        const size_t budget = (size_t)200 * 1024 / sizeof(int);
-        int nseg = (int)((budget - fixed) / big);
-        nseg = nseg > GRAD_THREADS / 32 ? GRAD_THREADS / 32 : (nseg < 1 ? 1 : nseg);
-        const size_t smem = (fixed + (size_t)nseg * big) * sizeof(int);
+        const size_t ints = side_ints(n, m, nseg) > side_ints(m, n, nseg) ? side_ints(n, m, nseg) : side_ints(m, n, nseg);
+        const size_t smem = ints * sizeof(int);
         auto kern = nn_grad_kernel<GRAD_THREADS>;
         static SmemAttrCache grad_attr;
         if (smem > 48 * 1024) HP_CUDA(ensure_dynamic_smem(kern, smem, grad_attr));
@@ -567,8 +589,23 @@ extern "C" int hp_nndistance(int b, int n, const float *xyz, int m, const float 
     if (b == 0 || (n == 0 && m == 0)) return HP_OK;
     HP_REQUIRE(n > 0 && m > 0, "hp_nndistance: one point set is empty (n=%d m=%d): nearest neighbour undefined", n, m);
     HP_REQUIRE(xyz && xyz2 && result && result_i && result2 && result2_i, "hp_nndistance: null pointer");
-    return nn_forward_launch(b, n, xyz, m, xyz2, result, result_i, result2, result2_i, nullptr, nullptr,
-                             (cudaStream_t)stream);
+    // The reference signature carries no workspace: take one from the stream-ordered pool (cudaMallocAsync / cudaFreeAsync:
+    // no synchronisation, legal under stream capture) and run the ring kernels like hp_nndistance_ws.  If the pool refuses,
+    // the workspace-free ordered-pair kernel computes the same bits at about half the speed.
+    cudaStream_t st = (cudaStream_t)stream;
+    if (use_ring()) {
+        const size_t bytes = nn_ring_workspace_bytes(b, n, m);
+        void *ws = nullptr;
+        if (cudaMallocAsync(&ws, bytes, st) == cudaSuccess && ws != nullptr) {
+            int rc = check_cuda(cudaMemsetAsync(ws, 0, bytes, st), "hp_nndistance: cudaMemsetAsync");
+            if (rc == HP_OK)
+                rc = nn_ring_forward_launch(b, n, xyz, m, xyz2, result, result_i, result2, result2_i, nullptr, nullptr, nullptr, ws, st);
+            const int rf = check_cuda(cudaFreeAsync(ws, st), "hp_nndistance: cudaFreeAsync");
+            return rc != HP_OK ? rc : rf;
+        }
+        (void)cudaGetLastError();  // pool unavailable: not an error of this call
+    }
+    return nn_forward_launch(b, n, xyz, m, xyz2, result, result_i, result2, result2_i, nullptr, nullptr, st);
 }
 
 extern "C" size_t hp_chamfer_workspace_bytes(int b, int n, int m) {
@@ -654,14 +691,17 @@ extern "C" int hp_chamfer_backward_inv(int b, int n, const float *xyz1, int m, c
                                    grad_xyz2, (cudaStream_t)stream);
 }
 
-extern "C" int hp_measure_chamfer_ring_only(int b, int n, const float *xyz1, int m, const float *xyz2, void *workspace,
-                                            size_t workspace_bytes, void *stream) {
+#ifdef HP_BENCH_BUILD
+extern "C" HP_API int hp_measure_chamfer_ring_only(int b, int n, const float *xyz1, int m, const float *xyz2, void *workspace,
+                                                   size_t workspace_bytes, void *stream) {
     HP_REQUIRE(b > 0 && n > 0 && m > 0 && xyz1 && xyz2, "hp_measure_chamfer_ring_only: bad arguments");
     HP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 &&
                    workspace_bytes >= hp_chamfer_workspace_bytes(b, n, m),
                "hp_measure_chamfer_ring_only: workspace null, misaligned or too small");
     return nn_ring_only_launch(b, n, xyz1, m, xyz2, workspace, (cudaStream_t)stream);
 }
+extern "C" HP_API int hp_measure_set_trace(void *device_u64_buffer) { return nn_ring_set_trace(device_u64_buffer); }
+#endif
 
 extern "C" int hp_chamfer_step_supported(int b, int n, int m) {
     return (b > 0 && use_ring() && nn_ring_step_supported(n, m)) ? 1 : 0;

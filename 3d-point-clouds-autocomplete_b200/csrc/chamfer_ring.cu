@@ -43,6 +43,21 @@ constexpr int RF_MAX_PER_THREAD = 32;           // 32768 / RF_MERGE_THREADS: lar
 
 typedef unsigned long long u64;
 
+#ifdef HP_BENCH_BUILD
+// bench library only: per-CTA timeline (globaltimer) of the ring and tail kernels, see hp_measure_set_trace
+__device__ unsigned long long *g_trace = nullptr;
+__device__ __forceinline__ void trace_mark(size_t slot) {
+    if (g_trace != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[slot] = t;
+    }
+}
+#define HP_TRACE(slot) do { if (threadIdx.x == 0) trace_mark(slot); } while (0)
+#else
+#define HP_TRACE(slot) do { } while (0)
+#endif
+
 struct RingNNArgs {
     const float *set1, *set2;  // [b,n,3], [b,m,3]
     int b, n, m;
@@ -52,9 +67,10 @@ struct RingNNArgs {
     float *dist1, *dist2;
     int *idx1, *idx2;
     float *loss;               // nullptr: no fused loss
-    float *losspart;           // [2b] per-(cloud,direction) sums
-    float *grouppart;          // [ngroups]
-    unsigned int *counters;    // [1 + ngroups] tickets; zero on entry, zero on exit
+    float *losspart;           // loss partials: [2b] per (cloud, direction) (unpack kernel) or per 256-source chunk (tail kernel)
+    unsigned int *counters;    // [1] loss ticket; zero on entry, zero on exit
+    unsigned int *ticket;      // [b] ring CTAs of the cloud that have merged their keys; zero on entry, zero on exit
+    unsigned int *done;        // [b] tail CTAs of the cloud that have read the keys; zero on entry, zero on exit
     // optional inverse index maps for the atomic-free backward (nullptr: not produced).
     //   inv1 [b][n + 2m]: perm1[n] = row indices i sorted by (idx1[i], i); then begin1[m], end1[m]: bucket of column k
     //   inv2 [b][m + 2n]: perm2[m] = column indices k sorted by (idx2[k], k); then begin2[n], end2[n]: bucket of row i
@@ -90,7 +106,8 @@ __device__ __forceinline__ RFGroup rf_load_group(const float *cols_p, int g) {
     return r;
 }
 
-// DBG: timing experiments only (HP_RING_VARIANT 10/11/12): bit 0 = two rotations instead of 32, bit 1 = no rescans
+// DBG (bench library only, HP_BENCH_BUILD): timing experiments, bit 0 = two rotations instead of 32, bit 1 = no rescans,
+// bit 2 = no ticket arrival
 template <int MINB, int DBG = 0>
 __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const RingNNArgs a) {
     __shared__ __align__(128) float rows_s[RF_ROWS * 3];
@@ -103,6 +120,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     asm volatile("griddepcontrol.launch_dependents;");  // a programmatically dependent tail kernel may start its prologue
+    HP_TRACE((size_t)blockIdx.x * 2);
     int bid = blockIdx.x;
     const int cc = bid % a.colchunks;
     bid /= a.colchunks;
@@ -323,6 +341,16 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
             __syncthreads();                             // next columns visible, wcolkey / cols_p consumed
         }
     }
+    // this CTA's candidates are merged: one more arrival on the cloud's ticket (bar.sync orders every thread's key atomics
+    // before thread 0's fence; the tail kernel's CTAs of this cloud acquire the ticket before they read the keys)
+    if (!(DBG & 4)) {  // (DBG 4: timing experiment without the arrival)
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(a.ticket + cloud, 1u);
+        }
+    }
+    HP_TRACE((size_t)blockIdx.x * 2 + 1);
 }
 
 
@@ -547,100 +575,57 @@ __device__ __forceinline__ void rf_build_inverse(const RingNNArgs &a, unsigned i
 }
 
 
-// key -> (distance, index); restores the zero state of the key arrays; fixed-order loss.
-// One block per (cloud, direction).  The loss is folded through a two-level ticket (groups of RF_GROUP blocks, then
-// groups) so that no single address sees more than RF_GROUP / (blocks / RF_GROUP) serialised atomics.
-constexpr int RF_GROUP = 32;
+// ---- deterministic loss ------------------------------------------------------------------------------------------
+// One summation order for every path (bit-identical losses from the unpack kernel and from the tail kernel):
+//   chunk partial            = the 256 distances of sources [256r, 256r + 256): xor-shuffle tree per warp, then the 8 warp
+//                              sums serially in warp order;
+//   (cloud, direction) sum   = its chunk partials serially in ascending order;
+//   total                    = thread t of 256 adds the (cloud, direction) sums t, t + 256, ... serially; the 256 accumulators
+//                              are folded by the xor tree per warp and serially over the 8 warps.
+// The partials meet in a[...].losspart; the last CTA to arrive on counters[0] folds them and restores the zero state.
+constexpr int LS_CHUNK = 256;
 
-__device__ __forceinline__ float rf_block_sum(float v, float *warp_part, int tid) {
-    v = warp_sum(v);
-    __syncthreads();  // warp_part reusable
-    if ((tid & 31) == 0) warp_part[tid >> 5] = v;
-    __syncthreads();
+__device__ __forceinline__ float rf_serial8(const float *w) {
     float s = 0.f;
-    if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < RF_MERGE_THREADS / 32; ++i) s += warp_part[i];
-    }
-    return s;  // valid in thread 0
+    for (int i = 0; i < 8; ++i) s += w[i];
+    return s;
 }
 
-// Deterministic loss: per-block partial -> two-level tickets (groups of RF_GROUP blocks, then groups), folded in block /
-// group order by the last arriver.  Call with all threads of the block; `v` = this thread's partial (fixed order).
-__device__ __forceinline__ void rf_loss_fold(const RingNNArgs &a, float v, float *warp_part, int *flag_p, int tid) {
-    int &flag = *flag_p;
-    const float s = rf_block_sum(v, warp_part, tid);
-    if (gridDim.x <= RF_MERGE_THREADS) {
-        // up to 1024 blocks: ONE ticket; the last arriver folds all partials with the fixed block_sum tree (thread i holds
-        // block i's partial).  One fence + one atomic on everybody's path, one more fence + load for the last block.
-        if (tid == 0) {
-            a.losspart[blockIdx.x] = s;
-            __threadfence();
-            flag = (atomicAdd(a.counters, 1u) == gridDim.x - 1);
-        }
-        __syncthreads();
-        if (flag) {  // block-uniform
-            __threadfence();
-            float t = 0.f;
-            if (tid < (int)gridDim.x) {
-                t = __ldcg(a.losspart + tid);
-                a.losspart[tid] = 0.f;  // the whole workspace returns to zero (its layout moves with the shape)
+// Called by every thread of the last-arriving CTA (>= 256 threads).  chunks1 / chunks2 > 0: losspart holds chunk partials,
+// per cloud [chunks1 of direction 0 | chunks2 of direction 1]; chunks1 == 0: losspart holds one sum per (cloud, direction).
+__device__ __forceinline__ void rf_loss_total(const RingNNArgs &a, int chunks1, int chunks2, float *wp8, int tid) {
+    float acc = 0.f;
+    if (tid < 256) {
+        for (int pd = tid; pd < 2 * a.b; pd += 256) {
+            float p;
+            if (chunks1 == 0) {
+                p = __ldcg(a.losspart + pd);
+                a.losspart[pd] = 0.f;
+            } else {
+                float *q = a.losspart + (size_t)(pd >> 1) * (chunks1 + chunks2) + ((pd & 1) ? chunks1 : 0);
+                const int nch = (pd & 1) ? chunks2 : chunks1;
+                p = 0.f;
+                for (int r = 0; r < nch; ++r) {
+                    p += __ldcg(q + r);
+                    q[r] = 0.f;
+                }
             }
-            const float tot = rf_block_sum(t, warp_part, tid);
-            if (tid == 0) {
-                a.loss[0] = tot;
-                a.counters[0] = 0u;
-            }
+            acc += p;
         }
-        return;
     }
-    const int group = blockIdx.x / RF_GROUP, ngroups = (gridDim.x + RF_GROUP - 1) / RF_GROUP;
-    const int gfirst = group * RF_GROUP, gcount = min(RF_GROUP, (int)gridDim.x - gfirst);
-    if (tid == 0) {
-        a.losspart[blockIdx.x] = s;
-        __threadfence();
-        flag = (atomicAdd(a.counters + 1 + group, 1u) == (unsigned)gcount - 1);
-    }
+    acc = warp_sum(acc);
+    __syncthreads();  // wp8 reusable
+    if (tid < 256 && (tid & 31) == 0) wp8[tid >> 5] = acc;
     __syncthreads();
-    if (flag) {  // block-uniform
-        // last block of its group: fold the group's partials in block order
-        __syncthreads();
-        if (tid < 32) {  // warp 0: one partial per lane (independent loads), summed by lane 0 in block order
-            __threadfence();
-            float p = 0.f;
-            if (tid < gcount) {
-                p = __ldcg(a.losspart + gfirst + tid);
-                a.losspart[gfirst + tid] = 0.f;  // the whole workspace returns to zero (its layout moves with the shape)
-            }
-            float t = 0.f;
-#pragma unroll
-            for (int i = 0; i < RF_GROUP; ++i) {
-                const float pi = __shfl_sync(0xffffffffu, p, i);
-                t += (i < gcount) ? pi : 0.f;
-            }
-            if (tid == 0) {
-                a.grouppart[group] = t;
-                a.counters[1 + group] = 0u;
-                __threadfence();
-                flag = (atomicAdd(a.counters, 1u) == (unsigned)ngroups - 1);
-            }
-        }
-        __syncthreads();
-        if (flag) {
-            // last group: fold the group sums in group order
-            float t = 0.f;
-            for (int i = tid; i < ngroups; i += RF_MERGE_THREADS) t += __ldcg(a.grouppart + i);
-            __threadfence();
-            const float tot = rf_block_sum(t, warp_part, tid);
-            for (int i = tid; i < ngroups; i += RF_MERGE_THREADS) a.grouppart[i] = 0.f;
-            if (tid == 0) {
-                a.loss[0] = tot;
-                a.counters[0] = 0u;
-            }
-        }
+    if (tid == 0) {
+        a.loss[0] = rf_serial8(wp8);
+        a.counters[0] = 0u;
     }
 }
 
+// key -> (distance, index); restores the zero state of the key arrays and of the cloud's ring ticket; fixed-order loss.
+// One block per (cloud, direction).
 template <bool INVERT>
 __global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const RingNNArgs a) {
     extern __shared__ __align__(16) unsigned int sortbuf[];  // INVERT: [sort_n] composites
@@ -653,7 +638,8 @@ __global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const 
     u64 *src = (dir2 ? a.colkey : a.rowkey) + (size_t)cloud * cnt;
     float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
     int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
-    // Phase 1 only READS the keys: the device-scope fences of the loss tickets below then have no stores of this SM to
+    if (!dir2 && tid == 0) a.ticket[cloud] = 0u;  // the ring kernel's arrivals are not needed on this path
+    // Phase 1 only READS the keys: the device-scope fence of the loss ticket below then has no stores of this SM to
     // drain (a fence issued after the 3 stores per element costs ~10 us).  Phase 2 (unpack_store) writes the outputs.
     auto unpack_store = [&]() {
         for (int e = tid; e < cnt; e += RF_MERGE_THREADS) {
@@ -673,220 +659,235 @@ __global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const 
         unpack_store();
         return;
     }
-    float v = 0.f;
-    for (int e = tid; e < cnt; e += RF_MERGE_THREADS) v += __uint_as_float((unsigned)((~__ldcg(src + e)) >> 32));  // fixed order
-    rf_loss_fold(a, v, warp_part, &flag, tid);
+    float p = 0.f;  // thread 0: this (cloud, direction)'s sum, chunk by chunk (see "deterministic loss")
+    for (int base = 0; base < cnt; base += RF_MERGE_THREADS) {  // block-uniform trip count
+        const int e = base + tid;
+        float v = e < cnt ? __uint_as_float((unsigned)((~__ldcg(src + e)) >> 32)) : 0.f;
+        v = warp_sum(v);
+        __syncthreads();  // warp_part reusable
+        if ((tid & 31) == 0) warp_part[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int grp = 0; grp < RF_MERGE_THREADS / LS_CHUNK; ++grp)
+                if (base + grp * LS_CHUNK < cnt) p += rf_serial8(warp_part + grp * 8);
+        }
+    }
+    if (tid == 0) {
+        a.losspart[blockIdx.x] = p;
+        __threadfence();
+        flag = (atomicAdd(a.counters, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (flag) {  // block-uniform: last arriver
+        __threadfence();
+        rf_loss_total(a, 0, 0, warp_part, tid);
+    }
     unpack_store();
 }
 
-// ---- fused tail of the training step: unpack + loss + inverse maps + BOTH gradients in one kernel -----------------
-// A cluster of two CTAs per cloud.  CTA `dir2 = rank` decodes the keys of its direction (dist / idx outputs, loss
-// partial), builds the inverse of that index map IN SHARED MEMORY and computes the gradient of the TARGET side:
-//     rank 0: rows -> columns (idx1), buckets over the columns,  grad_xyz2[k] = 2g[(b_k - a_idx2[k]) + sum_{i: idx1[i]=k} (b_k - a_i)]
-//     rank 1: columns -> rows (idx2), buckets over the rows,     grad_xyz1[i] = 2g[(a_i - b_idx1[i]) + sum_{k: idx2[k]=i} (a_i - b_k)]
-// (nndistance.cu:143-151).  The "own" term needs the OTHER direction's index, which the CTA reads from the other key array
-// itself; a cluster barrier orders those reads before the owner zero-restores its keys.  Both clouds' points are staged into
-// shared memory by bulk-TMA BEFORE griddepcontrol.wait, i.e. under the tail of the ring kernel when the launch is
-// programmatic (PDL); buckets, permutation and points are then read from shared memory only.  Summation order and
-// arithmetic are those of nn_grad_gather_kernel (ascending source index; buckets above GATHER_COOP warp-cooperatively),
-// so the gradients are bit-identical to the three-kernel path.
-struct RingFinishArgs {
+// ---- fused tail of the training step: unpack + loss + inverse index maps + BOTH gradients ------------------------------
+// One CTA of 256 threads per (cloud, direction, section of 256 TARGET points); thread = target.
+//     direction 0: rows -> columns (idx1), targets = columns,  grad_xyz2[k] = 2g[(b_k - a_idx2[k]) + sum_{i: idx1[i]=k} (b_k - a_i)]
+//     direction 1: columns -> rows (idx2), targets = rows,     grad_xyz1[i] = 2g[(a_i - b_idx1[i]) + sum_{k: idx2[k]=i} (a_i - b_k)]
+// (nndistance.cu:143-151).  The kernel is launched programmatically dependent on the ring kernel and does NOT wait for the
+// whole grid: the ring kernel's CTAs are ordered cloud-major and bump a per-cloud ticket when their keys are merged; a tail
+// CTA stages its points and clears its tables while it waits for ITS cloud's ticket, so the tails of the early clouds run
+// under the ring kernel's second wave and only the last clouds' tails (a few microseconds, all in parallel) are exposed.
+//   * every CTA reads all `cnt` source keys of its direction (8 per thread at 2048 points) and keeps those whose target falls
+//     into its section.  The inverse map is a STABLE counting sort without any sorting: sources are ranked among the equal
+//     targets of their 32-source chunk by __match_any_sync, a [chunk][target] count table is prefix-summed per target over
+//     the chunks (thread = target), and position = bucket begin + chunk prefix + rank.  Data-independent cost, buckets in
+//     ascending source order whatever the skew of the assignment.
+//   * gradients: arithmetic and summation order of nn_grad_gather_kernel (ascending source index; buckets above GATHER_COOP
+//     warp-cooperatively), so they are bit-identical to the three-kernel path.
+//   * distances / indices / loss chunk r of the direction are written by section r mod (number of sections).
+//   * the last tail CTA of a cloud to have read the keys (done ticket) restores the zero state of both key arrays and of the
+//     cloud's tickets; the last CTA on the loss ticket folds the loss and waits for the ring grid (griddepcontrol.wait), so
+//     the tail grid never completes before its prerequisite.
+struct RingTailArgs {
     const float *g;          // device scalar: upstream gradient of the loss
     float *grad1, *grad2;    // [b,n,3], [b,m,3]
+    int sec1, sec2;          // sections of direction 0 (ceil(m / 256) column sections) and 1 (ceil(n / 256) row sections)
+    int chunks1, chunks2;    // 256-source loss chunks of direction 0 (ceil(n / 256)) and 1 (ceil(m / 256))
+    unsigned int expected;   // ring CTAs per cloud
 };
-constexpr int GATHER_COOP_F = 32;  // == GATHER_COOP of nn_grad_gather_kernel (same summation tree)
+constexpr int TL_THREADS = 256, TL_SEC = 256, TL_WARPS = TL_THREADS / 32;
+constexpr int TL_MAX_POINTS = 4096;  // keys of a direction live in registers: <= 16 per thread
+constexpr int GATHER_COOP_F = 32;    // == GATHER_COOP of nn_grad_gather_kernel (same summation tree)
 
-// shared memory (bytes) of the fused tail; 0 if the shape does not fit (caller falls back to the three-kernel path)
-static size_t rf_finish_smem_bytes(int n, int m) {
+// dynamic shared memory of the tail kernel; 0 if the shape is not supported (caller takes the three-kernel path)
+static size_t rf_tail_smem_bytes(int n, int m) {
     const size_t big = (size_t)(n > m ? n : m);
-    if (big > 8192) return 0;
-    size_t ints = 4 * big + RX_WARPS * RX_BINS + RX_BINS;  // sort area + radix rank table
-    ints += 4 * big;                                       // perm | begin | end | idxT (each <= big)
-    size_t bytes = ints * 4;
-    bytes = (bytes + 15) & ~(size_t)15;
-    bytes += (((size_t)n * 12 + 15) & ~(size_t)15) + (((size_t)m * 12 + 15) & ~(size_t)15);
-    return bytes <= 227 * 1024 ? bytes : 0;
+    if (big > TL_MAX_POINTS) return 0;
+    const size_t c32 = (big + 31) / 32;
+    size_t bytes = c32 * TL_SEC * 2;               // table  u16 [chunk of 32 sources][target of the section]
+    bytes += ((big * 2 + 15) & ~(size_t)15) * 2;   // info, pbuf  u16 [source]
+    bytes += (big * 12 + 15) & ~(size_t)15;        // source points
+    bytes += TL_SEC * 12;                          // target points of the section
+    return bytes;
 }
 
-__global__ void __launch_bounds__(RF_MERGE_THREADS, 1) nn_ring_finish_kernel(const RingNNArgs a, const RingFinishArgs f) {
-    extern __shared__ __align__(16) unsigned int fsm[];
-    __shared__ float warp_part[RF_MERGE_THREADS / 32];
-    __shared__ int flag;
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int ROUNDS>  // ceil(cnt / 256) <= ROUNDS: the keys of the direction stay in registers between the phases
+__global__ void __launch_bounds__(TL_THREADS, 4) nn_ring_tail_kernel(const RingNNArgs a, const RingTailArgs f) {
+    extern __shared__ __align__(16) unsigned char tsm[];
+    __shared__ float wp_s[ROUNDS][TL_WARPS];
+    __shared__ int wscan_s[TL_WARPS];
+    __shared__ int begin_s[TL_SEC];
+    __shared__ int idxT_s[TL_SEC];
+    __shared__ int flag_s[2];
     __shared__ __align__(8) uint64_t mbar;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int cloud = blockIdx.x >> 1;
-    const bool dir2 = blockIdx.x & 1;       // == rank in the cluster
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per_cloud = f.sec1 + f.sec2;
+    const int cloud = blockIdx.x / per_cloud, rr = blockIdx.x - cloud * per_cloud;
+    const bool dir2 = rr >= f.sec1;
+    const int sec = dir2 ? rr - f.sec1 : rr, nsec = dir2 ? f.sec2 : f.sec1;
     const int cnt = dir2 ? a.m : a.n;       // sources of this direction
     const int ntgt = dir2 ? a.n : a.m;      // targets (the side whose gradient this CTA produces)
+    const int tbase = sec * TL_SEC, tcount = min(TL_SEC, ntgt - tbase);
     const int big = a.n > a.m ? a.n : a.m;
-    unsigned int *sortarea = fsm;                                   // keys | count | cursor | pbuf, then the radix table
-    int *perm_s = reinterpret_cast<int *>(fsm + 4 * (size_t)big + RX_WARPS * RX_BINS + RX_BINS);
-    int *begin_s = perm_s + big, *end_s = begin_s + ntgt;           // begin/end contiguous (rf_build_inverse contract)
-    int *idxT_s = perm_s + 3 * (size_t)big;
-    size_t off = ((8 * (size_t)big + RX_WARPS * RX_BINS + RX_BINS) * 4 + 15) & ~(size_t)15;
-    float *T_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(fsm) + off);
-    off += ((size_t)ntgt * 12 + 15) & ~(size_t)15;
-    float *S_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(fsm) + off);
-    const float *__restrict__ Tg = (dir2 ? a.set1 : a.set2) + (size_t)cloud * ntgt * 3;
+    const int c32 = (cnt + 31) >> 5;
+    unsigned short *table = reinterpret_cast<unsigned short *>(tsm);
+    size_t off = (size_t)((big + 31) >> 5) * TL_SEC * 2;
+    unsigned short *info = reinterpret_cast<unsigned short *>(tsm + off);
+    off += ((size_t)big * 2 + 15) & ~(size_t)15;
+    unsigned short *pbuf = reinterpret_cast<unsigned short *>(tsm + off);
+    off += ((size_t)big * 2 + 15) & ~(size_t)15;
+    float *S_s = reinterpret_cast<float *>(tsm + off);
+    off += ((size_t)big * 12 + 15) & ~(size_t)15;
+    float *T_s = reinterpret_cast<float *>(tsm + off);
+    const float *__restrict__ Tg = (dir2 ? a.set1 : a.set2) + ((size_t)cloud * ntgt + tbase) * 3;
     const float *__restrict__ Sg = (dir2 ? a.set2 : a.set1) + (size_t)cloud * cnt * 3;
 
-    // ---- prologue (independent of the ring kernel's results): both clouds into shared memory ----
+    // ---- prologue (independent of the ring kernel's results): points into shared memory, count table cleared ----
+    HP_TRACE((size_t)2 * a.b * a.rowchunks * a.colchunks + (size_t)blockIdx.x * 3);
     if (tid == 0) mbar_init(&mbar, 1);
     __syncthreads();
-    const uint32_t tb = rf_bulk_bytes(Tg, ntgt), sb = rf_bulk_bytes(Sg, cnt);
+    const uint32_t tb = rf_bulk_bytes(Tg, tcount), sb = rf_bulk_bytes(Sg, cnt);
     if (tid == 0 && tb + sb) {
         fence_proxy_async();
         mbar_expect_tx(&mbar, tb + sb);
         if (tb) bulk_g2s(T_s, Tg, tb, &mbar);
         if (sb) bulk_g2s(S_s, Sg, sb, &mbar);
     }
-    if (tb != (uint32_t)ntgt * 12u) rf_stage_tail(T_s, Tg, ntgt, ntgt, 0.f, tb, tid, RF_MERGE_THREADS);  // uniform; rare
-    if (sb != (uint32_t)cnt * 12u) rf_stage_tail(S_s, Sg, cnt, cnt, 0.f, sb, tid, RF_MERGE_THREADS);
-    unsigned int *keys_s = sortarea, *dtmp_s = sortarea + 3 * (size_t)big;  // distances parked in the (still unused) pbuf region
-    int *count = reinterpret_cast<int *>(sortarea) + big, *cursor = count + big, *pbuf = cursor + big;
-    for (int i = tid; i < ntgt; i += RF_MERGE_THREADS) count[i] = 0;
+    if (tb != (uint32_t)tcount * 12u) rf_stage_tail(T_s, Tg, tcount, tcount, 0.f, tb, tid, TL_THREADS);  // uniform; rare
+    if (sb != (uint32_t)cnt * 12u) rf_stage_tail(S_s, Sg, cnt, cnt, 0.f, sb, tid, TL_THREADS);
+    {
+        uint4 *t4 = reinterpret_cast<uint4 *>(table);
+        for (int i = tid; i < c32 * (TL_SEC * 2 / 16); i += TL_THREADS) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // ---- wait for this cloud's ring CTAs (all of them are resident or done when this grid is allowed to start) ----
+    if (tid == 0) {
+        while (ld_acquire_u32(a.ticket + cloud) < f.expected) __nanosleep(64);
+    }
+    HP_TRACE((size_t)2 * a.b * a.rowchunks * a.colchunks + (size_t)blockIdx.x * 3 + 1);
     __syncthreads();
 
-    asm volatile("griddepcontrol.wait;" ::: "memory");  // the ring kernel's keys are complete and visible
-
-    // ---- keys: own direction (distance + index, histogram of the targets), other direction (index of every target point) ----
+    // ---- keys: own direction (distance + target of every source), other direction (the own-term index of my target) ----
     u64 *src = (dir2 ? a.colkey : a.rowkey) + (size_t)cloud * cnt;
-    const u64 *oth = (dir2 ? a.rowkey : a.colkey) + (size_t)cloud * ntgt;
-    float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
-    int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
-    float v = 0.f;
-    for (int e = tid; e < cnt; e += RF_MERGE_THREADS) {
-        const u64 key = ~__ldcg(src + e);
-        const unsigned tgt = (unsigned)(key & 0xffffffffu);
-        keys_s[e] = tgt;
-        dtmp_s[e] = (unsigned)(key >> 32);
-        v += __uint_as_float((unsigned)(key >> 32));  // fixed order (same as nn_ring_unpack_kernel)
-        atomicAdd(&count[min(tgt, (unsigned)(ntgt - 1))], 1);
+    u64 *oth = (dir2 ? a.rowkey : a.colkey) + (size_t)cloud * ntgt;
+    u64 key[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int e = r * TL_THREADS + tid;
+        key[r] = e < cnt ? ~__ldcg(src + e) : 0ull;
     }
-    for (int k = tid; k < ntgt; k += RF_MERGE_THREADS) idxT_s[k] = (int)(unsigned)((~__ldcg(oth + k)) & 0xffffffffu);
-    // loss tickets first: nothing of this SM is in flight yet, so their fences are cheap
-    if (a.loss != nullptr) rf_loss_fold(a, v, warp_part, &flag, tid);
-    // both CTAs of the cluster have read both key arrays -> the owner may zero-restore its array
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    for (int e = tid; e < cnt; e += RF_MERGE_THREADS) {
-        src[e] = 0ull;
-        dist[e] = __uint_as_float(dtmp_s[e]);
-        idx[e] = (int)keys_s[e];
+    if (tid < tcount) idxT_s[tid] = (int)(unsigned)((~__ldcg(oth + tbase + tid)) & 0xffffffffu);
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int e = r * TL_THREADS + tid;
+        if (r * TL_THREADS < cnt) {  // block-uniform
+            const unsigned tl = (unsigned)(key[r] & 0xffffffffu) - (unsigned)tbase;
+            const bool insec = e < cnt && tl < (unsigned)tcount;
+            const unsigned peers = __match_any_sync(0xffffffffu, insec ? tl : 0xffffffffu);
+            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            if (insec && rank == 0) table[(size_t)(r * TL_WARPS + warp) * TL_SEC + tl] = (unsigned short)__popc(peers);
+            if (e < cnt) info[e] = insec ? (unsigned short)(tl | (rank << 8)) : (unsigned short)0xffffu;
+            if (a.loss != nullptr && (r % nsec) == sec) {  // block-uniform: this section owns loss chunk r
+                const float v = warp_sum(e < cnt ? __uint_as_float((unsigned)(key[r] >> 32)) : 0.f);
+                if (lane == 0) wp_s[r][warp] = v;
+            }
+        }
     }
-    __syncthreads();  // histogram complete; dtmp consumed before the placement re-uses the region
+    __syncthreads();  // table, info, idxT, warp sums complete; every key of both arrays this CTA needs has been read
+    if (tid == 0) {
+        flag_s[0] = (atomicAdd(a.done + cloud, 1u) == (unsigned)per_cloud - 1);  // last reader of the cloud restores the keys
+        flag_s[1] = 0;
+        if (a.loss != nullptr) {
+            const int nch = dir2 ? f.chunks2 : f.chunks1;
+            float *lp = a.losspart + (size_t)cloud * (f.chunks1 + f.chunks2) + (dir2 ? f.chunks1 : 0);
+            for (int r = sec; r < nch; r += nsec) lp[r] = rf_serial8(wp_s[r]);
+            __threadfence();  // nothing else of this thread is in flight: cheap
+            flag_s[1] = (atomicAdd(a.counters, 1u) == gridDim.x - 1);
+        }
+    }
 
-    // ---- exclusive scan of the histogram (contiguous chunk per thread, warp scan, scan of the warp totals) + largest bucket ----
-    __shared__ int scan_warp_f[RF_MERGE_THREADS / 32];
-    __shared__ int max_bucket_f;
-    const int per = (ntgt + RF_MERGE_THREADS - 1) / RF_MERGE_THREADS;
-    const int lo = min(ntgt, tid * per), hi = min(ntgt, lo + per);
-    int local = 0, lmax = 0;
-    for (int i = lo; i < hi; ++i) local += count[i], lmax = max(lmax, count[i]);
-    int inc = local;
+    // ---- per target: prefix of its counts over the chunks (-> stable position of every source), bucket size ----
+    int size = 0;
+    {
+        unsigned short *col = table + tid;
+#pragma unroll 8
+        for (int c = 0; c < c32; ++c) {
+            const int v = col[(size_t)c * TL_SEC];
+            col[(size_t)c * TL_SEC] = (unsigned short)size;
+            size += v;
+        }
+    }
+    int inc = size;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int u = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += u;
     }
-    lmax = __reduce_max_sync(0xffffffffu, lmax);
-    if (lane == 31) scan_warp_f[tid >> 5] = inc;
-    if (tid == 0) max_bucket_f = 0;
-    __syncthreads();
-    if (tid < 32) {
-        const int w = scan_warp_f[tid];
-        int winc = w;
+    if (lane == 31) wscan_s[warp] = inc;
+    __syncthreads();  // warp totals (and the flags) visible
+    int begin = inc - size;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, winc, o);
-            if (tid >= o) winc += u;
-        }
-        scan_warp_f[tid] = winc - w;  // exclusive prefix of the warp totals
+    for (int w = 0; w < TL_WARPS; ++w) begin += (w < warp) ? wscan_s[w] : 0;
+    begin_s[tid] = begin;
+    const bool fold_loss = flag_s[1] != 0, restore = flag_s[0] != 0;
+    if (fold_loss) {  // block-uniform: every tail CTA's partials are visible (their fence + ticket, ours below)
+        __threadfence();
+        rf_loss_total(a, f.chunks1, f.chunks2, wp_s[0], tid);
     }
-    if (lane == 0 && lmax > 0) atomicMax(&max_bucket_f, lmax);
-    __syncthreads();
-    const bool lean = max_bucket_f <= GATHER_COOP_F;  // block-uniform
-
-    const float gs = __ldg(f.g) * 2.f;
-    float *G = (dir2 ? f.grad1 : f.grad2) + (size_t)cloud * ntgt * 3;
-    if (lean) {
-        // ---- benign assignment (no bucket above GATHER_COOP): placement in arrival order, the gradient thread orders its
-        //      (tiny) bucket itself -- a 4-element sorting network, or ascending selection for 5..32 entries ----
-        {
-            int run = scan_warp_f[tid >> 5] + inc - local;
-            for (int i = lo; i < hi; ++i) {
-                const int c = count[i];
-                count[i] = run;   // begin
-                cursor[i] = run;  // becomes end after the placement
-                run += c;
+    __syncthreads();  // begin_s, chunk prefixes complete
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int e = r * TL_THREADS + tid;
+        if (e < cnt) {
+            const unsigned inf = info[e];
+            if (inf != 0xffffu) {
+                const unsigned tl = inf & 255u;
+                pbuf[begin_s[tl] + table[(size_t)(e >> 5) * TL_SEC + tl] + (inf >> 8)] = (unsigned short)e;
             }
         }
-        __syncthreads();
-        for (int e = tid; e < cnt; e += RF_MERGE_THREADS) pbuf[atomicAdd(&cursor[min(keys_s[e], (unsigned)(ntgt - 1))], 1)] = e;
-        if (tb + sb) mbar_wait(&mbar, 0);
-        __syncthreads();  // buckets complete, points visible
-        for (int k = tid; k < ntgt; k += RF_MERGE_THREADS) {
-            const int b0 = count[k], sz = cursor[k] - b0;
-            const float px = T_s[3 * k + 0], py = T_s[3 * k + 1], pz = T_s[3 * k + 2];
-            const int j = min(max(idxT_s[k], 0), cnt - 1);
-            float ax = gs * (px - S_s[3 * j + 0]);
-            float ay = gs * (py - S_s[3 * j + 1]);
-            float az = gs * (pz - S_s[3 * j + 2]);
-            auto acc = [&](int e) {
-                ax += -(gs * (S_s[3 * e + 0] - px));
-                ay += -(gs * (S_s[3 * e + 1] - py));
-                az += -(gs * (S_s[3 * e + 2] - pz));
-            };
-            if (sz <= 4) {
-                int e0 = sz > 0 ? pbuf[b0] : 0x7fffffff, e1 = sz > 1 ? pbuf[b0 + 1] : 0x7fffffff;
-                int e2 = sz > 2 ? pbuf[b0 + 2] : 0x7fffffff, e3 = sz > 3 ? pbuf[b0 + 3] : 0x7fffffff;
-                int t;
-                t = min(e0, e1), e1 = max(e0, e1), e0 = t;
-                t = min(e2, e3), e3 = max(e2, e3), e2 = t;
-                t = min(e0, e2), e2 = max(e0, e2), e0 = t;
-                t = min(e1, e3), e3 = max(e1, e3), e1 = t;
-                t = min(e1, e2), e2 = max(e1, e2), e1 = t;
-                if (sz > 0) acc(e0);
-                if (sz > 1) acc(e1);
-                if (sz > 2) acc(e2);
-                if (sz > 3) acc(e3);
-            } else {
-                int prev = -1;
-                for (int it = 0; it < sz; ++it) {  // ascending selection: sources are distinct
-                    int cur = 0x7fffffff;
-                    for (int p = b0; p < b0 + sz; ++p) {
-                        const int e = pbuf[p];
-                        cur = (e > prev && e < cur) ? e : cur;
-                    }
-                    acc(cur);
-                    prev = cur;
-                }
-            }
-            G[3 * k + 0] = ax, G[3 * k + 1] = ay, G[3 * k + 2] = az;
-        }
-        return;
     }
-
-    // ---- skewed assignment: data-independent stable sort (rf_build_inverse), buckets above GATHER_COOP warp-cooperatively ----
-    rf_build_inverse(a, sortarea, dir2, tid, perm_s, begin_s, end_s);
     if (tb + sb) mbar_wait(&mbar, 0);
-    __syncthreads();  // inverse complete, points visible
-    for (int base = 0; base < ntgt; base += RF_MERGE_THREADS) {  // block-uniform trip count
-        const int k = base + tid;
-        const bool valid = k < ntgt;
-        int pb = 0, pe = 0;
+    __syncthreads();  // buckets complete, points visible
+
+    // ---- gradient of my target: own term + its bucket in ascending source order ----
+    const float gs = __ldg(f.g) * 2.f;
+    {
+        const bool valid = tid < tcount;
         float px = 0.f, py = 0.f, pz = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
         if (valid) {
-            pb = begin_s[k], pe = end_s[k];
-            px = T_s[3 * k + 0], py = T_s[3 * k + 1], pz = T_s[3 * k + 2];
-            const int j = min(max(idxT_s[k], 0), cnt - 1);
+            px = T_s[3 * tid + 0], py = T_s[3 * tid + 1], pz = T_s[3 * tid + 2];
+            const int j = min(max(idxT_s[tid], 0), cnt - 1);
             ax = gs * (px - S_s[3 * j + 0]);
             ay = gs * (py - S_s[3 * j + 1]);
             az = gs * (pz - S_s[3 * j + 2]);
         }
-        const bool bigb = valid && (pe - pb) > GATHER_COOP_F;
+        const int pb = begin, pe = begin + size;
+        const bool bigb = valid && size > GATHER_COOP_F;
         if (valid && !bigb) {
             for (int p = pb; p < pe; ++p) {  // ascending source index: fixed summation order
-                const int e = perm_s[p];
+                const int e = pbuf[p];
                 ax += -(gs * (S_s[3 * e + 0] - px));
                 ay += -(gs * (S_s[3 * e + 1] - py));
                 az += -(gs * (S_s[3 * e + 2] - pz));
@@ -900,7 +901,7 @@ __global__ void __launch_bounds__(RF_MERGE_THREADS, 1) nn_ring_finish_kernel(con
             const float qx = __shfl_sync(0xffffffffu, px, srcl), qy = __shfl_sync(0xffffffffu, py, srcl), qz = __shfl_sync(0xffffffffu, pz, srcl);
             float sx = 0.f, sy = 0.f, sz = 0.f;
             for (int p = b0 + lane; p < b1; p += 32) {
-                const int e = perm_s[p];
+                const int e = pbuf[p];
                 sx += -(gs * (S_s[3 * e + 0] - qx));
                 sy += -(gs * (S_s[3 * e + 1] - qy));
                 sz += -(gs * (S_s[3 * e + 2] - qz));
@@ -908,8 +909,37 @@ __global__ void __launch_bounds__(RF_MERGE_THREADS, 1) nn_ring_finish_kernel(con
             sx = warp_sum(sx), sy = warp_sum(sy), sz = warp_sum(sz);
             if (lane == srcl) ax += sx, ay += sy, az += sz;
         }
-        if (valid) G[3 * k + 0] = ax, G[3 * k + 1] = ay, G[3 * k + 2] = az;
+        if (valid) {
+            float *G = (dir2 ? f.grad1 : f.grad2) + ((size_t)cloud * ntgt + tbase + tid) * 3;
+            G[0] = ax, G[1] = ay, G[2] = az;
+        }
     }
+    // ---- distances / indices of the source chunks this section owns ----
+    {
+        float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
+        int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int e = r * TL_THREADS + tid;
+            if ((r % nsec) == sec && e < cnt) {
+                dist[e] = __uint_as_float((unsigned)(key[r] >> 32));
+                idx[e] = (int)(unsigned)(key[r] & 0xffffffffu);
+            }
+        }
+    }
+    if (restore) {  // block-uniform: every tail CTA of the cloud has read the keys -> zero state for the next launch
+        ulonglong2 *z1 = reinterpret_cast<ulonglong2 *>(src), *z2 = reinterpret_cast<ulonglong2 *>(oth);  // 16-byte aligned iff even counts
+        if (((cnt | ntgt) & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(oth)) & 15) == 0) {
+            for (int i = tid; i < cnt / 2; i += TL_THREADS) z1[i] = make_ulonglong2(0ull, 0ull);
+            for (int i = tid; i < ntgt / 2; i += TL_THREADS) z2[i] = make_ulonglong2(0ull, 0ull);
+        } else {
+            for (int i = tid; i < cnt; i += TL_THREADS) src[i] = 0ull;
+            for (int i = tid; i < ntgt; i += TL_THREADS) oth[i] = 0ull;
+        }
+        if (tid == 0) a.ticket[cloud] = 0u, a.done[cloud] = 0u;
+    }
+    HP_TRACE((size_t)2 * a.b * a.rowchunks * a.colchunks + (size_t)blockIdx.x * 3 + 2);
+    if (fold_loss) asm volatile("griddepcontrol.wait;" ::: "memory");  // the tail grid does not complete before the ring grid
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -923,17 +953,17 @@ static int rf_rounds_per_cta(int b, int n, int m) {
 }
 
 struct RFLayout {
-    int ngroups;
-    size_t off_counters, off_losspart, off_grouppart, off_rowkey, off_colkey, total;
+    int chunks1, chunks2;
+    size_t off_counters, off_ticket, off_done, off_losspart, off_rowkey, off_colkey, total;
 };
 static RFLayout rf_layout(int b, int n, int m) {
     RFLayout L;
-    const size_t blocks = (size_t)2 * b;
-    L.ngroups = (int)((blocks + RF_GROUP - 1) / RF_GROUP);
+    L.chunks1 = (n + LS_CHUNK - 1) / LS_CHUNK, L.chunks2 = (m + LS_CHUNK - 1) / LS_CHUNK;
     L.off_counters = 0;
-    L.off_losspart = (sizeof(unsigned int) * (1 + (size_t)L.ngroups) + 15) & ~(size_t)15;
-    L.off_grouppart = L.off_losspart + blocks * sizeof(float);
-    L.off_rowkey = (L.off_grouppart + (size_t)L.ngroups * sizeof(float) + 15) & ~(size_t)15;
+    L.off_ticket = 16;
+    L.off_done = L.off_ticket + sizeof(unsigned int) * (size_t)b;
+    L.off_losspart = (L.off_done + sizeof(unsigned int) * (size_t)b + 15) & ~(size_t)15;
+    L.off_rowkey = (L.off_losspart + (size_t)b * (L.chunks1 + L.chunks2) * sizeof(float) + 15) & ~(size_t)15;
     L.off_colkey = L.off_rowkey + (size_t)b * n * sizeof(u64);
     L.total = L.off_colkey + (size_t)b * m * sizeof(u64);
     return L;
@@ -945,7 +975,7 @@ size_t nn_ring_workspace_bytes(int b, int n, int m) {
 }
 
 // Inputs must be finite with |coordinate| < 1e15 (padding points sit at +-1e18).  The workspace must be all zero on
-// entry (every byte: the key arrays move with the shape) and is all zero again when the two kernels have run.
+// entry (every byte: the key arrays move with the shape) and is all zero again when the kernels of a call have run.
 static int ceil_log2(int v) {
     int l = 0;
     while ((1 << l) < v) ++l;
@@ -958,34 +988,43 @@ bool nn_ring_inverse_supported(int n, int m) {
     return big <= 32768;  // composite (target << shift | source) in 30 bits, sort buffer <= 128 KB
 }
 
-bool nn_ring_step_supported(int n, int m) { return n > 0 && m > 0 && rf_finish_smem_bytes(n, m) != 0; }
+bool nn_ring_step_supported(int n, int m) { return n > 0 && m > 0 && rf_tail_smem_bytes(n, m) != 0; }
+
+enum RingMode { RING_UNPACK = 0, RING_STEP = 1, RING_ONLY = 2 };
 
 static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
                                int *idx2, float *loss, int *inv1, int *inv2, const float *step_g, float *step_grad1,
-                               float *step_grad2, void *workspace, cudaStream_t stream, bool ring_only = false);
+                               float *step_grad2, void *workspace, cudaStream_t stream, RingMode mode);
 
 int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
                            int *idx2, float *loss, int *inv1, int *inv2, void *workspace, cudaStream_t stream) {
     return nn_ring_launch_impl(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, inv1, inv2, nullptr, nullptr, nullptr, workspace,
-                               stream);
+                               stream, RING_UNPACK);
 }
 
-// measurement helper (bench.py roofline of the dominant kernel): the ring kernel alone; leaves the keys in the workspace
+#ifdef HP_BENCH_BUILD
+int nn_ring_set_trace(void *dev_ptr) {
+    unsigned long long *p = reinterpret_cast<unsigned long long *>(dev_ptr);
+    HP_CUDA(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
+    return HP_OK;
+}
+// bench library only (roofline of the dominant kernel): the ring kernel alone; leaves keys and tickets in the workspace
 int nn_ring_only_launch(int b, int n, const float *xyz1, int m, const float *xyz2, void *workspace, cudaStream_t stream) {
     return nn_ring_launch_impl(b, n, xyz1, m, xyz2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                               nullptr, workspace, stream, true);
+                               nullptr, workspace, stream, RING_ONLY);
 }
+#endif
 
-// forward + backward of the fused loss in two kernels (ring + fused tail); requires nn_ring_step_supported(n, m)
+// forward + backward of the fused loss in two kernels (ring + sectioned tail); requires nn_ring_step_supported(n, m)
 int nn_ring_step_launch(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_loss, float *dist1, int *idx1,
                         float *dist2, int *idx2, float *loss, float *grad1, float *grad2, void *workspace, cudaStream_t stream) {
     return nn_ring_launch_impl(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, nullptr, nullptr, grad_loss, grad1, grad2,
-                               workspace, stream);
+                               workspace, stream, RING_STEP);
 }
 
 static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
                                int *idx2, float *loss, int *inv1, int *inv2, const float *step_g, float *step_grad1,
-                               float *step_grad2, void *workspace, cudaStream_t stream, bool ring_only) {
+                               float *step_grad2, void *workspace, cudaStream_t stream, RingMode mode) {
     RingNNArgs a = {};
     const RFLayout L = rf_layout(b, n, m);
     unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
@@ -994,14 +1033,16 @@ static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const flo
     a.rowchunks = (n + RF_ROWS - 1) / RF_ROWS;
     a.colchunks = ((m + RF_COLS - 1) / RF_COLS + a.R - 1) / a.R;
     a.counters = reinterpret_cast<unsigned int *>(ws + L.off_counters);
+    a.ticket = reinterpret_cast<unsigned int *>(ws + L.off_ticket);
+    a.done = reinterpret_cast<unsigned int *>(ws + L.off_done);
     a.losspart = reinterpret_cast<float *>(ws + L.off_losspart);
-    a.grouppart = reinterpret_cast<float *>(ws + L.off_grouppart);
     a.rowkey = reinterpret_cast<u64 *>(ws + L.off_rowkey);
     a.colkey = reinterpret_cast<u64 *>(ws + L.off_colkey);
     a.dist1 = dist1, a.dist2 = dist2, a.idx1 = idx1, a.idx2 = idx2, a.loss = loss;
     const long long grid = (long long)b * a.rowchunks * a.colchunks;
     const long long ugrid = (long long)2 * b;
     HP_REQUIRE(grid <= 0x7fffffffLL && ugrid <= 0x7fffffffLL, "nn ring forward: grid too large (%lld CTAs)", grid);
+#ifdef HP_BENCH_BUILD
     static int variant = -1;
     if (variant < 0) {
         const char *e = getenv("HP_RING_VARIANT");
@@ -1013,34 +1054,40 @@ static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const flo
     else if (variant == 10) nn_ring_kernel<4, 1><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     else if (variant == 11) nn_ring_kernel<4, 2><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     else if (variant == 12) nn_ring_kernel<4, 3><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
-    else nn_ring_kernel<4><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    else if (variant == 20) nn_ring_kernel<4, 4><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    else
+#endif
+        nn_ring_kernel<4><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
     HP_LAUNCH_CHECK("nn_ring_kernel");
-    if (ring_only) return HP_OK;  // measurement helper: the keys stay in the workspace
-    if (step_g != nullptr) {
-        const size_t smem = rf_finish_smem_bytes(n, m);
-        HP_REQUIRE(smem != 0, "nn ring step: clouds too large for the fused tail (n=%d m=%d)", n, m);
-        const int big = n > m ? n : m;
-        a.sort_n = 1 << ceil_log2(big);
-        a.sort_shift = ceil_log2(big);
-        a.inv_fast = 1;
-        RingFinishArgs f;
+    if (mode == RING_ONLY) return HP_OK;  // measurement helper: keys and tickets stay in the workspace
+    if (mode == RING_STEP) {
+        const size_t smem = rf_tail_smem_bytes(n, m);
+        HP_REQUIRE(smem != 0 && loss != nullptr, "nn ring step: clouds too large for the fused tail (n=%d m=%d) or no loss output", n, m);
+        RingTailArgs f;
         f.g = step_g, f.grad1 = step_grad1, f.grad2 = step_grad2;
-        static SmemAttrCache attr;
-        HP_CUDA(ensure_dynamic_smem(nn_ring_finish_kernel, smem, attr));
-        static int pdl = -1;
-        if (pdl < 0) {
-            const char *e = getenv("HP_NO_PDL");
-            pdl = (e && atoi(e)) ? 0 : 1;
-        }
+        f.sec1 = (m + TL_SEC - 1) / TL_SEC, f.sec2 = (n + TL_SEC - 1) / TL_SEC;
+        f.chunks1 = L.chunks1, f.chunks2 = L.chunks2;
+        f.expected = (unsigned)(a.rowchunks * a.colchunks);
+        const long long tgrid = (long long)b * (f.sec1 + f.sec2);
+        HP_REQUIRE(tgrid <= 0x7fffffffLL, "nn ring step: grid too large (%lld CTAs)", tgrid);
+        const bool small = (n > m ? n : m) <= 8 * TL_THREADS;
+        static SmemAttrCache attr8, attr16;
+        if (small) HP_CUDA(ensure_dynamic_smem(nn_ring_tail_kernel<8>, smem, attr8));
+        else HP_CUDA(ensure_dynamic_smem(nn_ring_tail_kernel<16>, smem, attr16));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)ugrid), cfg.blockDim = dim3(RF_MERGE_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-        cudaLaunchAttribute attrs[2];
-        attrs[0].id = cudaLaunchAttributeClusterDimension;
-        attrs[0].val.clusterDim.x = 2, attrs[0].val.clusterDim.y = 1, attrs[0].val.clusterDim.z = 1;
-        attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attrs[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attrs, cfg.numAttrs = pdl ? 2 : 1;
-        HP_CUDA(cudaLaunchKernelEx(&cfg, nn_ring_finish_kernel, a, f));
+        cfg.gridDim = dim3((unsigned)tgrid), cfg.blockDim = dim3(TL_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+        cudaLaunchAttribute attrs[1];
+        attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attrs, cfg.numAttrs = 1;
+#ifdef HP_BENCH_BUILD
+        {
+            const char *e = getenv("HP_NO_PDL");
+            if (e && atoi(e)) cfg.numAttrs = 0;
+        }
+#endif
+        if (small) HP_CUDA(cudaLaunchKernelEx(&cfg, nn_ring_tail_kernel<8>, a, f));
+        else HP_CUDA(cudaLaunchKernelEx(&cfg, nn_ring_tail_kernel<16>, a, f));
     } else if (inv1 != nullptr && inv2 != nullptr) {
         HP_REQUIRE(nn_ring_inverse_supported(n, m), "nn ring forward: clouds too large for the in-kernel inverse (n=%d m=%d)", n, m);
         a.inv1 = inv1, a.inv2 = inv2;
@@ -1058,7 +1105,7 @@ static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const flo
     } else {
         nn_ring_unpack_kernel<false><<<(unsigned)ugrid, RF_MERGE_THREADS, 0, stream>>>(a);
     }
-    HP_LAUNCH_CHECK("nn_ring_unpack_kernel / nn_ring_finish_kernel");
+    HP_LAUNCH_CHECK("nn_ring_unpack_kernel / nn_ring_tail_kernel");
     return HP_OK;
 }
 

@@ -5,6 +5,9 @@
 #include <stdio.h>
 
 #include "hp_b200.h"
+#ifdef HP_BENCH_BUILD
+#include "hp_b200_bench.h"
+#endif
 
 namespace hp {
 

@@ -17,23 +17,38 @@ from __future__ import annotations
 
 import torch
 
+from ._glue import workspace_owner
 from .chamfer import chamfer_step, chamfer_step_supported
 from .target_network import target_network_backward, target_network_forward, target_network_num_weights
 
 
+class _OwnedGraph:
+    """A captured graph together with the zero-restored workspaces its kernels point at (kept alive with it)."""
+
+    def __init__(self, graph, workspaces):
+        self.graph, self.workspaces = graph, workspaces
+
+    def replay(self):
+        self.graph.replay()
+
+
 def _capture(fn, device, warmup: int = 3):
-    """Warm up on a side stream (allocates workspaces, sets kernel attributes), then capture `fn` once."""
+    """Warm up on a side stream (allocates workspaces, sets kernel attributes), then capture `fn` once.  Workspaces
+    requested during warm-up and capture belong to the returned graph object (``_glue.workspace_owner``), not to the
+    shared per-stream cache."""
+    store = {}
     side = torch.cuda.Stream(device=device)
     side.wait_stream(torch.cuda.current_stream(device))
-    with torch.cuda.stream(side):
-        for _ in range(warmup):
-            fn()
-    torch.cuda.current_stream(device).wait_stream(side)
-    torch.cuda.synchronize(device)
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, stream=side):
-        out = fn()
-    return graph, out, side
+    with workspace_owner(store):
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            out = fn()
+    return _OwnedGraph(graph, store), out, side
 
 
 class ChamferStepGraph:
@@ -157,6 +172,93 @@ class HotPathStepGraph:
     def replay(self):
         self.graph.replay()
         return self.rec, self.loss, self.grad_weights
+
+
+class FullModelStepGraph:
+    """ONE whole training step of the reference's trainer (core/epoch_loops.py:14-39; BASELINE config C4) as ONE CUDA graph:
+
+        latent            = full_model.mode.get_latent(...)          stock encoder(s)              (model/full_model.py:65)
+        weights [B,19011] = full_model.hyper_network(latent)         stock trunk + (fused) head    (:67)
+        rec     [B,N,3]   = fused TargetNetwork(weights, points)     one kernel                    (:70-74)
+        loss_r            = mean(loss_coef * ChamferLoss(gt, rec))   ring kernel + sectioned tail  (epoch_loops.py:25-26)
+        loss_all          = loss_r (+ KLD / B for the generative mode, :28-31)
+        loss_all.backward()                                          fused TargetNetwork backward, autograd through the
+                                                                     hypernetwork and the encoders
+        optimizer.step()                                             (optional; needs a capturable optimizer)
+
+    ``full_model`` is the caller's FullModel (the reference's class or the drop-in) already on ``device`` and in train mode; its
+    Parameters are updated in place by every replay when an optimizer is given.  Static inputs, refreshed by the caller before
+    ``replay()``: ``existing`` [B,3,Ne] and ``missing`` [B,3,Nm] (the layout FullModel.forward leaves them in, :56-60), ``gt``
+    [B,N,3], ``points`` [B,N,3] (the TargetNetwork inputs: ``load_points`` draws them on the host in the reference's RNG order
+    and copies them in).  Outputs refreshed in place: ``rec`` [B,N,3] (``rec.permute(0,2,1)`` is the trainer's
+    [B,3,N] view), ``loss_r``, ``loss_all``.  Inside the graph nothing is transposed or re-laid-out: the TargetNetwork writes the
+    [B,N,3] layout the Chamfer kernels read."""
+
+    def __init__(self, full_model, optimizer, batch: int, n_existing: int, n_missing: int, n_gt: int, device, loss_coef: float = 0.05,
+                 warmup: int = 3):
+        from .chamfer import ChamferLoss
+
+        self.device = torch.device(device)
+        self.model, self.optimizer, self.loss_coef = full_model, optimizer, float(loss_coef)
+        tcfg = full_model.target_network_config
+        self._loc, self._use_bias = tuple(int(c) for c in tcfg["layer_out_channels"]), bool(tcfg["use_bias"])
+        self._pg_cfg = full_model.point_generator_config
+        self._loss_fn = ChamferLoss()
+        self.generative = bool(full_model.mode.has_generativity())
+        with torch.cuda.device(self.device):
+            self.existing = torch.rand(batch, 3, n_existing, device=self.device) - 0.5
+            self.missing = torch.rand(batch, 3, max(n_missing, 1), device=self.device) - 0.5
+            self.gt = torch.rand(batch, n_gt, 3, device=self.device) - 0.5
+            self.points = torch.rand(batch, n_gt, 3, device=self.device) - 0.5
+            self.points_host = torch.empty(batch, n_gt, 3).pin_memory()
+            store = {}
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with workspace_owner(store):
+                with torch.cuda.stream(side):
+                    for _ in range(warmup):  # also lets Adam create its (capturable) state and cuBLAS pick its kernels
+                        self._step()
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                if optimizer is not None:
+                    optimizer.zero_grad(set_to_none=True)
+                else:
+                    for p in full_model.parameters():
+                        p.grad = None
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    self.rec, self.loss_r, self.loss_all = self._step()
+            self.graph, self._stream = _OwnedGraph(graph, store), side
+
+    def _step(self):
+        m = self.model
+        if self.optimizer is not None:
+            self.optimizer.zero_grad(set_to_none=True)
+        latent, mu, logvar = m.mode.get_latent(m, self.existing, self.missing, None)
+        weights = m.hyper_network(latent)
+        rec = target_network_forward(weights, self.points, self._loc, self._use_bias, False)
+        loss_r = torch.mean(self.loss_coef * self._loss_fn(self.gt, rec))   # ChamferLoss(preds, gts) is symmetric in its arguments
+        loss_all = loss_r
+        if self.generative:
+            kld = 0.5 * (torch.exp(logvar) + torch.square(mu) - 1 - logvar).sum()
+            loss_all = loss_r + torch.div(kld, self.existing.shape[0])
+        loss_all.backward()
+        if self.optimizer is not None:
+            self.optimizer.step()
+        return rec.detach(), loss_r.detach(), loss_all.detach()
+
+    def load_points(self, epoch: int):
+        """Draw this step's TargetNetwork input clouds on the host (global torch CPU RNG, the reference's order) and copy them
+        into the static ``points`` tensor (one pinned H2D copy, stream-ordered before the next replay)."""
+        from .target_network import generate_points
+
+        for j in range(self.points_host.size(0)):
+            self.points_host[j] = generate_points(self._pg_cfg, epoch, (self.points_host.size(1), 3))
+        self.points.copy_(self.points_host, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.rec, self.loss_r, self.loss_all
 
 
 class ChamferHostPipeline:

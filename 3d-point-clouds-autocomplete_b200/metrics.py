@@ -43,6 +43,30 @@ def _rank_world(group) -> Tuple[int, int]:
     return 0, 1
 
 
+def _host_staged(t: torch.Tensor, group) -> bool:
+    """gloo has no CUDA all_gather: with a gloo group (CPU test-suite, or several ranks sharing ONE GPU in
+    tests/test_metrics_multirank_gpu.py) the few-KB vectors are exchanged through host memory.  NCCL groups never stage."""
+    return t.is_cuda and dist.get_backend(group) == "gloo"
+
+
+def _all_gather(t: torch.Tensor, group) -> list:
+    world = dist.get_world_size(group)
+    src = t.cpu() if _host_staged(t, group) else t
+    out = [torch.empty_like(src) for _ in range(world)]
+    dist.all_gather(out, src.contiguous(), group=group)
+    return [o.to(t.device) for o in out] if src is not t else out
+
+
+def _all_reduce_min(t: torch.Tensor, group) -> torch.Tensor:
+    if _host_staged(t, group):
+        h = t.cpu()
+        dist.all_reduce(h, op=dist.ReduceOp.MIN, group=group)
+        t.copy_(h)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return t
+
+
 def shard_rows(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
     """Row block of `rank`: equal ceil-sized blocks (equal work: per-pair cost is data independent)."""
     per = (n_rows + world - 1) // world
@@ -56,9 +80,7 @@ def _all_gather_padded(t: torch.Tensor, per: int, total: int, fill, group) -> to
         return t[:total]
     pad = torch.full((per,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
     pad[: t.shape[0]] = t
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad, group=group)
-    return torch.cat(out, dim=0)[:total]
+    return torch.cat(_all_gather(pad, group), dim=0)[:total]
 
 
 def row_min_gathered(block: torch.Tensor, n_rows: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -86,11 +108,7 @@ def col_min_merged(block: torch.Tensor, row_begin: int, n_rows: int, group=None)
         idx = torch.full((ncols,), n_rows, dtype=torch.long, device=block.device)
     if world == 1:
         return val, idx
-    vals = [torch.empty_like(val) for _ in range(world)]
-    idxs = [torch.empty_like(idx) for _ in range(world)]
-    dist.all_gather(vals, val, group=group)
-    dist.all_gather(idxs, idx, group=group)
-    V, I = torch.stack(vals), torch.stack(idxs)  # [world, ncols]; rank order == ascending row order
+    V, I = torch.stack(_all_gather(val, group)), torch.stack(_all_gather(idx, group))  # [world, ncols]; rank order == ascending rows
     best = torch.min(V, dim=0)
     # lowest rank among equal minima == lowest global row index (row blocks are ordered by rank)
     first_rank = torch.argmax((V == best.values.unsqueeze(0)).to(torch.uint8), dim=0)
@@ -129,7 +147,7 @@ def nearest_other_from_pair_values(n: int, r: torch.Tensor, sidx: torch.Tensor, 
         out.scatter_reduce_(0, sidx.to(torch.int64), v, reduce="amin", include_self=True)
         out.scatter_reduce_(0, r.to(torch.int64), v, reduce="amin", include_self=True)
     if _rank_world(group)[1] > 1:
-        dist.all_reduce(out, op=dist.ReduceOp.MIN, group=group)
+        _all_reduce_min(out, group)
     return out
 
 

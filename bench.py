@@ -360,8 +360,8 @@ def run_ours(args):
     ring_ws = torch.zeros(native.load().hp_chamfer_workspace_bytes(B, N, M), dtype=torch.uint8, device=dev)
 
     def ring_only():
-        native.check(native.load().hp_measure_chamfer_ring_only(B, N, step.xyz1.data_ptr(), M, step.xyz2.data_ptr(), ring_ws.data_ptr(),
-                                                                ring_ws.numel(), stream.cuda_stream), "hp_measure_chamfer_ring_only")
+        native.check_bench(native.load_bench().hp_measure_chamfer_ring_only(B, N, step.xyz1.data_ptr(), M, step.xyz2.data_ptr(), ring_ws.data_ptr(),
+                                                                            ring_ws.numel(), stream.cuda_stream), "hp_measure_chamfer_ring_only")
 
     with ClockSampler(local_rank) as clocks:
         step_ms = _events_timed(torch, step.replay, args.steps, args.warmup, flush, stream, barrier)

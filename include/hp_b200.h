@@ -10,7 +10,8 @@
  *     returns without synchronising (fully stream-ordered, no legacy-stream memset --
  *     the reference's nndistancegrad() issues cudaMemset on the legacy stream,
  *     nndistance.cu:156-157; that hazard is not reproduced);
- *   - the library never allocates device memory: outputs and workspaces are caller-owned
+ *   - the library never allocates device memory (one documented exception: hp_nndistance, whose reference signature has no
+ *     workspace argument): outputs and workspaces are caller-owned
  *     (the reference's glue allocates outputs with torch::empty, structural_loss.cpp:32-33,
  *     49,64-65,90-93,111-112; our Python glue does the same);
  *   - return value: HP_OK (0) or an HP_ERR_* code; the reference's launchers return void and
@@ -62,15 +63,22 @@ HP_API const char *hp_last_error_message(void);
  *   result [b,n]  = min_k |xyz[b,j]-xyz2[b,k]|^2,  result_i = argmin (lowest index on ties)
  *   result2[b,m], result2_i: the reverse direction.
  * d = fma(dz,dz,fma(dx,dx,dy*dy)) in fp32, bit-identical to the reference build.
- * One launch covers both directions.  n==0 or m==0 with b>0 -> HP_ERR_INVALID_ARGUMENT
- * (the reference leaves the outputs uninitialised).  Inputs must be finite. */
+ * One launch sequence covers both directions.  n==0 or m==0 with b>0 -> HP_ERR_INVALID_ARGUMENT
+ * (the reference leaves the outputs uninitialised).
+ * Input domain (all nearest-neighbour entry points): coordinates must be finite with |x| < 1e15 -- the ring kernels pad
+ * partial tiles with points at +-1e18 and move running minima by one ulp for the tie rule; inf / NaN / larger magnitudes
+ * give undefined distances and indices (not validated on the device).
+ * The reference signature has no workspace argument: the call takes hp_chamfer_workspace_bytes() from the stream-ordered
+ * pool of the current device (cudaMallocAsync / cudaFreeAsync on `stream`: no synchronisation, capturable) and runs the
+ * same ring kernels as hp_nndistance_ws; it is the ONLY entry point of the library that allocates.  If the pool is
+ * unavailable the workspace-free ordered-pair kernel is used (same bits, about half the speed). */
 HP_API int hp_nndistance(int b, int n, const float *xyz, int m, const float *xyz2, float *result,
                   int *result_i, float *result2, int *result2_i, void *stream);
 
 /* hp_nndistance with a caller-provided workspace (hp_chamfer_workspace_bytes(b,n,m) bytes, 16-byte aligned,
  * zero-filled once when allocated; the kernels restore that state).  Runs the "warp ring" kernels, which
- * evaluate every UNORDERED point pair once for both directions (d is bit-symmetric) -- about twice as fast as
- * hp_nndistance, identical results.  Coordinates must be finite with |x| < 1e15. */
+ * evaluate every UNORDERED point pair once for both directions (d is bit-symmetric).  Identical results to hp_nndistance,
+ * without its pool allocation and memset.  Coordinates must be finite with |x| < 1e15. */
 HP_API int hp_nndistance_ws(int b, int n, const float *xyz, int m, const float *xyz2, float *result,
                      int *result_i, float *result2, int *result2_i, void *workspace, size_t workspace_bytes,
                      void *stream);
@@ -105,6 +113,13 @@ HP_API int hp_chamfer_backward(int b, int n, const float *xyz1, int m, const flo
                         const int *idx1, const int *idx2, const float *grad_loss,
                         float *grad_xyz1, float *grad_xyz2, void *stream);
 
+/* Replaces `ChamferLoss.batch_pairwise_dist(x, y)` (losses/champfer_loss.py:19-35), which callers such as
+ * `dist_chamfer` (utils/metrics.py:78-83) use to get the whole matrix:
+ *   P[b,i,j] = (|x_i|^2 + |y_j|^2) - 2 x_i.y_j   -- the reference's expansion form (may be slightly negative), fp32,
+ *   x [b,nx,3], y [b,ny,3], P [b,nx,ny] (4*b*nx*ny bytes, written once; the kernel is HBM-write bound).
+ * The reference builds it from three bmm and two discarded Gram matrices.  None of this library's hot paths needs P. */
+HP_API int hp_batch_pairwise_dist(int b, int nx, int ny, const float *x, const float *y, float *P, void *stream);
+
 /* Training-step pair: the forward additionally emits the INVERSE of both index maps (sorted in shared memory at the
  * tail of the forward's unpack kernel), so that the backward is a pure gather: one thread per point, no sort, no
  * atomics, same summation order (ascending source index) and bit-identical gradients to hp_chamfer_backward.
@@ -123,11 +138,13 @@ HP_API int hp_chamfer_backward_inv(int b, int n, const float *xyz1, int m, const
 /* One training step of the fused loss in TWO kernels: loss = ChamferLoss(xyz1, xyz2) (losses/champfer_loss.py:11-17)
  * and its gradients for the upstream scalar grad_loss[0] (device memory, known before the forward is enqueued -- e.g. the
  * trainer's constant loss coefficient, core/epoch_loops.py:25-26).  The ring kernel is followed by a single tail kernel
- * (launched programmatically dependent, so its prologue overlaps the ring kernel's tail) that decodes distances and
- * indices, reduces the loss in a fixed order, inverts both index maps in shared memory and gathers both gradients.
+ * (launched programmatically dependent; its CTAs wait for per-cloud tickets of the ring kernel instead of the whole grid, so
+ * the tails of the early clouds run under the ring kernel's last wave) that decodes distances and indices, reduces the loss
+ * in a fixed order, inverts both index maps in shared memory and gathers both gradients.
  * Outputs are bit-identical to hp_chamfer_forward_inv + hp_chamfer_backward_inv.  hp_chamfer_step_supported returns 0
- * when the clouds do not fit the tail kernel's shared memory (about 4000 points per cloud).  Workspace as for
- * hp_chamfer_forward. */
+ * for clouds above 4096 points (the tail kernel keeps a direction's keys in registers).  Workspace as for
+ * hp_chamfer_forward.  Both kernels must be enqueued by this call on one stream (the tail relies on the ring kernel's CTAs
+ * being resident or complete when it starts). */
 HP_API int hp_chamfer_step_supported(int b, int n, int m);
 HP_API int hp_chamfer_step(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_loss,
                     float *dist1, int *idx1, float *dist2, int *idx2, float *loss, float *grad_xyz1,
@@ -225,21 +242,6 @@ HP_API int hp_pairwise_cd(int na, int nb, int n, int m, const float *first, cons
  * strict upper triangle is evaluated and the pair list is what gets sharded across GPUs. */
 HP_API int hp_pairwise_cd_pairs(long long npairs, int n, int m, const float *first, const float *second,
                          const int *pair_r, const int *pair_s, float *cd, void *stream);
-
-/* ------------------------------------------------------------------------------------
- * Measurement helpers (used by bench.py for the roofline denominators; not on the path)
- * ---------------------------------------------------------------------------------- */
-/* Runs a register-resident FFMA (kind 0), packed FFMA2 (kind 1) or MUFU.EX2 (kind 2) chain, the Chamfer inner-loop
- * instruction mix (kinds 3-5), legacy mma.sync TF32 (kind 6), or a register-only replica of the ring kernel's rotation
- * (kinds 7-12: FMA-pipe ops only / + FMNMX3 / + FSETP,SEL bookkeeping / the latter with 3, 2, 1 warps per scheduler; see
- * csrc/api.cu and DESIGN.md 4.1) on every SM and returns the achieved rate in *rate (FLOP/s for kinds 0-1 and 3-6, ex2/s
- * for kind 2, packed instructions per lane per second for kinds 7-12), timed with CUDA events on `stream` (synchronises). */
-HP_API int hp_measure_peak(int kind, int iters, double *rate_host, void *stream);
-/* Launches ONLY the dominant kernel of the Chamfer step (nn_ring_kernel: all-pairs distances, both directions, keys into the
- * workspace) so that bench.py can time it alone with CUDA events.  The keys are left in `workspace` (zero-filled on entry,
- * hp_chamfer_workspace_bytes): use a private workspace and discard it afterwards. */
-HP_API int hp_measure_chamfer_ring_only(int b, int n, const float *xyz1, int m, const float *xyz2, void *workspace,
-                                 size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -59,7 +59,7 @@ v2, i2 = P.min(2)
 v1, i1 = P.min(1)
 loss = cl(b, a)
 loss.backward()
-out.update(uni_a=a.detach().numpy(), uni_b=b.detach().numpy(),
+out.update(uni_a=a.detach().numpy(), uni_b=b.detach().numpy(), uni_P=P.detach().numpy(),
            uni_dist_a=v2.detach().numpy(), uni_idx_a=i2.numpy().astype(np.int32),
            uni_dist_b=v1.detach().numpy(), uni_idx_b=i1.numpy().astype(np.int32),
            uni_loss=loss.detach().numpy(), uni_grad_a=a.grad.numpy().copy(), uni_grad_b=b.grad.numpy().copy())

@@ -8,8 +8,8 @@ import subprocess
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    text = open(os.path.join(REPO, "include", "hp_b200.h")).read()
+def _declared(header="hp_b200.h"):
+    text = open(os.path.join(REPO, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"HP_API[^;(]*?\b(hp_\w+)\s*\(", text)))
 
@@ -29,6 +29,21 @@ def test_library_exports_every_declared_symbol(hp):
 
 def test_ctypes_table_matches_header(hp):
     assert sorted(hp._native.SIGNATURES) == _declared()
+
+
+def test_product_library_holds_no_measurement_code(hp):
+    """hp_measure_* and the A/B environment switches live in libhp_b200_bench.so only (include/hp_b200_bench.h)."""
+    bench_only = _declared("hp_b200_bench.h")
+    assert bench_only == ["hp_measure_chamfer_ring_only", "hp_measure_peak", "hp_measure_set_trace"]
+    assert sorted(hp._native.BENCH_SIGNATURES) == bench_only
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", hp._native.LIB_PATH], text=True)
+    assert "hp_measure" not in syms
+    blob = open(hp._native.LIB_PATH, "rb").read()
+    for knob in (b"HP_RING_VARIANT", b"HP_NO_PDL", b"HP_NN_RING", b"HP_NN_VARIANT"):
+        assert knob not in blob, knob
+    bench = ctypes.CDLL(hp._native.BENCH_LIB_PATH)
+    for name in bench_only + _declared():
+        assert hasattr(bench, name), name
 
 
 def test_no_torch_or_python_in_the_abi(hp):

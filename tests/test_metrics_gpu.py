@@ -73,12 +73,17 @@ def test_pairwise_cd_vs_reference_expansion_form(hp, oracle):
     np.testing.assert_allclose(cd, ref, rtol=1e-5)
 
 
-def test_pairwise_emd_vs_match_cost(hp):
+def test_pairwise_emd_vs_oracle_and_reference_extension(hp, oracle, ref_ext):
+    """The match-free fused cost (hp_emd_cost_pairs, several batched calls) against the C oracle's approxmatch + matchcost and
+    against the reference's own extension composed like emd_approx (utils/metrics.py:71-76): ApproxMatch -> MatchCost -> / N."""
     a, b = _sets(3, 4, 256, 256, seed=6)
     ad, bd = a.to(DEV), b.to(DEV)
     emd = hp.pairwise_emd(ad, bd, max_pairs_per_call=5)  # forces several batched calls
+    np.testing.assert_allclose(emd.cpu().numpy(), oracle.pairwise_emd(a.numpy(), b.numpy()), rtol=1e-5)
     for r in range(3):
-        row = hp.match_cost(ad[r:r + 1].expand(4, -1, -1).contiguous(), bd) / 256.0
+        rep = ad[r:r + 1].expand(4, -1, -1).contiguous()
+        match, _temp = ref_ext.ApproxMatch(rep, bd)
+        row = ref_ext.MatchCost(rep, bd, match) / 256.0
         torch.testing.assert_close(emd[r], row, rtol=1e-5, atol=1e-8)
 
 
@@ -101,16 +106,21 @@ def test_compute_all_metrics_reference_keys_without_1nn(hp):
                                   "mmd(Fidelity)-EMD", "cov(Coverage)-EMD", "mmd_smp-EMD"])
 
 
-def test_dist_chamfer_and_emd_approx(hp):
+def test_dist_chamfer_and_emd_approx(hp, oracle, ref_ext):
+    """dist_chamfer against the reference's arithmetic (expansion-form matrix of champfer_loss.py:19-35, torch port pinned to the
+    reference by tests/test_oracle_golden.py, then P.min(1) / P.min(2) like utils/metrics.py:78-83); emd_approx against the
+    reference extension's ApproxMatch + MatchCost."""
     a, b = _sets(3, 3, 200, 150, seed=3)
     ad, bd = a.to(DEV), b.to(DEV)
     dl, dr = hp.metrics.dist_chamfer(ad, bd, hp.ChamferLoss())
-    P = hp.ChamferLoss().batch_pairwise_dist(ad, bd)
-    torch.testing.assert_close(dl, P.min(1)[0], rtol=0, atol=2e-6)
-    torch.testing.assert_close(dr, P.min(2)[0], rtol=0, atol=2e-6)
+    P = oracle.batch_pairwise_dist_torch(a, b)
+    torch.testing.assert_close(dl.cpu(), P.min(1)[0], rtol=0, atol=2e-6)
+    torch.testing.assert_close(dr.cpu(), P.min(2)[0], rtol=0, atol=2e-6)
     a2, b2 = _sets(2, 2, 128, 128, seed=4)
     e = hp.metrics.emd_approx(a2.to(DEV), b2.to(DEV))
-    torch.testing.assert_close(e, hp.match_cost(a2.to(DEV), b2.to(DEV)) / 128.0)
+    match, _temp = ref_ext.ApproxMatch(a2.to(DEV), b2.to(DEV))
+    torch.testing.assert_close(e, ref_ext.MatchCost(a2.to(DEV), b2.to(DEV), match) / 128.0, rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(e.cpu().numpy(), oracle.match_cost(a2.numpy(), b2.numpy()) / 128.0, rtol=1e-5)
 
 
 def test_jsd_vs_oracle_on_seeded_sets(hp, oracle):

@@ -1,0 +1,10 @@
+#!/usr/bin/env bash
+# usage: tools/gpurun_retry.sh <timeout_s> '<command>' [gpus]   -- retries while the pod answers busy (exit code 3), nothing charged
+T=$1; CMD=$2; G=${3:-1}
+for i in $(seq 1 20); do
+  if [ "$G" = "1" ]; then /usr/local/graft/bin/gpurun --timeout "$T" -- "$CMD"; else /usr/local/graft/bin/gpurun --gpus "$G" --timeout "$T" -- "$CMD"; fi
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 120
+done
+exit 3
