@@ -88,3 +88,67 @@ def completeness(query_points, ref_points, thres: float = 0.03, device=None) -> 
     q, r = _dev(query_points, device).unsqueeze(0), _dev(ref_points, device).unsqueeze(0)
     d1, _i1, _d2, _i2 = NNDistance(q, r)
     return float((d1.sqrt() < thres).float().mean().item())
+
+
+# --------------------------------------------------------------------------------------
+# evaluate_generativity (core/experiments.py:63-104): the generation loop, batched
+# --------------------------------------------------------------------------------------
+def generate_completions(full_model, existing: torch.Tensor, n_samples: int, epoch: int, device, mean: float = 0.0,
+                         std: float = 0.005, n_points: int = 2048, keep_lowest: int = 1024, max_batch: int = 256,
+                         return_uncut: bool = False):
+    """The inner loop of ``evaluate_generativity`` (core/experiments.py:79-91) for ONE partial shape ``existing`` [1, N, 3] (or
+    already transposed [1, 3, N]): ``n_samples`` completions from fresh noise, each cut to the ``keep_lowest`` points with the
+    smallest second coordinate (``pc.T[pc[1].argsort()[:1024]]``, :87) -> ``[n_samples, keep_lowest, 3]`` on ``device``.
+
+    The reference runs ``n_samples`` batch-1 forwards: per sample one CPU ``normal_`` draw of the noise, the encoder of the SAME
+    ``existing`` again, the hypernetwork, ~15 TargetNetwork launches, one H2D copy, one D2H copy and a numpy argsort.  Here the
+    host draws happen in the reference's order (noise_j, then the TargetNetwork input cloud of sample j: identical global-RNG
+    consumption), the encoder runs once, and hypernetwork + fused TargetNetwork + the cut run on the whole batch.
+    ``full_model`` is the reference's (or the drop-in) FullModel in eval mode; needs a generative mode (HyperPocket).
+    ``return_uncut=True`` additionally returns the full reconstructions [n_samples, n_points, 3] (before the cut)."""
+    from .target_network import generate_points, target_network_forward
+
+    device = torch.device(device)
+    if existing.size(-1) == 3:  # model/full_model.py:56-57 (the reference transposes its argument in place)
+        existing.transpose_(existing.dim() - 2, existing.dim() - 1)
+    noise_size = full_model.get_noise_size()
+    tcfg = full_model.target_network_config
+    loc, use_bias = list(tcfg["layer_out_channels"]), bool(tcfg["use_bias"])
+    noises = torch.empty(n_samples, noise_size)
+    points = torch.empty(n_samples, n_points, 3)
+    if device.type == "cuda":
+        noises, points = noises.pin_memory(), points.pin_memory()
+    for j in range(n_samples):  # host RNG in the reference's order: fixed_noise (:82), then generate_points (full_model.py:72)
+        noises[j] = torch.zeros(1, noise_size).normal_(mean=mean, std=std)[0]
+        points[j] = generate_points(full_model.point_generator_config, epoch, (n_points, 3))
+    out, full = [], []
+    with torch.no_grad():
+        real_mu = full_model.real_encoder(existing.to(device))           # HyperPocket.get_latent, eval branch (:108-113)
+        for j0 in range(0, n_samples, max_batch):
+            nz = noises[j0:j0 + max_batch].to(device, non_blocking=True)
+            latent = torch.cat([nz, real_mu.expand(nz.size(0), -1)], 1)
+            weights = full_model.hyper_network(latent)
+            rec = target_network_forward(weights, points[j0:j0 + max_batch].to(device, non_blocking=True), loc, use_bias, False)
+            order = torch.argsort(rec[:, :, 1], dim=1, stable=True)[:, :keep_lowest]     # [b, keep]: ascending second coordinate
+            out.append(torch.gather(rec, 1, order.unsqueeze(-1).expand(-1, -1, 3)))
+            if return_uncut:
+                full.append(rec)
+    if return_uncut:
+        return torch.cat(out).contiguous(), torch.cat(full).contiguous()
+    return torch.cat(out).contiguous()
+
+
+def evaluate_generativity_for_shape(full_model, existing: torch.Tensor, cat_gt: torch.Tensor, epoch: int, device, batch_size=None,
+                                    mean: float = 0.0, std: float = 0.005, group=None, with_jsd: bool = True) -> dict:
+    """One iteration of the outer loop of ``evaluate_generativity`` (core/experiments.py:76-99): ``len(cat_gt)`` completions of
+    ``existing`` against the ground-truth missing parts ``cat_gt`` [G, 1024, 3] -> the dict the reference accumulates per
+    category (compute_all_metrics keys as floats + 'jsd')."""
+    from .chamfer import ChamferLoss
+    from .metrics import compute_all_metrics, jsd_between_point_cloud_sets
+
+    cat_gt = cat_gt.to(device).contiguous()
+    recs = generate_completions(full_model, existing, cat_gt.size(0), epoch, device, mean, std, keep_lowest=cat_gt.size(1))
+    res = {k: float(v.item()) for k, v in compute_all_metrics(recs, cat_gt, batch_size, ChamferLoss(), group=group).items()}
+    if with_jsd:
+        res["jsd"] = float(jsd_between_point_cloud_sets(recs, cat_gt))
+    return res

@@ -95,6 +95,18 @@ class ChamferStepGraph:
                 self.h2d_bytes = (self.xyz1.numel() + self.xyz2.numel()) * 4
                 self.d2h_bytes = (self.xyz1.numel() + self.xyz2.numel()) * 4 + 4
 
+                def host_step_loss_only():
+                    # what a trainer's step moves: inputs in, the loss value out; the gradients stay on the device for the
+                    # TargetNetwork backward (core/epoch_loops.py:19-39 reads only .item() of the losses)
+                    self.xyz1.copy_(self.xyz1_host, non_blocking=True)
+                    self.xyz2.copy_(self.xyz2_host, non_blocking=True)
+                    loss, _d1, _i1, _d2, _i2, g1, g2 = chamfer_step(self.xyz1, self.xyz2, self._one)
+                    self.loss_host.copy_(loss, non_blocking=True)
+                    return loss, g1, g2
+
+                self.host_graph_loss, self._host_loss_outs, _ = _capture(host_step_loss_only, self.device)
+                self.d2h_bytes_loss_only = 4
+
     def replay(self):
         """Inputs: self.xyz1 / self.xyz2 (device).  Outputs refreshed in place: loss [1], dist*, idx*, grad_xyz*."""
         self.graph.replay()
@@ -111,6 +123,17 @@ class ChamferStepGraph:
             self.xyz2_host.copy_(xyz2_host)
         self.host_graph.replay()
         return self.loss_host, self.grad_xyz1_host, self.grad_xyz2_host
+
+    def run_from_host_loss_only(self):
+        """Pinned-host inputs (``xyz1_host`` / ``xyz2_host``) -> ``loss_host``; the gradients stay on the device
+        (``grad_outputs_on_device()``).  One graph: two H2D copies, ring kernel, tail kernel, one 4-byte D2H copy."""
+        if self.host_graph is None:
+            raise RuntimeError("construct ChamferStepGraph(with_host_io=True) to use run_from_host_loss_only")
+        self.host_graph_loss.replay()
+        return self.loss_host
+
+    def grad_outputs_on_device(self):
+        return self._host_loss_outs[1], self._host_loss_outs[2]
 
 
 class TargetNetworkStepGraph:
