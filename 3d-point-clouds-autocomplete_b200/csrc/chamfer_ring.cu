@@ -32,9 +32,11 @@
 namespace hp {
 
 constexpr int RF_RQ = 8, RF_RC = 4;
-constexpr int RF_WARPS = 4;
 constexpr int RF_WROWS = 32 * RF_RQ;            // 256 rows per warp
-constexpr int RF_ROWS = RF_WARPS * RF_WROWS;    // 1024 rows per CTA
+#ifndef HP_RING_WARPS
+#define HP_RING_WARPS 4
+#endif
+constexpr int RF_DEFAULT_WARPS = HP_RING_WARPS; // warps per CTA of the product build: a CTA owns RF_DEFAULT_WARPS x 256 rows
 constexpr int RF_COLS = 32 * RF_RC;             // 128 columns per round
 constexpr float RF_PAD_ROW = 1.0e18f;           // padding points: finite, farther than any real pair
 constexpr float RF_PAD_COL = -1.0e18f;
@@ -45,17 +47,19 @@ typedef unsigned long long u64;
 
 #ifdef HP_BENCH_BUILD
 // bench library only: per-CTA timeline (globaltimer) of the ring and tail kernels, see hp_measure_set_trace
-__device__ unsigned long long *g_trace = nullptr;
-__device__ __forceinline__ void trace_mark(size_t slot) {
-    if (g_trace != nullptr) {
+static unsigned long long *g_trace_host = nullptr;  // handed to the kernels through their argument struct
+__device__ __forceinline__ void trace_mark(unsigned long long *trace, size_t slot) {
+    if (trace != nullptr) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_trace[slot] = t;
+        trace[slot] = t;
     }
 }
-#define HP_TRACE(slot) do { if (threadIdx.x == 0) trace_mark(slot); } while (0)
+#define HP_TRACE(slot) do { if (threadIdx.x == 0) trace_mark(a.trace, slot); } while (0)
+#define HP_TRACE_T(thread, slot) do { if (threadIdx.x == (thread)) trace_mark(a.trace, slot); } while (0)
 #else
 #define HP_TRACE(slot) do { } while (0)
+#define HP_TRACE_T(thread, slot) do { } while (0)
 #endif
 
 struct RingNNArgs {
@@ -71,6 +75,9 @@ struct RingNNArgs {
     unsigned int *counters;    // [1] loss ticket; zero on entry, zero on exit
     unsigned int *ticket;      // [b] ring CTAs of the cloud that have merged their keys; zero on entry, zero on exit
     unsigned int *done;        // [b] tail CTAs of the cloud that have read the keys; zero on entry, zero on exit
+    unsigned long long *trace; // bench library only: per-CTA timeline (nullptr = off)
+    int stage_sources;         // tail kernel: 1 = the direction's source points are staged in shared memory, 0 = read through L1
+    int tickets;               // 1: ring CTAs bump the per-cloud ticket (tail CTAs wait per cloud); 0: the tail waits for the whole grid
     // optional inverse index maps for the atomic-free backward (nullptr: not produced).
     //   inv1 [b][n + 2m]: perm1[n] = row indices i sorted by (idx1[i], i); then begin1[m], end1[m]: bucket of column k
     //   inv2 [b][m + 2n]: perm2[m] = column indices k sorted by (idx2[k], k); then begin2[n], end2[n]: bucket of row i
@@ -78,6 +85,16 @@ struct RingNNArgs {
     int sort_n, sort_shift;    // power-of-two sort size and bit position of the key in the composite (key << shift | pos)
     int inv_fast;              // 1: counting sort with radix fallback in shared memory, 0: bitonic only
 };
+
+// Key merge: a REDUCTION (no return value -> SASS RED, fire and forget).  Written in PTX on purpose: with a fence later in the
+// kernel nvcc turns atomicMax() with an unused result into ATOM, and a warp cannot exit while an ATOM's return is outstanding --
+// every CTA then lingers for an L2 round trip at its end (measured: the ring kernel 48 -> 52 us).
+__device__ __forceinline__ void red_max_u64(u64 *addr, u64 v) {
+    asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u32(unsigned int *addr, unsigned int v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ float bump_up(float v) { return __int_as_float(__float_as_int(v) + 1); }
 __device__ __forceinline__ float bump_down(float v) { return __int_as_float(__float_as_int(v) - 1); }
@@ -108,8 +125,9 @@ __device__ __forceinline__ RFGroup rf_load_group(const float *cols_p, int g) {
 
 // DBG (bench library only, HP_BENCH_BUILD): timing experiments, bit 0 = two rotations instead of 32, bit 1 = no rescans,
 // bit 2 = no ticket arrival
-template <int MINB, int DBG = 0>
-__global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const RingNNArgs a) {
+template <int WARPS, int MINB, int DBG = 0>
+__global__ void __launch_bounds__(WARPS * 32, MINB) nn_ring_kernel(const RingNNArgs a) {
+    constexpr int RF_WARPS = WARPS, RF_ROWS = WARPS * RF_WROWS;  // a CTA owns WARPS x 256 rows (a.rowchunks is sized for it)
     __shared__ __align__(128) float rows_s[RF_ROWS * 3];
     __shared__ __align__(128) float cols_raw[RF_COLS * 3];
     __shared__ __align__(128) float cols_p[RF_COLS * 3];
@@ -180,12 +198,15 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
         if (cbase >= m) break;                           // uniform
         const int ncols = min(RF_COLS, m - cbase);
         // here: cols_raw holds this round's columns (all threads have waited + synchronised), previous round's state consumed
-        {   // permute column tid into the packed group layout; reset the merge keys and this warp's column state
-            const int g = tid >> 2, k = tid & 3;
-            float *dst = cols_p + g * 12 + ((k & 2) ? 6 : 0) + (k & 1);
-            dst[0] = cols_raw[tid * 3 + 0], dst[2] = cols_raw[tid * 3 + 1], dst[4] = cols_raw[tid * 3 + 2];
+        {   // permute the columns into the packed group layout; reset the merge keys and this warp's column state
 #pragma unroll
-            for (int w = 0; w < RF_WARPS; ++w) wcolkey[w][tid] = ~0ull;  // RF_COLS == blockDim.x; inactive warps stay at 'none'
+            for (int c = tid; c < RF_COLS; c += RF_WARPS * 32) {
+                const int g = c >> 2, k = c & 3;
+                float *dst = cols_p + g * 12 + ((k & 2) ? 6 : 0) + (k & 1);
+                dst[0] = cols_raw[c * 3 + 0], dst[2] = cols_raw[c * 3 + 1], dst[4] = cols_raw[c * 3 + 2];
+#pragma unroll
+                for (int w = 0; w < RF_WARPS; ++w) wcolkey[w][c] = ~0ull;  // inactive warps stay at 'none'
+            }
 #pragma unroll
             for (int i = 0; i < RF_RC; ++i) wmn[lane * RF_RC + i] = __int_as_float(0x7f800000), wrot[lane * RF_RC + i] = 0;
         }
@@ -264,7 +285,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
                 float sm = 0.f; int sr = 0;
 #pragma unroll
                 for (int j = 0; j < RF_RQ; ++j) sm += best[j], sr += rot[j];
-                atomicMax(a.rowkey + (size_t)cloud * n + row0 + lrow0, ((u64)__float_as_uint(sm) << 32) | (unsigned)sr);
+                red_max_u64(a.rowkey + (size_t)cloud * n + row0 + lrow0, ((u64)__float_as_uint(sm) << 32) | (unsigned)sr);
             } else {
             // ---- rows: exact value, then the lowest column index of the winning group with d == value ----
             // (branch-free: the 8 re-evaluations are independent so that their loads and FMA chains overlap)
@@ -287,7 +308,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
                 u64 *rk = a.rowkey + (size_t)cloud * n + row0 + lrow0;
 #pragma unroll
                 for (int j = 0; j < RF_RQ; ++j)
-                    if (j < nvalid) atomicMax(rk + j, rkey[j]);
+                    if (j < nvalid) red_max_u64(rk + j, rkey[j]);
             }
             // ---- columns: lane L finalises group L (padding columns included: their keys are never merged) ----
             {
@@ -327,11 +348,14 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
             }
         }  // warp_active
         __syncthreads();
-        if (tid < ncols) {
-            u64 key = wcolkey[0][tid];
 #pragma unroll
-            for (int w = 1; w < RF_WARPS; ++w) key = wcolkey[w][tid] < key ? wcolkey[w][tid] : key;
-            atomicMax(a.colkey + (size_t)cloud * m + cbase + tid, ~key);
+        for (int c = tid; c < RF_COLS; c += RF_WARPS * 32) {
+            if (c < ncols) {
+                u64 key = wcolkey[0][c];
+#pragma unroll
+                for (int w = 1; w < RF_WARPS; ++w) key = wcolkey[w][c] < key ? wcolkey[w][c] : key;
+                red_max_u64(a.colkey + (size_t)cloud * m + cbase + c, ~key);
+            }
         }
         if (more) {
             if (nb_bytes) {
@@ -343,11 +367,11 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MINB) nn_ring_kernel(const Ring
     }
     // this CTA's candidates are merged: one more arrival on the cloud's ticket (bar.sync orders every thread's key atomics
     // before thread 0's fence; the tail kernel's CTAs of this cloud acquire the ticket before they read the keys)
-    if (!(DBG & 4)) {  // (DBG 4: timing experiment without the arrival)
+    if (!(DBG & 4) && a.tickets) {  // (DBG 4: timing experiment without the arrival)
         __syncthreads();
         if (tid == 0) {
             __threadfence();
-            atomicAdd(a.ticket + cloud, 1u);
+            red_add_u32(a.ticket + cloud, 1u);
         }
     }
     HP_TRACE((size_t)blockIdx.x * 2 + 1);
@@ -592,12 +616,15 @@ __device__ __forceinline__ float rf_serial8(const float *w) {
     return s;
 }
 
-// Called by every thread of the last-arriving CTA (>= 256 threads).  chunks1 / chunks2 > 0: losspart holds chunk partials,
-// per cloud [chunks1 of direction 0 | chunks2 of direction 1]; chunks1 == 0: losspart holds one sum per (cloud, direction).
-__device__ __forceinline__ void rf_loss_total(const RingNNArgs &a, int chunks1, int chunks2, float *wp8, int tid) {
-    float acc = 0.f;
-    if (tid < 256) {
-        for (int pd = tid; pd < 2 * a.b; pd += 256) {
+// Called by ONE WARP of the last-arriving CTA; lane l plays threads l, l + 32, ..., l + 224 of the 256 of the definition above.
+// chunks1 / chunks2 > 0: losspart holds chunk partials, per cloud [chunks1 of direction 0 | chunks2 of direction 1];
+// chunks1 == 0: losspart holds one sum per (cloud, direction).
+__device__ __forceinline__ void rf_loss_total_warp(const RingNNArgs &a, int chunks1, int chunks2, int lane) {
+    float tot = 0.f;
+#pragma unroll 1
+    for (int vw = 0; vw < 8; ++vw) {  // "warp" vw of the definition
+        float acc = 0.f;
+        for (int pd = vw * 32 + lane; pd < 2 * a.b; pd += 256) {
             float p;
             if (chunks1 == 0) {
                 p = __ldcg(a.losspart + pd);
@@ -606,20 +633,25 @@ __device__ __forceinline__ void rf_loss_total(const RingNNArgs &a, int chunks1, 
                 float *q = a.losspart + (size_t)(pd >> 1) * (chunks1 + chunks2) + ((pd & 1) ? chunks1 : 0);
                 const int nch = (pd & 1) ? chunks2 : chunks1;
                 p = 0.f;
-                for (int r = 0; r < nch; ++r) {
-                    p += __ldcg(q + r);
-                    q[r] = 0.f;
+                for (int r0 = 0; r0 < nch; r0 += 8) {  // eight loads in flight, then the serial sum in chunk order
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = (r0 + i < nch) ? __ldcg(q + r0 + i) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (r0 + i < nch) {
+                            p += v[i];
+                            q[r0 + i] = 0.f;
+                        }
+                    }
                 }
             }
             acc += p;
         }
+        tot += warp_sum(acc);  // serial over the 8 "warps", each folded by the xor tree
     }
-    acc = warp_sum(acc);
-    __syncthreads();  // wp8 reusable
-    if (tid < 256 && (tid & 31) == 0) wp8[tid >> 5] = acc;
-    __syncthreads();
-    if (tid == 0) {
-        a.loss[0] = rf_serial8(wp8);
+    if (lane == 0) {
+        a.loss[0] = tot;
         a.counters[0] = 0u;
     }
 }
@@ -638,7 +670,7 @@ __global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const 
     u64 *src = (dir2 ? a.colkey : a.rowkey) + (size_t)cloud * cnt;
     float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
     int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
-    if (!dir2 && tid == 0) a.ticket[cloud] = 0u;  // the ring kernel's arrivals are not needed on this path
+    if (!dir2 && tid == 0 && a.tickets) a.ticket[cloud] = 0u;  // the ring kernel's arrivals are not needed on this path
     // Phase 1 only READS the keys: the device-scope fence of the loss ticket below then has no stores of this SM to
     // drain (a fence issued after the 3 stores per element costs ~10 us).  Phase 2 (unpack_store) writes the outputs.
     auto unpack_store = [&]() {
@@ -679,9 +711,9 @@ __global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const 
         flag = (atomicAdd(a.counters, 1u) == gridDim.x - 1);
     }
     __syncthreads();
-    if (flag) {  // block-uniform: last arriver
+    if (flag && tid < 32) {  // last arriver: one warp folds the (cloud, direction) sums
         __threadfence();
-        rf_loss_total(a, 0, 0, warp_part, tid);
+        rf_loss_total_warp(a, 0, 0, tid);
     }
     unpack_store();
 }
@@ -712,19 +744,21 @@ struct RingTailArgs {
     int chunks1, chunks2;    // 256-source loss chunks of direction 0 (ceil(n / 256)) and 1 (ceil(m / 256))
     unsigned int expected;   // ring CTAs per cloud
 };
-constexpr int TL_THREADS = 256, TL_SEC = 256, TL_WARPS = TL_THREADS / 32;
+constexpr int TL_THREADS = 256, TL_SEC = 256, TL_WARPS = TL_THREADS / 32;  // compute threads: thread = target of the section
+constexpr int TL_CTA_THREADS = TL_THREADS + 32;                            // + one service warp
 constexpr int TL_MAX_POINTS = 4096;  // keys of a direction live in registers: <= 16 per thread
 constexpr int GATHER_COOP_F = 32;    // == GATHER_COOP of nn_grad_gather_kernel (same summation tree)
+constexpr int TL_FAST = 8;           // buckets up to this size take the slot path (no ranking, no prefix sums)
 
 // dynamic shared memory of the tail kernel; 0 if the shape is not supported (caller takes the three-kernel path)
-static size_t rf_tail_smem_bytes(int n, int m) {
+static size_t rf_tail_smem_bytes(int n, int m, bool stage_sources = true) {
     const size_t big = (size_t)(n > m ? n : m);
     if (big > TL_MAX_POINTS) return 0;
     const size_t c32 = (big + 31) / 32;
     size_t bytes = c32 * TL_SEC * 2;               // table  u16 [chunk of 32 sources][target of the section]
     bytes += ((big * 2 + 15) & ~(size_t)15) * 2;   // info, pbuf  u16 [source]
-    bytes += (big * 12 + 15) & ~(size_t)15;        // source points
     bytes += TL_SEC * 12;                          // target points of the section
+    if (stage_sources) bytes += (big * 12 + 15) & ~(size_t)15;  // source points (last: absent in whole-grid mode)
     return bytes;
 }
 
@@ -734,17 +768,29 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     return v;
 }
 
+// named barriers of the tail kernel: 0 = whole CTA (compute warps + service warp), 1 = the 8 compute warps,
+// 2 = hand-over from the compute warps (arrive) to the service warp (sync)
+__device__ __forceinline__ void tl_compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tl_handover_arrive() { asm volatile("bar.arrive 2, 288;" ::: "memory"); }
+__device__ __forceinline__ void tl_handover_wait() { asm volatile("bar.sync 2, 288;" ::: "memory"); }
+
 template <int ROUNDS>  // ceil(cnt / 256) <= ROUNDS: the keys of the direction stay in registers between the phases
-__global__ void __launch_bounds__(TL_THREADS, 4) nn_ring_tail_kernel(const RingNNArgs a, const RingTailArgs f) {
+__global__ void __maxnreg__(56) nn_ring_tail_kernel(const RingNNArgs a, const RingTailArgs f) {
     extern __shared__ __align__(16) unsigned char tsm[];
     __shared__ float wp_s[ROUNDS][TL_WARPS];
     __shared__ int wscan_s[TL_WARPS];
     __shared__ int begin_s[TL_SEC];
     __shared__ int idxT_s[TL_SEC];
     __shared__ int flag_s[2];
+    __shared__ int fcnt_s[TL_SEC];                                   // fast path: sources per target ...
+    __shared__ __align__(16) unsigned short fslot_s[TL_SEC][TL_FAST];  // ... and the first TL_FAST of them, in arrival order
+    __shared__ int fover_s;                                          // some target of the section has more than TL_FAST sources
     __shared__ __align__(8) uint64_t mbar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool service = warp == TL_WARPS;  // warp 8: staging, tickets, loss fold -- everything that waits on global memory
     const int per_cloud = f.sec1 + f.sec2;
+    // cloud-major like the ring kernel: the tails of the early clouds (complete long before) run first and free their slots,
+    // the tails of the last clouds become resident while the ring kernel drains and wait for their tickets
     const int cloud = blockIdx.x / per_cloud, rr = blockIdx.x - cloud * per_cloud;
     const bool dir2 = rr >= f.sec1;
     const int sec = dir2 ? rr - f.sec1 : rr, nsec = dir2 ? f.sec2 : f.sec1;
@@ -759,197 +805,341 @@ __global__ void __launch_bounds__(TL_THREADS, 4) nn_ring_tail_kernel(const RingN
     off += ((size_t)big * 2 + 15) & ~(size_t)15;
     unsigned short *pbuf = reinterpret_cast<unsigned short *>(tsm + off);
     off += ((size_t)big * 2 + 15) & ~(size_t)15;
-    float *S_s = reinterpret_cast<float *>(tsm + off);
-    off += ((size_t)big * 12 + 15) & ~(size_t)15;
     float *T_s = reinterpret_cast<float *>(tsm + off);
+    off += TL_SEC * 12;
     const float *__restrict__ Tg = (dir2 ? a.set1 : a.set2) + ((size_t)cloud * ntgt + tbase) * 3;
     const float *__restrict__ Sg = (dir2 ? a.set2 : a.set1) + (size_t)cloud * cnt * 3;
-
-    // ---- prologue (independent of the ring kernel's results): points into shared memory, count table cleared ----
-    HP_TRACE((size_t)2 * a.b * a.rowchunks * a.colchunks + (size_t)blockIdx.x * 3);
-    if (tid == 0) mbar_init(&mbar, 1);
-    __syncthreads();
-    const uint32_t tb = rf_bulk_bytes(Tg, tcount), sb = rf_bulk_bytes(Sg, cnt);
-    if (tid == 0 && tb + sb) {
-        fence_proxy_async();
-        mbar_expect_tx(&mbar, tb + sb);
-        if (tb) bulk_g2s(T_s, Tg, tb, &mbar);
-        if (sb) bulk_g2s(S_s, Sg, sb, &mbar);
-    }
-    if (tb != (uint32_t)tcount * 12u) rf_stage_tail(T_s, Tg, tcount, tcount, 0.f, tb, tid, TL_THREADS);  // uniform; rare
-    if (sb != (uint32_t)cnt * 12u) rf_stage_tail(S_s, Sg, cnt, cnt, 0.f, sb, tid, TL_THREADS);
-    {
-        uint4 *t4 = reinterpret_cast<uint4 *>(table);
-        for (int i = tid; i < c32 * (TL_SEC * 2 / 16); i += TL_THREADS) t4[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    // ---- wait for this cloud's ring CTAs (all of them are resident or done when this grid is allowed to start) ----
-    if (tid == 0) {
-        while (ld_acquire_u32(a.ticket + cloud) < f.expected) __nanosleep(64);
-    }
-    HP_TRACE((size_t)2 * a.b * a.rowchunks * a.colchunks + (size_t)blockIdx.x * 3 + 1);
-    __syncthreads();
-
-    // ---- keys: own direction (distance + target of every source), other direction (the own-term index of my target) ----
+    float *S_stage = reinterpret_cast<float *>(tsm + off);                 // only carved out when a.stage_sources
+    const float *__restrict__ S_s = a.stage_sources ? S_stage : Sg;        // sources: shared memory, or global through L1
     u64 *src = (dir2 ? a.colkey : a.rowkey) + (size_t)cloud * cnt;
     u64 *oth = (dir2 ? a.rowkey : a.colkey) + (size_t)cloud * ntgt;
-    u64 key[ROUNDS];
-#pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int e = r * TL_THREADS + tid;
-        key[r] = e < cnt ? ~__ldcg(src + e) : 0ull;
-    }
-    if (tid < tcount) idxT_s[tid] = (int)(unsigned)((~__ldcg(oth + tbase + tid)) & 0xffffffffu);
-#pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int e = r * TL_THREADS + tid;
-        if (r * TL_THREADS < cnt) {  // block-uniform
-            const unsigned tl = (unsigned)(key[r] & 0xffffffffu) - (unsigned)tbase;
-            const bool insec = e < cnt && tl < (unsigned)tcount;
-            const unsigned peers = __match_any_sync(0xffffffffu, insec ? tl : 0xffffffffu);
-            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-            if (insec && rank == 0) table[(size_t)(r * TL_WARPS + warp) * TL_SEC + tl] = (unsigned short)__popc(peers);
-            if (e < cnt) info[e] = insec ? (unsigned short)(tl | (rank << 8)) : (unsigned short)0xffffu;
-            if (a.loss != nullptr && (r % nsec) == sec) {  // block-uniform: this section owns loss chunk r
-                const float v = warp_sum(e < cnt ? __uint_as_float((unsigned)(key[r] >> 32)) : 0.f);
-                if (lane == 0) wp_s[r][warp] = v;
-            }
-        }
-    }
-    __syncthreads();  // table, info, idxT, warp sums complete; every key of both arrays this CTA needs has been read
-    if (tid == 0) {
-        flag_s[0] = (atomicAdd(a.done + cloud, 1u) == (unsigned)per_cloud - 1);  // last reader of the cloud restores the keys
-        flag_s[1] = 0;
-        if (a.loss != nullptr) {
-            const int nch = dir2 ? f.chunks2 : f.chunks1;
-            float *lp = a.losspart + (size_t)cloud * (f.chunks1 + f.chunks2) + (dir2 ? f.chunks1 : 0);
-            for (int r = sec; r < nch; r += nsec) lp[r] = rf_serial8(wp_s[r]);
-            __threadfence();  // nothing else of this thread is in flight: cheap
-            flag_s[1] = (atomicAdd(a.counters, 1u) == gridDim.x - 1);
-        }
-    }
 
-    // ---- per target: prefix of its counts over the chunks (-> stable position of every source), bucket size ----
-    int size = 0;
-    {
-        unsigned short *col = table + tid;
-#pragma unroll 8
-        for (int c = 0; c < c32; ++c) {
-            const int v = col[(size_t)c * TL_SEC];
-            col[(size_t)c * TL_SEC] = (unsigned short)size;
-            size += v;
+    // ---- prologue (independent of the ring kernel's results): points into shared memory, count table cleared ----
+    const size_t tr0 = (size_t)2 * a.b * a.rowchunks * a.colchunks + (size_t)blockIdx.x * 10;  // bench build: 10 timeline slots per CTA
+    (void)tr0;
+    HP_TRACE(tr0);
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    const uint32_t tb = rf_bulk_bytes(Tg, tcount), sb = a.stage_sources ? rf_bulk_bytes(Sg, cnt) : 0u;
+    if (service) {
+        if (lane == 0 && tb + sb) {
+            fence_proxy_async();
+            mbar_expect_tx(&mbar, tb + sb);
+            if (tb) bulk_g2s(T_s, Tg, tb, &mbar);
+            if (sb) bulk_g2s(S_stage, Sg, sb, &mbar);
         }
-    }
-    int inc = size;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += u;
-    }
-    if (lane == 31) wscan_s[warp] = inc;
-    __syncthreads();  // warp totals (and the flags) visible
-    int begin = inc - size;
-#pragma unroll
-    for (int w = 0; w < TL_WARPS; ++w) begin += (w < warp) ? wscan_s[w] : 0;
-    begin_s[tid] = begin;
-    const bool fold_loss = flag_s[1] != 0, restore = flag_s[0] != 0;
-    if (fold_loss) {  // block-uniform: every tail CTA's partials are visible (their fence + ticket, ours below)
-        __threadfence();
-        rf_loss_total(a, f.chunks1, f.chunks2, wp_s[0], tid);
-    }
-    __syncthreads();  // begin_s, chunk prefixes complete
-#pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int e = r * TL_THREADS + tid;
-        if (e < cnt) {
-            const unsigned inf = info[e];
-            if (inf != 0xffffu) {
-                const unsigned tl = inf & 255u;
-                pbuf[begin_s[tl] + table[(size_t)(e >> 5) * TL_SEC + tl] + (inf >> 8)] = (unsigned short)e;
-            }
+        // ---- wait for this cloud's ring CTAs (all of them are resident or done when this grid is allowed to start) ----
+        if (f.expected == 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");  // whole-grid mode: the ring kernel's keys are complete and visible
+        } else if (lane == 0) {
+            while (ld_acquire_u32(a.ticket + cloud) < f.expected) __nanosleep(20);
         }
+        HP_TRACE_T(TL_THREADS, tr0 + 1);
+        __syncwarp();
+    } else {
+        if (tb != (uint32_t)tcount * 12u) rf_stage_tail(T_s, Tg, tcount, tcount, 0.f, tb, tid, TL_THREADS);  // uniform; rare
+        if (a.stage_sources && sb != (uint32_t)cnt * 12u) rf_stage_tail(S_stage, Sg, cnt, cnt, 0.f, sb, tid, TL_THREADS);
+        uint4 *t4 = reinterpret_cast<uint4 *>(table);
+        for (int i = tid; i < c32 * (TL_SEC * 2 / 16); i += TL_THREADS) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+        fcnt_s[tid] = 0;
+        if (tid == 0) fover_s = 0;
     }
-    if (tb + sb) mbar_wait(&mbar, 0);
-    __syncthreads();  // buckets complete, points visible
+    __syncthreads();  // ticket acquired (service warp), table cleared (compute warps)
 
-    // ---- gradient of my target: own term + its bucket in ascending source order ----
-    const float gs = __ldg(f.g) * 2.f;
-    {
-        const bool valid = tid < tcount;
-        float px = 0.f, py = 0.f, pz = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-        if (valid) {
-            px = T_s[3 * tid + 0], py = T_s[3 * tid + 1], pz = T_s[3 * tid + 2];
-            const int j = min(max(idxT_s[tid], 0), cnt - 1);
-            ax = gs * (px - S_s[3 * j + 0]);
-            ay = gs * (py - S_s[3 * j + 1]);
-            az = gs * (pz - S_s[3 * j + 2]);
-        }
-        const int pb = begin, pe = begin + size;
-        const bool bigb = valid && size > GATHER_COOP_F;
-        if (valid && !bigb) {
-            for (int p = pb; p < pe; ++p) {  // ascending source index: fixed summation order
-                const int e = pbuf[p];
-                ax += -(gs * (S_s[3 * e + 0] - px));
-                ay += -(gs * (S_s[3 * e + 1] - py));
-                az += -(gs * (S_s[3 * e + 2] - pz));
+    if (service) {
+        // ---- service warp: done ticket, loss partials + loss ticket, total fold -- off the compute warps' critical path ----
+        tl_handover_wait();  // the compute warps have read every key they need and written their loss warp sums
+        if (lane == 0) {
+            // both arrivals are issued before either result is looked at: the round trip of the first hides under the fence
+            const unsigned old_done = atomicAdd(a.done + cloud, 1u);  // last reader of the cloud restores the keys
+            unsigned old_cnt = 0xffffffffu;
+            if (a.loss != nullptr) {
+                const int nch = dir2 ? f.chunks2 : f.chunks1;
+                float *lp = a.losspart + (size_t)cloud * (f.chunks1 + f.chunks2) + (dir2 ? f.chunks1 : 0);
+                for (int r = sec; r < nch; r += nsec) lp[r] = rf_serial8(wp_s[r]);
+                __threadfence();
+                old_cnt = atomicAdd(a.counters, 1u);
             }
+            flag_s[0] = old_done == (unsigned)per_cloud - 1;
+            flag_s[1] = old_cnt == gridDim.x - 1;
         }
-        unsigned todo = __ballot_sync(0xffffffffu, bigb);
-        while (todo) {  // big buckets: the whole warp, lane-strided ascending + fixed shuffle tree
-            const int srcl = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int b0 = __shfl_sync(0xffffffffu, pb, srcl), b1 = __shfl_sync(0xffffffffu, pe, srcl);
-            const float qx = __shfl_sync(0xffffffffu, px, srcl), qy = __shfl_sync(0xffffffffu, py, srcl), qz = __shfl_sync(0xffffffffu, pz, srcl);
-            float sx = 0.f, sy = 0.f, sz = 0.f;
-            for (int p = b0 + lane; p < b1; p += 32) {
-                const int e = pbuf[p];
-                sx += -(gs * (S_s[3 * e + 0] - qx));
-                sy += -(gs * (S_s[3 * e + 1] - qy));
-                sz += -(gs * (S_s[3 * e + 2] - qz));
-            }
-            sx = warp_sum(sx), sy = warp_sum(sy), sz = warp_sum(sz);
-            if (lane == srcl) ax += sx, ay += sy, az += sz;
+        HP_TRACE_T(TL_THREADS, tr0 + 7);
+        __syncwarp();
+        if (flag_s[1]) {  // warp-uniform: every tail CTA's partials are visible (their fence + ticket, ours below)
+            __threadfence();
+            rf_loss_total_warp(a, f.chunks1, f.chunks2, lane);
         }
-        if (valid) {
-            float *G = (dir2 ? f.grad1 : f.grad2) + ((size_t)cloud * ntgt + tbase + tid) * 3;
-            G[0] = ax, G[1] = ay, G[2] = az;
-        }
-    }
-    // ---- distances / indices of the source chunks this section owns ----
-    {
-        float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
-        int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
+    } else {
+        // ---- keys: own direction (distance + target of every source), other direction (the own-term index of my target) ----
+        u64 key[ROUNDS];
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const int e = r * TL_THREADS + tid;
-            if ((r % nsec) == sec && e < cnt) {
-                dist[e] = __uint_as_float((unsigned)(key[r] >> 32));
-                idx[e] = (int)(unsigned)(key[r] & 0xffffffffu);
+            key[r] = e < cnt ? ~__ldcg(src + e) : 0ull;
+        }
+        const u64 okey = tid < tcount ? ~__ldcg(oth + tbase + tid) : 0ull;
+        if (a.loss != nullptr) {
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r) {
+                if (r * TL_THREADS < cnt && (r % nsec) == sec) {  // block-uniform: this section owns loss chunk r
+                    const int e = r * TL_THREADS + tid;
+                    const float v = warp_sum(e < cnt ? __uint_as_float((unsigned)(key[r] >> 32)) : 0.f);
+                    if (lane == 0) wp_s[r][warp] = v;
+                }
+            }
+        }
+        if (tid < tcount) idxT_s[tid] = (int)(unsigned)(okey & 0xffffffffu);
+        __threadfence_block();
+        HP_TRACE(tr0 + 2);
+        tl_handover_arrive();  // every key this CTA needs is in registers: the service warp may take the tickets (non-blocking for us)
+        const float gs = __ldg(f.g) * 2.f;
+        float *G = (dir2 ? f.grad1 : f.grad2) + ((size_t)cloud * ntgt + tbase + tid) * 3;
+        // ---- slot path: when no target of the section has more than TL_FAST sources (every benign assignment: trained networks,
+        //      uniform clouds), the buckets are filled by shared-memory atomics in arrival order and the target's thread orders its
+        //      (at most TL_FAST) entries itself -- same ascending summation order, hence the same bits, as the general path ----
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int e = r * TL_THREADS + tid;
+            const unsigned tl = (unsigned)(key[r] & 0xffffffffu) - (unsigned)tbase;
+            if (e < cnt && tl < (unsigned)tcount) {
+                const int pos = atomicAdd(&fcnt_s[tl], 1);
+                if (pos < TL_FAST) fslot_s[tl][pos] = (unsigned short)e;
+                else fover_s = 1;
+            }
+        }
+        if (tb + sb) mbar_wait(&mbar, 0);
+        tl_compute_sync();  // slots complete, points visible
+        if (!fover_s) {     // block-uniform
+            if (tid < tcount) {
+                const float px = T_s[3 * tid + 0], py = T_s[3 * tid + 1], pz = T_s[3 * tid + 2];
+                const int j = min(max(idxT_s[tid], 0), cnt - 1);
+                float ax = gs * (px - S_s[3 * j + 0]), ay = gs * (py - S_s[3 * j + 1]), az = gs * (pz - S_s[3 * j + 2]);
+                const int sz = fcnt_s[tid];
+                const uint4 sl = *reinterpret_cast<const uint4 *>(fslot_s[tid]);  // 8 x u16
+                int es[TL_FAST] = {(int)(sl.x & 0xffffu), (int)(sl.x >> 16), (int)(sl.y & 0xffffu), (int)(sl.y >> 16),
+                                   (int)(sl.z & 0xffffu), (int)(sl.z >> 16), (int)(sl.w & 0xffffu), (int)(sl.w >> 16)};
+#pragma unroll
+                for (int q = 0; q < TL_FAST; ++q) es[q] = q < sz ? es[q] : 0x7fffffff;
+                // Batcher's odd-even merge sort for 8 keys (19 compare-exchanges): ascending source order
+#define HP_CE(i, j) { const int lo_ = min(es[i], es[j]); es[j] = max(es[i], es[j]); es[i] = lo_; }
+                HP_CE(0, 1) HP_CE(2, 3) HP_CE(4, 5) HP_CE(6, 7)
+                HP_CE(0, 2) HP_CE(1, 3) HP_CE(4, 6) HP_CE(5, 7)
+                HP_CE(1, 2) HP_CE(5, 6)
+                HP_CE(0, 4) HP_CE(1, 5) HP_CE(2, 6) HP_CE(3, 7)
+                HP_CE(2, 4) HP_CE(3, 5)
+                HP_CE(1, 2) HP_CE(3, 4) HP_CE(5, 6)
+#undef HP_CE
+#pragma unroll
+                for (int q = 0; q < TL_FAST; ++q) {
+                    if (q < sz) {
+                        const int e = es[q];
+                        ax += -(gs * (S_s[3 * e + 0] - px));
+                        ay += -(gs * (S_s[3 * e + 1] - py));
+                        az += -(gs * (S_s[3 * e + 2] - pz));
+                    }
+                }
+                G[0] = ax, G[1] = ay, G[2] = az;
+            }
+        } else {
+        // ---- general path: stable counting sort by ranking + chunk prefix sums (data-independent cost, any skew) ----
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int e = r * TL_THREADS + tid;
+            if (r * TL_THREADS < cnt) {  // block-uniform
+                const unsigned tl = (unsigned)(key[r] & 0xffffffffu) - (unsigned)tbase;
+                const bool insec = e < cnt && tl < (unsigned)tcount;
+                const unsigned peers = __match_any_sync(0xffffffffu, insec ? tl : 0xffffffffu);
+                const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+                if (insec && rank == 0) table[(size_t)(r * TL_WARPS + warp) * TL_SEC + tl] = (unsigned short)__popc(peers);
+                if (e < cnt) info[e] = insec ? (unsigned short)(tl | (rank << 8)) : (unsigned short)0xffffu;
+            }
+        }
+        tl_compute_sync();     // table, info, idxT complete
+        HP_TRACE(tr0 + 3);
+
+        // ---- per target: prefix of its counts over the chunks (-> stable position of every source), bucket size ----
+        int size = 0;
+        {
+            unsigned short *col = table + tid;
+#pragma unroll 8
+            for (int c = 0; c < c32; ++c) {
+                const int v = col[(size_t)c * TL_SEC];
+                col[(size_t)c * TL_SEC] = (unsigned short)size;
+                size += v;
+            }
+        }
+        int inc = size;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) wscan_s[warp] = inc;
+        tl_compute_sync();  // warp totals visible
+        int begin = inc - size;
+#pragma unroll
+        for (int w = 0; w < TL_WARPS; ++w) begin += (w < warp) ? wscan_s[w] : 0;
+        begin_s[tid] = begin;
+        tl_compute_sync();  // begin_s, chunk prefixes complete
+        HP_TRACE(tr0 + 4);
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int e = r * TL_THREADS + tid;
+            if (e < cnt) {
+                const unsigned inf = info[e];
+                if (inf != 0xffffu) {
+                    const unsigned tl = inf & 255u;
+                    pbuf[begin_s[tl] + table[(size_t)(e >> 5) * TL_SEC + tl] + (inf >> 8)] = (unsigned short)e;
+                }
+            }
+        }
+        tl_compute_sync();  // buckets complete
+        HP_TRACE(tr0 + 5);
+
+        // ---- gradient of my target: own term + its bucket in ascending source order ----
+        {
+            const bool valid = tid < tcount;
+            float px = 0.f, py = 0.f, pz = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+            if (valid) {
+                px = T_s[3 * tid + 0], py = T_s[3 * tid + 1], pz = T_s[3 * tid + 2];
+                const int j = min(max(idxT_s[tid], 0), cnt - 1);
+                ax = gs * (px - S_s[3 * j + 0]);
+                ay = gs * (py - S_s[3 * j + 1]);
+                az = gs * (pz - S_s[3 * j + 2]);
+            }
+            const int pb = begin, pe = begin + size;
+            const bool bigb = valid && size > GATHER_COOP_F;
+            if (valid && !bigb) {
+                for (int p = pb; p < pe; ++p) {  // ascending source index: fixed summation order
+                    const int e = pbuf[p];
+                    ax += -(gs * (S_s[3 * e + 0] - px));
+                    ay += -(gs * (S_s[3 * e + 1] - py));
+                    az += -(gs * (S_s[3 * e + 2] - pz));
+                }
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, bigb);
+            while (todo) {  // big buckets: the whole warp, lane-strided ascending + fixed shuffle tree
+                const int srcl = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int b0 = __shfl_sync(0xffffffffu, pb, srcl), b1 = __shfl_sync(0xffffffffu, pe, srcl);
+                const float qx = __shfl_sync(0xffffffffu, px, srcl), qy = __shfl_sync(0xffffffffu, py, srcl), qz = __shfl_sync(0xffffffffu, pz, srcl);
+                float sx = 0.f, sy = 0.f, sz = 0.f;
+                for (int p = b0 + lane; p < b1; p += 32) {
+                    const int e = pbuf[p];
+                    sx += -(gs * (S_s[3 * e + 0] - qx));
+                    sy += -(gs * (S_s[3 * e + 1] - qy));
+                    sz += -(gs * (S_s[3 * e + 2] - qz));
+                }
+                sx = warp_sum(sx), sy = warp_sum(sy), sz = warp_sum(sz);
+                if (lane == srcl) ax += sx, ay += sy, az += sz;
+            }
+            if (valid) G[0] = ax, G[1] = ay, G[2] = az;
+        }
+        }  // general path
+        // ---- distances / indices of the source chunks this section owns ----
+        {
+            float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
+            int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r) {
+                const int e = r * TL_THREADS + tid;
+                if ((r % nsec) == sec && e < cnt) {
+                    dist[e] = __uint_as_float((unsigned)(key[r] >> 32));
+                    idx[e] = (int)(unsigned)(key[r] & 0xffffffffu);
+                }
             }
         }
     }
-    if (restore) {  // block-uniform: every tail CTA of the cloud has read the keys -> zero state for the next launch
-        ulonglong2 *z1 = reinterpret_cast<ulonglong2 *>(src), *z2 = reinterpret_cast<ulonglong2 *>(oth);  // 16-byte aligned iff even counts
+    HP_TRACE(tr0 + 6);
+    __syncthreads();  // flags of the service warp visible to everybody
+    if (flag_s[0]) {  // block-uniform: every tail CTA of the cloud has read the keys -> zero state for the next launch
         if (((cnt | ntgt) & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(oth)) & 15) == 0) {
-            for (int i = tid; i < cnt / 2; i += TL_THREADS) z1[i] = make_ulonglong2(0ull, 0ull);
-            for (int i = tid; i < ntgt / 2; i += TL_THREADS) z2[i] = make_ulonglong2(0ull, 0ull);
+            ulonglong2 *z1 = reinterpret_cast<ulonglong2 *>(src), *z2 = reinterpret_cast<ulonglong2 *>(oth);
+            for (int i = tid; i < cnt / 2; i += TL_CTA_THREADS) z1[i] = make_ulonglong2(0ull, 0ull);
+            for (int i = tid; i < ntgt / 2; i += TL_CTA_THREADS) z2[i] = make_ulonglong2(0ull, 0ull);
         } else {
-            for (int i = tid; i < cnt; i += TL_THREADS) src[i] = 0ull;
-            for (int i = tid; i < ntgt; i += TL_THREADS) oth[i] = 0ull;
+            for (int i = tid; i < cnt; i += TL_CTA_THREADS) src[i] = 0ull;
+            for (int i = tid; i < ntgt; i += TL_CTA_THREADS) oth[i] = 0ull;
         }
         if (tid == 0) a.ticket[cloud] = 0u, a.done[cloud] = 0u;
     }
-    HP_TRACE((size_t)2 * a.b * a.rowchunks * a.colchunks + (size_t)blockIdx.x * 3 + 2);
-    if (fold_loss) asm volatile("griddepcontrol.wait;" ::: "memory");  // the tail grid does not complete before the ring grid
+    HP_TRACE(tr0 + 8);
+    if (flag_s[1]) asm volatile("griddepcontrol.wait;" ::: "memory");  // the tail grid does not complete before the ring grid
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
 // rounds per CTA: 1 unless the grid is many waves deep (then the row staging is amortised over more columns)
-static int rf_rounds_per_cta(int b, int n, int m) {
-    const long long rowchunks = (n + RF_ROWS - 1) / RF_ROWS, rounds = (m + RF_COLS - 1) / RF_COLS;
-    const long long want = (long long)sm_count() * 64;
+static int rf_rounds_per_cta(int b, int n, int m, int rows_per_cta) {
+    const long long rowchunks = (n + rows_per_cta - 1) / rows_per_cta, rounds = (m + RF_COLS - 1) / RF_COLS;
+    const long long want = (long long)sm_count() * 64 * (1024 / rows_per_cta);
     int R = 1;
     while (R < 8 && (long long)b * rowchunks * ((rounds + 2 * R - 1) / (2 * R)) >= want) R *= 2;
     return R;
+}
+
+// The ring kernel and the tail kernel share SMs while the tail runs under the ring kernel's last wave.  An SM cannot change
+// its L1 / shared-memory split while CTAs are resident, so both kernels ask for the SAME (maximum shared memory) carve-out;
+// otherwise a tail CTA can only start on an SM that has drained completely (measured: tails started 15 us late).
+struct CarveCache {
+    bool done[64] = {false};
+};
+template <typename K>
+static cudaError_t ensure_max_carveout(K kern, CarveCache &cache) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && cache.done[dev]) return cudaSuccess;
+#ifdef HP_BENCH_BUILD
+    {
+        const char *env = getenv("HP_NO_CARVEOUT");  // A/B: leave the driver's default L1 / shared-memory split
+        if (env && atoi(env)) return cudaSuccess;
+    }
+#endif
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) cache.done[dev] = true;
+    return e;
+}
+
+template <int WARPS, int MINB, int DBG = 0>
+static int ring_launch(const RingNNArgs &a, long long grid, cudaStream_t stream) {
+    static CarveCache carve;
+    HP_CUDA(ensure_max_carveout(nn_ring_kernel<WARPS, MINB, DBG>, carve));
+    nn_ring_kernel<WARPS, MINB, DBG><<<(unsigned)grid, WARPS * 32, 0, stream>>>(a);
+    return HP_OK;
+}
+
+// Per-cloud tickets (tails of early clouds run under the ring kernel's last wave, at the price of a fence at the end of every
+// ring CTA) or whole-grid wait (no fence; every tail starts when the ring grid has completed).  The bench library can switch
+// with HP_TAIL_TICKETS=0|1; the product build uses the constant.
+#ifndef HP_TAIL_TICKETS_DEFAULT
+#define HP_TAIL_TICKETS_DEFAULT 1
+#endif
+static int tail_tickets() {
+#ifdef HP_BENCH_BUILD
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HP_TAIL_TICKETS");
+        v = e ? (atoi(e) != 0) : HP_TAIL_TICKETS_DEFAULT;
+    }
+    return v;
+#else
+    return HP_TAIL_TICKETS_DEFAULT;
+#endif
+}
+
+// warps (x 256 rows) per ring CTA: the product build's constant; the bench library can override it with HP_RING_WARPS=1|2|4
+static int ring_warps() {
+#ifdef HP_BENCH_BUILD
+    static int w = -1;
+    if (w < 0) {
+        const char *e = getenv("HP_RING_WARPS");
+        w = e ? atoi(e) : RF_DEFAULT_WARPS;
+        if (w != 1 && w != 2 && w != 4) w = RF_DEFAULT_WARPS;
+    }
+    return w;
+#else
+    return RF_DEFAULT_WARPS;
+#endif
 }
 
 struct RFLayout {
@@ -1004,8 +1194,7 @@ int nn_ring_forward_launch(int b, int n, const float *xyz1, int m, const float *
 
 #ifdef HP_BENCH_BUILD
 int nn_ring_set_trace(void *dev_ptr) {
-    unsigned long long *p = reinterpret_cast<unsigned long long *>(dev_ptr);
-    HP_CUDA(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
+    g_trace_host = reinterpret_cast<unsigned long long *>(dev_ptr);
     return HP_OK;
 }
 // bench library only (roofline of the dominant kernel): the ring kernel alone; leaves keys and tickets in the workspace
@@ -1029,8 +1218,19 @@ static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const flo
     const RFLayout L = rf_layout(b, n, m);
     unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
     a.set1 = xyz1, a.set2 = xyz2, a.b = b, a.n = n, a.m = m;
-    a.R = rf_rounds_per_cta(b, n, m);
-    a.rowchunks = (n + RF_ROWS - 1) / RF_ROWS;
+    const int warps = ring_warps(), rows_per_cta = warps * RF_WROWS;
+    a.tickets = (mode == RING_STEP && tail_tickets()) ? 1 : 0;
+#ifdef HP_BENCH_BUILD
+    a.trace = g_trace_host;
+    {
+        const char *env = getenv("HP_RING_ONLY_TICKETS");  // A/B: what the ticket arrival costs the ring kernel alone
+        if (mode == RING_ONLY && env && atoi(env)) a.tickets = 1;
+    }
+#endif
+    // whole-grid mode: every tail CTA should be resident when the ring grid completes -> four per SM: sources through L1
+    a.stage_sources = a.tickets ? 1 : 0;
+    a.R = rf_rounds_per_cta(b, n, m, rows_per_cta);
+    a.rowchunks = (n + rows_per_cta - 1) / rows_per_cta;
     a.colchunks = ((m + RF_COLS - 1) / RF_COLS + a.R - 1) / a.R;
     a.counters = reinterpret_cast<unsigned int *>(ws + L.off_counters);
     a.ticket = reinterpret_cast<unsigned int *>(ws + L.off_ticket);
@@ -1042,40 +1242,50 @@ static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const flo
     const long long grid = (long long)b * a.rowchunks * a.colchunks;
     const long long ugrid = (long long)2 * b;
     HP_REQUIRE(grid <= 0x7fffffffLL && ugrid <= 0x7fffffffLL, "nn ring forward: grid too large (%lld CTAs)", grid);
+    int rc_launch = HP_OK;
 #ifdef HP_BENCH_BUILD
     static int variant = -1;
     if (variant < 0) {
         const char *e = getenv("HP_RING_VARIANT");
         variant = e ? atoi(e) : 0;
     }
-    if (variant == 1) nn_ring_kernel<5><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
-    else if (variant == 2) nn_ring_kernel<6><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
-    else if (variant == 3) nn_ring_kernel<3><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
-    else if (variant == 10) nn_ring_kernel<4, 1><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
-    else if (variant == 11) nn_ring_kernel<4, 2><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
-    else if (variant == 12) nn_ring_kernel<4, 3><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
-    else if (variant == 20) nn_ring_kernel<4, 4><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    if (variant == 1) rc_launch = ring_launch<4, 5>(a, grid, stream);
+    else if (variant == 2) rc_launch = ring_launch<4, 6>(a, grid, stream);
+    else if (variant == 3) rc_launch = ring_launch<4, 3>(a, grid, stream);
+    else if (variant == 10) rc_launch = ring_launch<4, 4, 1>(a, grid, stream);
+    else if (variant == 11) rc_launch = ring_launch<4, 4, 2>(a, grid, stream);
+    else if (variant == 12) rc_launch = ring_launch<4, 4, 3>(a, grid, stream);
+    else if (variant == 20 && mode == RING_ONLY) rc_launch = ring_launch<4, 4, 4>(a, grid, stream);  // no tickets: never with a tail
     else
 #endif
-        nn_ring_kernel<4><<<(unsigned)grid, RF_WARPS * 32, 0, stream>>>(a);
+    if (warps == 1) rc_launch = ring_launch<1, 16>(a, grid, stream);
+    else if (warps == 2) rc_launch = ring_launch<2, 8>(a, grid, stream);
+    else rc_launch = ring_launch<4, 4>(a, grid, stream);
+    if (rc_launch != HP_OK) return rc_launch;
     HP_LAUNCH_CHECK("nn_ring_kernel");
     if (mode == RING_ONLY) return HP_OK;  // measurement helper: keys and tickets stay in the workspace
     if (mode == RING_STEP) {
-        const size_t smem = rf_tail_smem_bytes(n, m);
+        const size_t smem = rf_tail_smem_bytes(n, m, a.stage_sources != 0);
         HP_REQUIRE(smem != 0 && loss != nullptr, "nn ring step: clouds too large for the fused tail (n=%d m=%d) or no loss output", n, m);
         RingTailArgs f;
         f.g = step_g, f.grad1 = step_grad1, f.grad2 = step_grad2;
         f.sec1 = (m + TL_SEC - 1) / TL_SEC, f.sec2 = (n + TL_SEC - 1) / TL_SEC;
         f.chunks1 = L.chunks1, f.chunks2 = L.chunks2;
-        f.expected = (unsigned)(a.rowchunks * a.colchunks);
+        f.expected = a.tickets ? (unsigned)(a.rowchunks * a.colchunks) : 0u;
         const long long tgrid = (long long)b * (f.sec1 + f.sec2);
         HP_REQUIRE(tgrid <= 0x7fffffffLL, "nn ring step: grid too large (%lld CTAs)", tgrid);
         const bool small = (n > m ? n : m) <= 8 * TL_THREADS;
         static SmemAttrCache attr8, attr16;
-        if (small) HP_CUDA(ensure_dynamic_smem(nn_ring_tail_kernel<8>, smem, attr8));
-        else HP_CUDA(ensure_dynamic_smem(nn_ring_tail_kernel<16>, smem, attr16));
+        static CarveCache carve8, carve16;
+        if (small) {
+            HP_CUDA(ensure_dynamic_smem(nn_ring_tail_kernel<8>, smem, attr8));
+            HP_CUDA(ensure_max_carveout(nn_ring_tail_kernel<8>, carve8));
+        } else {
+            HP_CUDA(ensure_dynamic_smem(nn_ring_tail_kernel<16>, smem, attr16));
+            HP_CUDA(ensure_max_carveout(nn_ring_tail_kernel<16>, carve16));
+        }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)tgrid), cfg.blockDim = dim3(TL_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+        cfg.gridDim = dim3((unsigned)tgrid), cfg.blockDim = dim3(TL_CTA_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
         cudaLaunchAttribute attrs[1];
         attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attrs[0].val.programmaticStreamSerializationAllowed = 1;

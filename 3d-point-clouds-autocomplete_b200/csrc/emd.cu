@@ -18,6 +18,14 @@
 // distance and the two exponent scalings run as FADD2/FMUL2/FFMA2, the exponential on MUFU.EX2.
 // Bound: MUFU (16 ex2/clk/SM) and the FP32 pipe are within ~10% of each other for this mix.
 //
+// Match-free metrics path (hp_emd_cost_pairs): P3 of level j and P1 of level j-1 sweep the same (row, column) pairs and P1's
+// sum needs nothing of P3 but the row scalar remainL[k], so they run as ONE sweep (emd_fused31_kernel): one distance evaluation
+// and ONE ex2 for both -- the next level's e' = ex2(d * scale') is evaluated and the current level's e = e'^4 follows by two
+// multiplies (level' = level / 4).  Per level: MUFU work 3 ops per pair (ex2 in P2, ex2 + sqrt in the fused sweep) instead of 4,
+// 19 launches per auction instead of 27.  e'^4 deviates from ex2.approx(d * scale) by <= ~1.2e-6 relative (four times the
+// 2^-22 bound of ex2.approx plus two roundings); the cost stays within 1e-5 of the reference extension (tests).  The API path
+// (hp_approxmatch*, which returns `match`) keeps the reference's exact arithmetic below.
+//
 // Numerics kept from the reference build (verified in its sm_100 SASS):
 //   d = fma(dz,dz,fma(dx,dx,dy*dy));  arg = (d * level) * 1.4426950216f;  e = ex2.approx(arg)
 //   P1/P2: acc = fma(e, w, acc) in ascending column order;  P3: t = ratioL*e; acc = fma(t, ratioR, acc),
@@ -35,6 +43,7 @@ struct EmdArgs {
     const int *ia, *ib;           // per-pair cloud index into first / second (nullptr = pair index)
     float *state;                 // [pairs][2(n+m)] = remainL[n] remainR[m] ratioL[n] ratioR[m]
     float *partial;               // [pairs][S][rstride] row partial sums (column-split mode) or nullptr
+    float *partial2;              // the same for the second sum of the fused P3 + P1 sweep
     float *match;                 // [pairs][m][n] or nullptr
     float *costpart;              // [pairs][cp_stride] per-CTA cost partials or nullptr
     float *hist;                  // [pairs][9][n+m] per-level ratioL[n] ratioR[m] (match written once at the end) or nullptr
@@ -205,6 +214,128 @@ __global__ void __launch_bounds__(THREADS) emd_pass_kernel(const EmdArgs a) {
             for (int i = 0; i < THREADS / 32; ++i) t += warp_part[i];
             a.costpart[(size_t)pair * a.cp_stride + ((size_t)a.level_index * a.row_tiles + rt) * a.S + s] = t;
         }
+    }
+}
+
+// Fused sweep of the match-free path: P3 of level `a.j` (weights ratioR, row scalar ratioL, cost) and P1 of level `a.j - 1`
+// (weights remainR) over rows = xyz1, columns = xyz2.  Epilogue per row k (non-split): remainL[k] = max(0, remainL[k] - acc3),
+// then ratioL[k] = remainL[k] / acc1 with acc1 started at 1e-9 (approxmatch.cu:68,92,193).
+template <int RQ, int THREADS, bool SPLIT>
+__global__ void __launch_bounds__(THREADS) emd_fused31_kernel(const EmdArgs a) {
+    __shared__ __align__(16) float xs[EMD_CC], ys[EMD_CC], zs[EMD_CC], w3s[EMD_CC], w1s[EMD_CC];
+    __shared__ float warp_part[THREADS / 32];
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int s = bid % a.S;
+    bid /= a.S;
+    const int rt = bid % a.row_tiles;
+    const int pair = bid / a.row_tiles;
+    const int n = a.n, m = a.m;
+    const size_t c1 = a.ia ? (size_t)a.ia[pair] : (size_t)pair, c2 = a.ib ? (size_t)a.ib[pair] : (size_t)pair;
+    const float *__restrict__ R = a.first + c1 * n * 3;
+    const float *__restrict__ C = a.second + c2 * m * 3;
+    float *st = a.state + (size_t)pair * 2 * (n + m);
+    const float *remainR = st + n, *ratioR = st + n + m + n;
+    const float level_next = -powf(4.0f, (float)(a.j - 1));  // approxmatch.cu:56, on the device like the reference
+    const float scale = level_next * 1.4426950216293334961f;  // exact: the level is a power of two (see emd_pass_kernel)
+    const f32x2 scale2 = pack2(scale, scale);
+
+    f32x2 qx[RQ], qy[RQ], qz[RQ];
+    float acc3[RQ], acc1[RQ], rl[RQ], cost[RQ];
+    int row[RQ];
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+        row[q] = rt * (THREADS * RQ) + q * THREADS + tid;
+        float x = 0.f, y = 0.f, z = 0.f;
+        rl[q] = 0.f;
+        if (row[q] < n) {
+            x = __ldg(R + (size_t)row[q] * 3 + 0), y = __ldg(R + (size_t)row[q] * 3 + 1), z = __ldg(R + (size_t)row[q] * 3 + 2);
+            rl[q] = st[n + m + row[q]];  // ratioL[k] of the current level
+        }
+        qx[q] = pack2(x, x), qy[q] = pack2(y, y), qz[q] = pack2(z, z);
+        acc3[q] = 0.f, cost[q] = 0.f;
+        acc1[q] = (s == 0) ? 1e-9f : 0.f;
+    }
+    const int c_begin = s * a.span, c_end = min(m, c_begin + a.span);
+    for (int c0 = c_begin; c0 < c_end; c0 += EMD_CC) {
+        for (int i = tid; i < EMD_CC; i += THREADS) {
+            const int c = c0 + i;
+            float x = 0.f, y = 0.f, z = 0.f, w3 = 0.f, w1 = 0.f;  // zero weights: padded columns add exactly nothing
+            if (c < c_end) x = __ldg(C + (size_t)c * 3 + 0), y = __ldg(C + (size_t)c * 3 + 1), z = __ldg(C + (size_t)c * 3 + 2), w3 = ratioR[c], w1 = remainR[c];
+            xs[i] = x, ys[i] = y, zs[i] = z, w3s[i] = w3, w1s[i] = w1;
+        }
+        __syncthreads();
+        const int cnt4 = (min(EMD_CC, c_end - c0) + 3) & ~3;
+#pragma unroll 2
+        for (int c = 0; c < cnt4; c += 4) {
+            const ulonglong2 cx = *reinterpret_cast<const ulonglong2 *>(xs + c);
+            const ulonglong2 cy = *reinterpret_cast<const ulonglong2 *>(ys + c);
+            const ulonglong2 cz = *reinterpret_cast<const ulonglong2 *>(zs + c);
+            const float4 w3 = *reinterpret_cast<const float4 *>(w3s + c);
+            const float4 w1 = *reinterpret_cast<const float4 *>(w1s + c);
+            const float w3v[4] = {w3.x, w3.y, w3.z, w3.w}, w1v[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int q = 0; q < RQ; ++q) {
+                const f32x2 d01 = sqdist_exact2(qx[q], qy[q], qz[q], cx.x, cy.x, cz.x);
+                const f32x2 d23 = sqdist_exact2(qx[q], qy[q], qz[q], cx.y, cy.y, cz.y);
+                float t[4], d[4];
+                unpack2(mul2(d01, scale2), t[0], t[1]);
+                unpack2(mul2(d23, scale2), t[2], t[3]);
+                unpack2(d01, d[0], d[1]);
+                unpack2(d23, d[2], d[3]);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float en = ex2_approx(t[v]);          // next level's e
+                    const float e2 = __fmul_rn(en, en);
+                    const float ec = __fmul_rn(e2, e2);         // current level's e = en^4
+                    acc1[q] = __fmaf_rn(en, w1v[v], acc1[q]);
+                    const float u = __fmul_rn(rl[q], ec);
+                    acc3[q] = __fmaf_rn(u, w3v[v], acc3[q]);
+                    cost[q] = __fmaf_rn(__fmul_rn(u, w3v[v]), sqrt_approx(d[v]), cost[q]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+        if (row[q] < n) {
+            if (SPLIT) {
+                a.partial[((size_t)pair * a.S + s) * a.rstride + row[q]] = acc3[q];
+                a.partial2[((size_t)pair * a.S + s) * a.rstride + row[q]] = acc1[q];
+            } else {
+                const float rem = fmaxf(0.0f, st[row[q]] - acc3[q]);  // approxmatch.cu:193
+                st[row[q]] = rem;
+                st[n + m + row[q]] = rem / acc1[q];                   // :92 (acc1 includes the 1e-9 start, :68)
+            }
+        }
+    }
+    float c = 0.f;
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) c += (row[q] < n) ? cost[q] : 0.f;
+    c = warp_sum(c);
+    if ((tid & 31) == 0) warp_part[tid >> 5] = c;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < THREADS / 32; ++i) t += warp_part[i];
+        a.costpart[(size_t)pair * a.cp_stride + ((size_t)a.level_index * a.row_tiles + rt) * a.S + s] = t;
+    }
+}
+
+// Column-split mode of the fused sweep: fold the S slices of both sums in ascending order, then both row epilogues.
+__global__ void emd_combine31_kernel(const EmdArgs a) {
+    const size_t total = (size_t)a.pairs * a.n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int pair = (int)(i / a.n), r = (int)(i % a.n);
+        const float *p3 = a.partial + (size_t)pair * a.S * a.rstride + r, *p1 = a.partial2 + (size_t)pair * a.S * a.rstride + r;
+        float acc3 = p3[0], acc1 = p1[0];
+        for (int s = 1; s < a.S; ++s) acc3 += p3[(size_t)s * a.rstride], acc1 += p1[(size_t)s * a.rstride];
+        float *st = a.state + (size_t)pair * 2 * (a.n + a.m);
+        const float rem = fmaxf(0.0f, st[r] - acc3);
+        st[r] = rem;
+        st[a.n + a.m + r] = rem / acc1;
     }
 }
 
@@ -490,6 +621,64 @@ static int run_auction(EmdArgs a, cudaStream_t stream) {
     return HP_OK;
 }
 
+template <int RQ, int THREADS, bool SPLIT>
+static int launch_fused31(EmdArgs a, cudaStream_t stream) {
+    a.row_tiles = (a.n + THREADS * RQ - 1) / (THREADS * RQ);
+    const long long grid = (long long)a.pairs * a.row_tiles * a.S;
+    HP_REQUIRE(grid <= 0x7fffffffLL, "emd: grid too large (%lld CTAs); split the batch", grid);
+    emd_fused31_kernel<RQ, THREADS, SPLIT><<<(unsigned)grid, THREADS, 0, stream>>>(a);
+    HP_LAUNCH_CHECK("emd_fused31_kernel");
+    return HP_OK;
+}
+// same tile rule as launch_pass_auto<3> / row_tiles_auto (the cost partial layout depends on it)
+template <bool SPLIT>
+static int launch_fused31_auto(const EmdArgs &a, cudaStream_t stream) {
+    const long long want = (long long)sm_count() * 4;
+    auto ctas = [&](int tile) { return (long long)a.pairs * ((a.n + tile - 1) / tile) * a.S; };
+    if (ctas(128 * 8) >= want) return launch_fused31<8, 128, SPLIT>(a, stream);
+    if (ctas(128 * 4) >= want) return launch_fused31<4, 128, SPLIT>(a, stream);
+    if (ctas(64 * 4) >= want) return launch_fused31<4, 64, SPLIT>(a, stream);
+    return launch_fused31<2, 64, SPLIT>(a, stream);
+}
+
+// The match-free auction with P3(level) + P1(next level) fused: P1(first level); then per level P2, fused sweep (the last
+// level: plain P3 with the cost).  19 launches (+ one combine per launch in column-split mode).
+template <bool SPLIT>
+static int run_auction_fused(EmdArgs a, cudaStream_t stream) {
+    const int blocks = sm_count() * 4;
+    emd_init_kernel<<<blocks, 256, 0, stream>>>(a.state, a.pairs, a.n, a.m);
+    HP_LAUNCH_CHECK("emd_init_kernel");
+    const int span_rows_n = a.S > 1 ? ((a.n + a.S - 1) / a.S + EMD_CC - 1) / EMD_CC * EMD_CC : a.n;  // columns = xyz1 (P2)
+    const int span_rows_m = a.S > 1 ? ((a.m + a.S - 1) / a.S + EMD_CC - 1) / EMD_CC * EMD_CC : a.m;  // columns = xyz2 (P1, P3)
+    int rc, li = 0;
+    a.j = 7, a.level_index = 0, a.first_level = 1, a.span = span_rows_m;
+    if ((rc = launch_pass_auto<1, SPLIT, false, false>(a, stream)) != HP_OK) return rc;
+    if (SPLIT) {
+        emd_combine_kernel<1><<<blocks, 256, 0, stream>>>(a);
+        HP_LAUNCH_CHECK("emd_combine_kernel<1>");
+    }
+    for (int j = 7; j > -2; --j, ++li) {  // approxmatch.cu:55
+        a.j = j, a.level_index = li, a.first_level = (li == 0);
+        a.span = span_rows_n;
+        if ((rc = launch_pass_auto<2, SPLIT, false, false>(a, stream)) != HP_OK) return rc;
+        if (SPLIT) {
+            emd_combine_kernel<2><<<blocks, 256, 0, stream>>>(a);
+            HP_LAUNCH_CHECK("emd_combine_kernel<2>");
+        }
+        a.span = span_rows_m;
+        if (j > -1) {
+            if ((rc = launch_fused31_auto<SPLIT>(a, stream)) != HP_OK) return rc;
+            if (SPLIT) {
+                emd_combine31_kernel<<<blocks, 256, 0, stream>>>(a);
+                HP_LAUNCH_CHECK("emd_combine31_kernel");
+            }
+        } else {  // last level: nothing follows, plain P3 with the cost (remainL is not needed any more)
+            if ((rc = launch_pass_auto<3, SPLIT, false, true>(a, stream)) != HP_OK) return rc;
+        }
+    }
+    return HP_OK;
+}
+
 // Column split for the workspace-backed path.  Work items = pairs x row tiles x column slices, all of equal cost; the
 // slice count is chosen so that the items spread evenly over the SMs (items / (ceil(items/SMs)*SMs) close to 1: the
 // reference shape B=32, 2048^2 gets 8 slices -> 1024 items = 6.9 per SM instead of 512 = 3.5 per SM), preferring fewer
@@ -582,14 +771,14 @@ extern "C" size_t hp_emd_cost_workspace_bytes(int pairs, int n, int m) {
     const int S = choose_split(pairs, n, m);
     const size_t big = (size_t)(n > m ? n : m);
     const size_t state = (size_t)pairs * 2 * ((size_t)n + m);
-    const size_t partial = S > 1 ? (size_t)pairs * S * big : 0;
+    const size_t partial = S > 1 ? (size_t)2 * pairs * S * big : 0;  // two sums in the fused P3 + P1 sweep
     const int rt_max = (n + 127) / 128;  // upper bound: the smallest row tile is 64 threads x 2 rows
     const size_t costpart = (size_t)pairs * 9 * rt_max * S;
     return (state + partial + costpart) * sizeof(float) + 64;
 }
 
-extern "C" int hp_emd_cost_pairs(int pairs, int n, int m, const float *first, const int *ia, const float *second,
-                                 const int *ib, float *cost, void *workspace, size_t workspace_bytes, void *stream_v) {
+static int emd_cost_pairs_impl(int pairs, int n, int m, const float *first, const int *ia, const float *second, const int *ib,
+                               float *cost, void *workspace, size_t workspace_bytes, void *stream_v, bool fused) {
     HP_REQUIRE(pairs >= 0 && n >= 0 && m >= 0, "hp_emd_cost_pairs: negative size (pairs=%d n=%d m=%d)", pairs, n, m);
     if (pairs == 0) return HP_OK;
     HP_REQUIRE(n > 0 && m > 0, "hp_emd_cost_pairs: empty point set (n=%d m=%d)", n, m);
@@ -609,16 +798,30 @@ extern "C" int hp_emd_cost_pairs(int pairs, int n, int m, const float *first, co
     ws += (size_t)pairs * 2 * ((size_t)n + m);
     a.partial = S > 1 ? ws : nullptr;
     ws += S > 1 ? (size_t)pairs * S * big : 0;
+    a.partial2 = S > 1 ? ws : nullptr;
+    ws += S > 1 ? (size_t)pairs * S * big : 0;
     a.costpart = ws;
     a.match = nullptr;
     a.n = n, a.m = m, a.pairs = pairs, a.S = S, a.rstride = (int)big;
     const int rt3 = row_tiles_auto(pairs, n, S);  // the row tiling P3 will use (same rule as launch_pass_auto<3>)
     a.cp_stride = 9 * rt3 * S;
-    int rc = (S > 1) ? run_auction<true, false, true>(a, stream) : run_auction<false, false, true>(a, stream);
+    int rc;
+    if (fused) rc = (S > 1) ? run_auction_fused<true>(a, stream) : run_auction_fused<false>(a, stream);
+    else rc = (S > 1) ? run_auction<true, false, true>(a, stream) : run_auction<false, false, true>(a, stream);
     if (rc != HP_OK) return rc;
     emd_cost_finish_kernel<<<(pairs + 127) / 128, 128, 0, stream>>>(a.costpart, a.cp_stride, pairs, cost);
     HP_LAUNCH_CHECK("emd_cost_finish_kernel");
     return HP_OK;
+}
+
+extern "C" int hp_emd_cost_pairs(int pairs, int n, int m, const float *first, const int *ia, const float *second,
+                                 const int *ib, float *cost, void *workspace, size_t workspace_bytes, void *stream) {
+    return emd_cost_pairs_impl(pairs, n, m, first, ia, second, ib, cost, workspace, workspace_bytes, stream, true);
+}
+
+extern "C" int hp_emd_cost_pairs_exact(int pairs, int n, int m, const float *first, const int *ia, const float *second,
+                                       const int *ib, float *cost, void *workspace, size_t workspace_bytes, void *stream) {
+    return emd_cost_pairs_impl(pairs, n, m, first, ia, second, ib, cost, workspace, workspace_bytes, stream, false);
 }
 
 extern "C" int hp_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *out,

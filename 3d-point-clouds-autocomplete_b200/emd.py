@@ -87,11 +87,12 @@ _emd_ws = {}
 
 
 def emd_cost_pairs(first: torch.Tensor, second: torch.Tensor, ia: Optional[torch.Tensor] = None,
-                   ib: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   ib: Optional[torch.Tensor] = None, exact: bool = False) -> torch.Tensor:
     """Match-free fused EMD cost: cost[p] = match_cost(first[ia[p]], second[ib[p]]) (forward only).
 
     No [pairs, M, N] matrix is ever written: the auction's per-level weights are folded into the cost
-    inside pass 3 (utils/metrics.py only ever uses match_cost under no_grad)."""
+    inside pass 3 (utils/metrics.py only ever uses match_cost under no_grad).  ``exact=True`` evaluates every
+    exponential like the reference (hp_emd_cost_pairs_exact: 4 instead of 3 MUFU operations per point pair and level)."""
     check_points(first, "first")
     check_points(second, "second")
     check_same_device(first, second)
@@ -121,9 +122,10 @@ def emd_cost_pairs(first: torch.Tensor, second: torch.Tensor, ia: Optional[torch
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
             _emd_ws[key] = ws
-        rc = lib.hp_emd_cost_pairs(pairs, n, m, first.data_ptr(), ia.data_ptr() if ia is not None else None,
-                                   second.data_ptr(), ib.data_ptr() if ib is not None else None, cost.data_ptr(),
-                                   ws.data_ptr(), ws.numel(), stream)
+        fn = lib.hp_emd_cost_pairs_exact if exact else lib.hp_emd_cost_pairs
+        rc = fn(pairs, n, m, first.data_ptr(), ia.data_ptr() if ia is not None else None,
+                second.data_ptr(), ib.data_ptr() if ib is not None else None, cost.data_ptr(),
+                ws.data_ptr(), ws.numel(), stream)
     _native.check(rc, "hp_emd_cost_pairs")
     return cost
 

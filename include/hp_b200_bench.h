@@ -28,8 +28,8 @@ HP_API int hp_measure_chamfer_ring_only(int b, int n, const float *xyz1, int m, 
                                  size_t workspace_bytes, void *stream);
 
 /* Per-CTA timeline of the Chamfer step: while a device buffer is set (NULL switches it off), every nn_ring_kernel CTA writes
- * its %globaltimer at start / end to slots [2*cta, 2*cta+1] and every nn_ring_tail_kernel CTA its start / ticket-acquired / end
- * to slots [2*ring_ctas + 3*cta ...] (nanoseconds).  tools/chamfer_timeline.py prints the summary. */
+ * its %globaltimer at start / end to slots [2*cta, 2*cta+1] and every nn_ring_tail_kernel CTA its %globaltimer
+ * at ten points of its life to slots [2*ring_ctas + 10*cta ...] (nanoseconds; see the HP_TRACE marks in csrc/chamfer_ring.cu).  tools/chamfer_timeline.py prints the summary. */
 HP_API int hp_measure_set_trace(void *device_u64_buffer);
 
 #ifdef __cplusplus

@@ -24,9 +24,10 @@ loss = torch.empty(1, device=dev); g1 = torch.empty(B, N, 3, device=dev); g2 = t
 one = torch.ones(1, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 st = torch.cuda.current_stream().cuda_stream
-ring_ctas = B * ((N + 1023) // 1024) * ((M + 127) // 128)
+RW = int(os.environ.get('HP_RING_WARPS', '4')) * 256  # rows per ring CTA (bench library switch)
+ring_ctas = B * ((N + RW - 1) // RW) * ((M + 127) // 128)
 tail_ctas = B * ((N + 255) // 256 + (M + 255) // 256)
-trace = torch.zeros(2 * ring_ctas + 3 * tail_ctas, dtype=torch.int64, device=dev)
+trace = torch.zeros(2 * ring_ctas + 10 * tail_ctas, dtype=torch.int64, device=dev)
 
 
 def step():
@@ -39,23 +40,33 @@ for _ in range(5):
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ts = []
-for _ in range(50):
+for _ in range(200):
     flush.fill_(1)
     e0.record(); step(); e1.record()
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
-print(f"step (eager launches, L2 flushed): median {np.median(ts):.1f} us  min {min(ts):.1f} us   HP_NO_PDL={os.environ.get('HP_NO_PDL', '0')}")
+print(f"step (eager launches, L2 flushed): mean {np.mean(ts):.2f} median {np.median(ts):.1f} us  min {min(ts):.1f} us   HP_NO_PDL={os.environ.get('HP_NO_PDL', '0')} "
+      f"HP_RING_WARPS={os.environ.get('HP_RING_WARPS', '4')} HP_TAIL_TICKETS={os.environ.get('HP_TAIL_TICKETS', 'default')} HP_RING_VARIANT={os.environ.get('HP_RING_VARIANT', '0')}")
+if os.environ.get("HP_TIMELINE_BRIEF"):
+    sys.exit(0)
 nat.check_bench(lib.hp_measure_set_trace(trace.data_ptr()), "trace")
-for rep in range(3):
+for rep in range(2):
     trace.zero_()
     flush.fill_(1)
     step()
     torch.cuda.synchronize()
     t = trace.cpu().numpy().astype(np.float64)
     r = t[: 2 * ring_ctas].reshape(-1, 2)
-    q = t[2 * ring_ctas:].reshape(-1, 3)
+    q10 = t[2 * ring_ctas:].reshape(-1, 10)
     t0 = r[:, 0].min()
-    r, q = (r - t0) / 1e3, (q - t0) / 1e3
+    q10 = (q10 - t0) / 1e3
+    q = q10[:, [0, 1, 8]]
+    r = (r - t0) / 1e3
+    names = ["start", "ticket", "keys+loss sums", "ranking", "prefix+scan", "placement", "gather+stores", "service flags", "end"]
+    late = q10[:, 1] > r[:, 1].max() - 1.0   # tail CTAs whose ticket came with the last ring CTAs: the exposed ones
+    print("tail phases (us after the ticket; median over all CTAs | over the last-cloud CTAs): " + ", ".join(
+        f"{names[i]} {np.median(q10[:, i] - q10[:, 1]):.1f}|{np.median(q10[late, i] - q10[late, 1]):.1f}" for i in (2, 3, 4, 5, 6, 7, 8)
+        if np.median(q10[:, i]) > 0))
     print(f"--- rep {rep}: ring CTAs {ring_ctas}, tail CTAs {tail_ctas} (times in us from the first ring CTA's start)")
     print(f"ring: last start {r[:,0].max():.1f}  first end {r[:,1].min():.1f}  last end {r[:,1].max():.1f}  CTA duration median {np.median(r[:,1]-r[:,0]):.1f} max {(r[:,1]-r[:,0]).max():.1f}")
     print(f"tail: first start {q[:,0].min():.1f}  last start {q[:,0].max():.1f}  last end {q[:,2].max():.1f}")
@@ -67,6 +78,23 @@ for rep in range(3):
         print(f"  cloud {c:3d}: ring done {rc[:,1].max():6.1f} | tail start {qc[:,0].min():6.1f}..{qc[:,0].max():6.1f}  ticket {qc[:,1].min():6.1f}..{qc[:,1].max():6.1f}  end {qc[:,2].min():6.1f}..{qc[:,2].max():6.1f}")
     started_before = (q[:, 0] < r[:, 1].max()).sum()
     print(f"tail CTAs started before the ring kernel's last CTA ended: {started_before} / {tail_ctas}; exposed tail = {q[:,2].max() - r[:,1].max():.1f} us")
+nat.check_bench(lib.hp_measure_set_trace(None), "trace off")
+# the ring kernel alone: per-CTA timeline (start time vs duration), then event timing
+nat.check_bench(lib.hp_measure_set_trace(trace.data_ptr()), "trace")
+ring_ws0 = torch.zeros_like(ws)
+trace.zero_()
+flush.fill_(1)
+nat.check_bench(lib.hp_measure_chamfer_ring_only(B, N, a.data_ptr(), M, b.data_ptr(), ring_ws0.data_ptr(), ring_ws0.numel(), st), "ring")
+torch.cuda.synchronize()
+t = trace.cpu().numpy().astype(np.float64)
+r = t[: 2 * ring_ctas].reshape(-1, 2)
+r = (r - r[:, 0].min()) / 1e3
+order = np.argsort(r[:, 0])
+dur = (r[:, 1] - r[:, 0])[order]
+print(f"ring alone: last start {r[:,0].max():.1f}  last end {r[:,1].max():.1f}; CTA duration by start order: first 592 median {np.median(dur[:592]):.1f}, "
+      f"next {len(dur)-592} median {np.median(dur[592:]):.1f}, last 100 median {np.median(dur[-100:]):.1f} min {dur.min():.1f} max {dur.max():.1f}")
+ends = np.sort(r[:, 1])
+print("ring alone: CTAs still running at t = " + ", ".join(f"{tt}us:{int((r[:,0] <= tt).sum() - (r[:,1] <= tt).sum())}" for tt in (5, 15, 25, 30, 35, 40, 45, 48)))
 nat.check_bench(lib.hp_measure_set_trace(None), "trace off")
 # the ring kernel alone, with and without the ticket arrival
 ring_ws = torch.zeros_like(ws)

@@ -1,10 +1,10 @@
 #!/usr/bin/env bash
+# every python call under its own timeout: a kernel that waits for a ticket that never comes must not eat the GPU budget
 mkdir -p gpurun_out
 {
-python tools/chamfer_timeline.py
-HP_NO_PDL=1 python tools/chamfer_timeline.py | head -1
-HP_RING_VARIANT=20 python tools/chamfer_timeline.py | tail -1
-} > gpurun_out/r2_timeline.txt 2>&1
-cat gpurun_out/r2_timeline.txt
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/r2_launches_timeline.csv python tools/chamfer_timeline.py > /dev/null 2>&1
-grep -o '"nn_ring[a-z_]*[^"]*","[^"]*","[^"]*","[^"]*","[^"]*","gpu__time_duration.sum","[a-z]*","[0-9.,]*"' gpurun_out/r2_launches_timeline.csv | awk -F'","' '{print $1, $NF}' | sort | uniq -c | sort -rn | head -12
+echo "===== tickets (default)"; HP_TAIL_TICKETS=1 timeout 120 python tools/chamfer_timeline.py || echo "FAILED/TIMEOUT rc=$?"
+echo "===== whole-grid wait";   HP_TAIL_TICKETS=0 timeout 120 python tools/chamfer_timeline.py || echo "FAILED/TIMEOUT rc=$?"
+echo "===== whole-grid wait, 5 CTAs/SM";   HP_TAIL_TICKETS=0 HP_RING_VARIANT=1 HP_TIMELINE_BRIEF=1 timeout 120 python tools/chamfer_timeline.py || echo "FAILED/TIMEOUT rc=$?"
+echo "===== tickets, 5 CTAs/SM";   HP_TAIL_TICKETS=1 HP_RING_VARIANT=1 HP_TIMELINE_BRIEF=1 timeout 120 python tools/chamfer_timeline.py || echo "FAILED/TIMEOUT rc=$?"
+} > gpurun_out/r2_timeline2.txt 2>&1
+cat gpurun_out/r2_timeline2.txt
