@@ -620,9 +620,9 @@ __device__ __forceinline__ float rf_serial8(const float *w) {
 // chunks1 / chunks2 > 0: losspart holds chunk partials, per cloud [chunks1 of direction 0 | chunks2 of direction 1];
 // chunks1 == 0: losspart holds one sum per (cloud, direction).
 __device__ __forceinline__ void rf_loss_total_warp(const RingNNArgs &a, int chunks1, int chunks2, int lane) {
-    float tot = 0.f;
-#pragma unroll 1
-    for (int vw = 0; vw < 8; ++vw) {  // "warp" vw of the definition
+    float accv[8];
+#pragma unroll
+    for (int vw = 0; vw < 8; ++vw) {  // "warp" vw of the definition; unrolled: the loads of the eight groups overlap
         float acc = 0.f;
         for (int pd = vw * 32 + lane; pd < 2 * a.b; pd += 256) {
             float p;
@@ -648,8 +648,11 @@ __device__ __forceinline__ void rf_loss_total_warp(const RingNNArgs &a, int chun
             }
             acc += p;
         }
-        tot += warp_sum(acc);  // serial over the 8 "warps", each folded by the xor tree
+        accv[vw] = acc;
     }
+    float tot = 0.f;
+#pragma unroll
+    for (int vw = 0; vw < 8; ++vw) tot += warp_sum(accv[vw]);  // serial over the 8 "warps", each folded by the xor tree
     if (lane == 0) {
         a.loss[0] = tot;
         a.counters[0] = 0u;

@@ -18,13 +18,16 @@
 // distance and the two exponent scalings run as FADD2/FMUL2/FFMA2, the exponential on MUFU.EX2.
 // Bound: MUFU (16 ex2/clk/SM) and the FP32 pipe are within ~10% of each other for this mix.
 //
-// Match-free metrics path (hp_emd_cost_pairs): P3 of level j and P1 of level j-1 sweep the same (row, column) pairs and P1's
-// sum needs nothing of P3 but the row scalar remainL[k], so they run as ONE sweep (emd_fused31_kernel): one distance evaluation
-// and ONE ex2 for both -- the next level's e' = ex2(d * scale') is evaluated and the current level's e = e'^4 follows by two
-// multiplies (level' = level / 4).  Per level: MUFU work 3 ops per pair (ex2 in P2, ex2 + sqrt in the fused sweep) instead of 4,
-// 19 launches per auction instead of 27.  e'^4 deviates from ex2.approx(d * scale) by <= ~1.2e-6 relative (four times the
-// 2^-22 bound of ex2.approx plus two roundings); the cost stays within 1e-5 of the reference extension (tests).  The API path
-// (hp_approxmatch*, which returns `match`) keeps the reference's exact arithmetic below.
+// Match-free metrics path.  hp_emd_cost_pairs evaluates every exponential exactly like the reference (same expression in all
+// three passes of a level): measured 1.4e-6 worst relative deviation of the cost from the reference extension over 64x64 cloud
+// pairs of 2048 points (tests/test_metrics_reference_parity_gpu.py).
+// hp_emd_cost_pairs_fast is an opt-in shortcut: P3 of level j and P1 of level j-1 sweep the same (row, column) pairs and P1's sum
+// needs nothing of P3 but the row scalar remainL[k], so they run as ONE sweep (emd_fused31_kernel) with ONE ex2 for both -- the
+// next level's e' = ex2(d * scale') is evaluated and the current level's e = e'^4 follows by two multiplies (level' = level / 4):
+// 3 instead of 4 MUFU operations per pair and level, 19 launches instead of 27, 1.18x faster at B=32, 2048^2 (1.28 vs 1.52 ms).
+// e'^4 deviates from ex2.approx(d * scale) by ~1e-6 relative, P3 then no longer sends exactly what P2 accepted, and the
+// nine-level feedback amplifies that to up to 2.1e-5 on the cost (same test) -- above the 1e-5 parity bar, hence not the default.
+// (Giving P2 the same e'^4, so that P2 and P3 agree with each other but not with P1, measured WORSE: 1.6e-4.)
 //
 // Numerics kept from the reference build (verified in its sm_100 SASS):
 //   d = fma(dz,dz,fma(dx,dx,dy*dy));  arg = (d * level) * 1.4426950216f;  e = ex2.approx(arg)
@@ -816,12 +819,12 @@ static int emd_cost_pairs_impl(int pairs, int n, int m, const float *first, cons
 
 extern "C" int hp_emd_cost_pairs(int pairs, int n, int m, const float *first, const int *ia, const float *second,
                                  const int *ib, float *cost, void *workspace, size_t workspace_bytes, void *stream) {
-    return emd_cost_pairs_impl(pairs, n, m, first, ia, second, ib, cost, workspace, workspace_bytes, stream, true);
+    return emd_cost_pairs_impl(pairs, n, m, first, ia, second, ib, cost, workspace, workspace_bytes, stream, false);
 }
 
-extern "C" int hp_emd_cost_pairs_exact(int pairs, int n, int m, const float *first, const int *ia, const float *second,
-                                       const int *ib, float *cost, void *workspace, size_t workspace_bytes, void *stream) {
-    return emd_cost_pairs_impl(pairs, n, m, first, ia, second, ib, cost, workspace, workspace_bytes, stream, false);
+extern "C" int hp_emd_cost_pairs_fast(int pairs, int n, int m, const float *first, const int *ia, const float *second,
+                                      const int *ib, float *cost, void *workspace, size_t workspace_bytes, void *stream) {
+    return emd_cost_pairs_impl(pairs, n, m, first, ia, second, ib, cost, workspace, workspace_bytes, stream, true);
 }
 
 extern "C" int hp_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *out,

@@ -87,12 +87,12 @@ _emd_ws = {}
 
 
 def emd_cost_pairs(first: torch.Tensor, second: torch.Tensor, ia: Optional[torch.Tensor] = None,
-                   ib: Optional[torch.Tensor] = None, exact: bool = False) -> torch.Tensor:
+                   ib: Optional[torch.Tensor] = None, fast: bool = False) -> torch.Tensor:
     """Match-free fused EMD cost: cost[p] = match_cost(first[ia[p]], second[ib[p]]) (forward only).
 
     No [pairs, M, N] matrix is ever written: the auction's per-level weights are folded into the cost
-    inside pass 3 (utils/metrics.py only ever uses match_cost under no_grad).  ``exact=True`` evaluates every
-    exponential like the reference (hp_emd_cost_pairs_exact: 4 instead of 3 MUFU operations per point pair and level)."""
+    inside pass 3 (utils/metrics.py only ever uses match_cost under no_grad).  ``fast=True`` takes hp_emd_cost_pairs_fast
+    (one ex2 shared between two passes: 1.18x faster, but up to 2.1e-5 off the reference's cost -- outside the 1e-5 bar)."""
     check_points(first, "first")
     check_points(second, "second")
     check_same_device(first, second)
@@ -122,7 +122,7 @@ def emd_cost_pairs(first: torch.Tensor, second: torch.Tensor, ia: Optional[torch
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
             _emd_ws[key] = ws
-        fn = lib.hp_emd_cost_pairs_exact if exact else lib.hp_emd_cost_pairs
+        fn = lib.hp_emd_cost_pairs_fast if fast else lib.hp_emd_cost_pairs
         rc = fn(pairs, n, m, first.data_ptr(), ia.data_ptr() if ia is not None else None,
                 second.data_ptr(), ib.data_ptr() if ib is not None else None, cost.data_ptr(),
                 ws.data_ptr(), ws.numel(), stream)

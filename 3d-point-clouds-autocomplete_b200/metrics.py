@@ -216,7 +216,7 @@ def nearest_other_cd(pcs: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def pairwise_emd(first: torch.Tensor, second: torch.Tensor, row_begin: int = 0, row_end: Optional[int] = None,
-                 max_pairs_per_call: int = 4096, exact: bool = False) -> torch.Tensor:
+                 max_pairs_per_call: int = 4096, fast: bool = False) -> torch.Tensor:
     """emd[r - row_begin, s] = match_cost(first_r, second_s) / N  (emd_approx, utils/metrics.py:71-76)."""
     check_points(first, "first")
     check_points(second, "second")
@@ -235,7 +235,7 @@ def pairwise_emd(first: torch.Tensor, second: torch.Tensor, row_begin: int = 0, 
         p = torch.arange(p0, p1, device=dev, dtype=torch.int64)
         ia = (row_begin + p // nb).to(torch.int32).contiguous()
         ib = (p % nb).to(torch.int32).contiguous()
-        flat[p0:p1] = emd_cost_pairs(first, second, ia, ib, exact=exact) / float(n)
+        flat[p0:p1] = emd_cost_pairs(first, second, ia, ib, fast=fast) / float(n)
     return out
 
 

@@ -50,11 +50,12 @@ def test_compute_all_metrics_vs_reference_arithmetic(hp, tmp_path, n_smp, n_ref,
     # the matrices themselves
     M_cd, M_emd = hp.metrics._pairwise_EMD_CD_(rd, sd)
     np.testing.assert_allclose(M_cd.cpu().numpy(), R["M_rs_cd"], rtol=1e-5, atol=2e-6)
-    ex = hp.pairwise_emd(rd, sd, exact=True).cpu().numpy()
-    rel = lambda x: float(np.max(np.abs(x - R["M_rs_emd"]) / np.abs(R["M_rs_emd"])))  # noqa: E731
-    print("EMDREL " + json.dumps({"shape": [n_smp, n_ref, npts], "fused_max_rel": rel(M_emd.cpu().numpy()), "exact_max_rel": rel(ex),
-                                  "fused_vs_exact": float(np.max(np.abs(ex - M_emd.cpu().numpy()) / np.abs(ex)))}))
     np.testing.assert_allclose(M_emd.cpu().numpy(), R["M_rs_emd"], rtol=1e-5)
+    # the opt-in shortcut (one ex2 shared by two passes) is measured, not trusted: a few 1e-5 off, documented in csrc/emd.cu
+    fast = hp.pairwise_emd(rd, sd, fast=True).cpu().numpy()
+    rel = lambda x: float(np.max(np.abs(x - R["M_rs_emd"]) / np.abs(R["M_rs_emd"])))  # noqa: E731
+    print("EMDREL " + json.dumps({"shape": [n_smp, n_ref, npts], "default_max_rel": rel(M_emd.cpu().numpy()), "fast_max_rel": rel(fast)}))
+    assert rel(fast) < 1e-4
     M_rr_emd = hp.pairwise_emd(rd, rd).cpu().numpy()
     M_ss_cd = hp.pairwise_cd(sd, sd).cpu().numpy()
     np.testing.assert_allclose(M_rr_emd, R["M_rr_emd"], rtol=1e-5)

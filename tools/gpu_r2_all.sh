@@ -1,16 +1,23 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
-HP_TAIL_TICKETS=1 timeout 120 python tools/chamfer_timeline.py > gpurun_out/r2_timeline3.txt 2>&1; head -14 gpurun_out/r2_timeline3.txt; tail -3 gpurun_out/r2_timeline3.txt
-timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -40 > gpurun_out/r2_gputests.log; cat gpurun_out/r2_gputests.log
-timeout 600 python bench.py --steps 200 --warmup 10 --no-other-paths --no-metrics-eval --no-cpu-baseline > gpurun_out/r2_bench_quick.json 2> gpurun_out/r2_bench_quick.err
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -30 > gpurun_out/r2_gputests.log; cat gpurun_out/r2_gputests.log
+( time timeout 900 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err ) 2>&1 | tail -3
+tail -5 gpurun_out/r2_bench.err
+( time timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err ) 2>&1 | tail -3
 python - <<'PY'
 import json
-try:
-    d = json.loads(open("gpurun_out/r2_bench_quick.json").read().strip().splitlines()[-1])
-    r = d["roofline"]
-    print("step ms", d["ms_per_step"], "ring ms", r["kernel_ms"], "fwd ms", r["forward_ms"], "bwd ms", r["bwd_kernel_ms"],
-          "frac ring", r["frac"], "fwd+bwd frac", r["fwd+bwd_frac"], "e2e", d["e2e"]["ms_per_step"], d["e2e"]["with_gradients_d2h_ms_per_step"], d["e2e"]["pipelined_independent_steps_ms_per_step"], "eager", d["eager_api"]["ms_per_step"])
-except Exception as e:
-    print("bench failed", e)
-    print(open("gpurun_out/r2_bench_quick.err").read()[-3000:])
+for f in ("gpurun_out/r2_bench.json", "gpurun_out/r2_bench_reference.json"):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, {k: d[k] for k in ("value", "ms_per_step", "steps") if k in d}, "e2e", d.get("e2e", {}).get("value"))
+        if "roofline" in d:
+            r = d["roofline"]
+            print(" roofline", {k: r[k] for k in ("frac", "kernel_ms", "forward_ms", "fwd+bwd_frac")})
+            print(" metrics_eval", r.get("metrics_eval"))
+            print(" cpu", d.get("cpu_baseline"), d.get("cpu_baseline_c1"))
+            print(" other", json.dumps(d.get("other_paths"), indent=0)[:3000])
+            print(" comparators", d.get("secondary_comparators"))
+            print(" c4", d.get("c4_full_step"))
+    except Exception as e:
+        print(f, "FAILED", e)
 PY

@@ -16,8 +16,8 @@ for (b, n, m) in [(2, 300, 257), (1, 1100, 130)]:
     loss.backward()
     d1, d2 = hp.nn_distance(a, c)
     (d1.sum() + 2 * d2.sum()).backward()
-    hp.chamfer_step(a.detach(), c.detach(), torch.tensor(0.5, device=dev))  # ring forward + fused tail (cluster of 2, PDL)
-    skew = (c.detach() * 0.02).contiguous()                                  # skewed assignment: radix path of the fused tail
+    hp.chamfer_step(a.detach(), c.detach(), torch.tensor(0.5, device=dev))  # ring forward + sectioned tail (tickets, PDL): slot path
+    skew = (c.detach() * 0.02).contiguous()                                  # skewed assignment: ranking / prefix path of the tail
     hp.chamfer_step(a.detach(), skew, torch.tensor(0.5, device=dev))
     e1, i1, e2, i2 = hp.NNDistance(a.detach(), c.detach())
     hp.NNDistanceGrad(a.detach(), c.detach(), i1, i2, torch.ones_like(e1), torch.ones_like(e2))  # sorting backward
@@ -33,6 +33,8 @@ match, _ = hp.ApproxMatch(p, q)
 hp.MatchCost(p, q, match)
 hp.MatchCostGrad(p, q, match)
 hp.emd_cost_pairs(p, p.flip(0))
+hp.emd_cost_pairs(p, p.flip(0), fast=True)                                      # fused P3 + P1 sweep
+hp.batch_pairwise_dist(p, q)                                                     # a2: the expansion-form matrix
 s1 = (torch.rand(6, 128, 3, generator=g) - 0.5).to(dev)
 s2 = (torch.rand(5, 128, 3, generator=g) - 0.5).to(dev)
 hp.compute_all_metrics(s1, s2, with_emd=True, one_nn=True)
