@@ -1,5 +1,6 @@
 """GPU parity tests for approximate EMD (approx_match / match_cost), through the C ABI.
-Bar (north star): EMD costs and gradients within 1e-5 relative of the reference's CUDA extension."""
+Bar (north star): EMD costs and gradients within 1e-5 relative of the reference's CUDA extension; the tolerances below are the
+measured deviations (tools/emd_grad_probe.py) with a small margin, all inside that bar."""
 import numpy as np
 import pytest
 import torch
@@ -53,8 +54,11 @@ def test_vs_reference_extension_live(hp, ref_ext, b, n, m):
     torch.cuda.synchronize()
     torch.testing.assert_close(cost, rcost, rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(fused, rcost, rtol=1e-5, atol=1e-7)
-    torch.testing.assert_close(match, rmatch, rtol=5e-4, atol=2e-6)
-    assert _rel(g1.cpu().numpy(), rg1.cpu().numpy()) < 2e-5 and _rel(g2.cpu().numpy(), rg2.cpu().numpy()) < 2e-5
+    # the auction repeats the reference's arithmetic in the reference's order: the match matrix is the reference's up to
+    # flushed denormals (measured: 98-99 % of the entries bit-identical, the rest below 1e-17 of the largest entry), and the
+    # gradients computed from OUR match are inside the 1e-5 bar with a wide margin (measured: grad1 identical, grad2 3e-7)
+    assert _rel(match.cpu().numpy(), rmatch.cpu().numpy()) < 1e-12
+    assert _rel(g1.cpu().numpy(), rg1.cpu().numpy()) < 1e-6 and _rel(g2.cpu().numpy(), rg2.cpu().numpy()) < 1e-6
 
 
 def test_vs_cpu_oracle(hp, oracle):
@@ -106,8 +110,8 @@ def test_match_cost_autograd(hp, ref_ext):
     rcost = ref_ext.MatchCost(ad.detach(), cd.detach(), rmatch)
     torch.cuda.synchronize()
     torch.testing.assert_close(cost.detach(), rcost, rtol=1e-5, atol=1e-7)
-    assert _rel(ad.grad.cpu().numpy(), (rg1 * w.view(-1, 1, 1)).cpu().numpy()) < 2e-5
-    assert _rel(cd.grad.cpu().numpy(), (rg2 * w.view(-1, 1, 1)).cpu().numpy()) < 2e-5
+    assert _rel(ad.grad.cpu().numpy(), (rg1 * w.view(-1, 1, 1)).cpu().numpy()) < 1e-5
+    assert _rel(cd.grad.cpu().numpy(), (rg2 * w.view(-1, 1, 1)).cpu().numpy()) < 1e-5
     with torch.no_grad():
         fused = hp.match_cost(ad, cd)  # no grad -> match-free kernel
     torch.testing.assert_close(fused, rcost, rtol=1e-5, atol=1e-7)
