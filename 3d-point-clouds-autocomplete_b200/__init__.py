@@ -15,7 +15,8 @@ from .emd import (ApproxMatch, MatchCost, MatchCostFunction, MatchCostGrad, appr
 
 from . import target_network  # noqa: F401
 from .target_network import (TargetNetwork, generate_points, generate_points_batched, reconstruct_batch,  # noqa: F401
-                             target_network_backward, target_network_forward, target_network_num_weights)
+                             target_network_backward, target_network_forward, target_network_num_weights,
+                             target_network_set_mode)
 from . import graphs  # noqa: F401
 from .graphs import (ChamferHostPipeline, ChamferStepGraph, FullModelStepGraph, HotPathStepGraph,  # noqa: F401
                      TargetNetworkStepGraph)

@@ -52,6 +52,7 @@ SIGNATURES = {
     "hp_emd_cost_pairs": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hp_emd_cost_pairs_fast": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hp_target_network_num_weights": (_ll, [_int, ctypes.POINTER(_int), _int]),
+    "hp_target_network_set_mode": (_int, [_int]),
     "hp_target_network_forward": (_int, [_int, _int, _int, ctypes.POINTER(_int), _int, _vp, _vp, _ll, _vp, _int, _vp]),
     "hp_target_network_backward_workspace_bytes": (_sz, [_int, _int, _int, ctypes.POINTER(_int), _int]),
     "hp_target_network_backward": (_int, [_int, _int, _int, ctypes.POINTER(_int), _int, _vp, _vp, _ll, _vp, _int, _vp, _vp,

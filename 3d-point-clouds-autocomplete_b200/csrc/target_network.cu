@@ -527,6 +527,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_backward_kernel(const TNArgs
     if (cur >= 0) flush(cur);
 }
 
+}  // namespace hp
+#include "target_network_mma.cuh"
+namespace hp {
+
 // ---- generic path: any widths ------------------------------------------------------------------------
 constexpr int TNG_T = 32;        // points per tile
 constexpr int TNG_THREADS = 256;
@@ -654,6 +658,9 @@ __global__ void __launch_bounds__(TNG_THREADS) tn_generic_backward_kernel(const 
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
+// 0: 3xTF32 on the tensor cores (target_network_mma.cuh, default); 1: the FP32-pipe kernels above
+static int g_tn_mode = 0;
+
 static bool tn_is_fast_shape(int n_layers, const int *dims) {
     return n_layers == 5 && dims[0] == 3 && dims[1] == C1 && dims[2] == C2 && dims[3] == C3 && dims[4] == C4 && dims[5] == 3;
 }
@@ -709,6 +716,12 @@ static int tn_generic_args(TNGenArgs &g, int n_layers, const int *dims, size_t &
 
 using namespace hp;
 
+extern "C" int hp_target_network_set_mode(int mode) {
+    HP_REQUIRE(mode == 0 || mode == 1, "hp_target_network_set_mode: mode %d is neither 0 (3xTF32 tensor cores) nor 1 (FP32 pipe)", mode);
+    g_tn_mode = mode;
+    return HP_OK;
+}
+
 extern "C" long long hp_target_network_num_weights(int n_layers, const int *dims, int use_bias) {
     if (n_layers < 1 || n_layers > TN_MAX_LAYERS || dims == nullptr) return -1;
     long long off = 0;
@@ -734,6 +747,15 @@ extern "C" int hp_target_network_forward(int b, int n, int n_layers, const int *
     cudaStream_t stream = (cudaStream_t)stream_v;
     a.weights = weights, a.points = points, a.pstride = points_batch_stride, a.out = out;
     a.B = b, a.N = n, a.channels_first = channels_first ? 1 : 0;
+    if (tn_is_fast_shape(n_layers, dims) && g_tn_mode == 0) {
+        const long long units = (long long)b * ((n + 15) / 16), sms = sm_count();
+        const unsigned grid = (unsigned)(units < sms ? units : sms);
+        static SmemAttrCache mattr;
+        HP_CUDA(ensure_dynamic_smem(tn_mma_forward_kernel, TMF_SMEM, mattr));
+        tn_mma_forward_kernel<<<grid, TMF_THREADS, TMF_SMEM, stream>>>(a);
+        HP_LAUNCH_CHECK("tn_mma_forward_kernel");
+        return HP_OK;
+    }
     if (tn_is_fast_shape(n_layers, dims)) {
         int grid;
         tn_geometry(b, n, grid, a.S);
@@ -809,7 +831,18 @@ extern "C" int hp_target_network_backward(int b, int n, int n_layers, const int 
                                               (((size_t)b * sizeof(unsigned int) + 15) & ~(size_t)15));
         // the counter region moves with b, so a reused workspace cannot be trusted to be zero there
         HP_CUDA(cudaMemsetAsync(a.counters, 0, (size_t)b * sizeof(unsigned int), stream));
-        static SmemAttrCache attr0, attr1;
+        static SmemAttrCache attr0, attr1, mattr0, mattr1;
+        if (g_tn_mode == 0) {
+            if (grad_points) {
+                HP_CUDA(ensure_dynamic_smem(tn_mma_backward_kernel<true>, TMB_SMEM, mattr1));
+                tn_mma_backward_kernel<true><<<(unsigned)grid, TMB_THREADS, TMB_SMEM, stream>>>(a);
+            } else {
+                HP_CUDA(ensure_dynamic_smem(tn_mma_backward_kernel<false>, TMB_SMEM, mattr0));
+                tn_mma_backward_kernel<false><<<(unsigned)grid, TMB_THREADS, TMB_SMEM, stream>>>(a);
+            }
+            HP_LAUNCH_CHECK("tn_mma_backward_kernel");
+            return HP_OK;
+        }
         if (grad_points) {
             HP_CUDA(ensure_dynamic_smem(tn_backward_kernel<true>, TNB_SMEM, attr1));
             tn_backward_kernel<true><<<(unsigned)grid, TN_THREADS, TNB_SMEM, stream>>>(a);

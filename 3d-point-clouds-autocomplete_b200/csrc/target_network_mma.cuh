@@ -1,0 +1,605 @@
+// target_network_mma.cuh -- the TargetNetwork fast path (3 -> 32 -> 64 -> 128 -> 64 -> 3) on the tensor cores as error-compensated
+// 3xTF32 (included by target_network.cu; shares TNArgs and the launch geometry with the FP32-pipe kernels there).
+//
+// Why it is admissible: tools/tf32x3_study.cu / profiles/r02_tf32x3_study.txt -- with every operand split into hi + lo (both tf32)
+// and lo*hi + hi*lo + hi*hi accumulated in fp32, the K = 32..128 contractions of this network stay within 2.3e-6 of the fp32 FFMA
+// chain end to end (bar: 1e-5 against torch.mm fp32, model/target_network.py:31-38); a weight-gradient contraction over all 2048 points
+// in ONE tensor-core accumulator does not (1.6e-5), so dW is accumulated per 128-point tile on the tensor cores and the tile sums are
+// added on the FP32 pipe.
+//
+// Design (mma.sync.m16n8k8 tf32; the fragment algebra is what makes it cheap):
+//   * a WARP owns 16 points and walks ALL layers for them in registers: the accumulator fragment of one layer IS the A fragment of
+//     the next.  With MMA column c of channel tile j bound to channel 8j + s(c), s(2t) = t, s(2t+1) = t+4, lane (g,t) holds
+//     C = {(g, 8j+t), (g, 8j+t+4), (g+8, 8j+t), (g+8, 8j+t+4)} -- exactly {a0, a2, a1, a3} of contraction step j of the next layer.
+//     No activation touches shared memory in the forward.
+//   * weights live in shared memory as rows of the NON-contracted index with stride = contraction length + 4 (== 4 mod 32): the B
+//     fragment (row 8j + s(g), columns 8k + t and 8k + t + 4) is two conflict-free LDS.32; hi/lo are split on the fly (the FP32 pipe is
+//     idle under the MMAs).  The backward stages each matrix a second time TRANSPOSED for the dgrad contraction (over `out`).
+//   * layer 1 (K = 3) and the 3-wide contractions of the output layer's backward run as plain FFMA in fragment layout.
+//   * BACKWARD (one CTA of 8 warps per SM, 128-point tiles): recompute the forward in registers, storing the activations of the tile to
+//     shared memory as [point][channel] rows (stride 296 == 8 mod 32) only because wgrad contracts over POINTS, which needs them
+//     transposed: dW_L[o][k] = sum_p Z_L[p][o] A_{L-1}[p][k] reads both operands straight from those rows as conflict-free fragments.
+//     The dgrad chain Z_{L-1} = relu'(A_{L-1}) * (Z_L W_L) stays in registers (ReLU gates are 144 bits per lane), Z_L overwrites A_L
+//     in shared memory for wgrad.  dW lives in 72 persistent registers per thread across the tiles of a sample; per-CTA partials of a
+//     sample shared by several CTAs are folded by the last CTA to arrive in ascending CTA order (deterministic, no float atomics).
+#pragma once
+
+namespace hp {
+
+constexpr int TMF_WARPS = 12;                 // forward CTA: 384 threads (<= 168 registers each)
+constexpr int TMF_THREADS = TMF_WARPS * 32;
+constexpr int TMB_WARPS = 8;                  // backward CTA: 256 threads (<= 255 registers each)
+constexpr int TMB_THREADS = TMB_WARPS * 32;
+constexpr int TM_ACT_LD = 296;                // activation row stride: 32 + 64 + 128 + 64 + 8, == 8 (mod 32)
+constexpr int TM_A1 = 0, TM_A2 = 32, TM_A3 = 96, TM_A4 = 224;  // column of each layer's block inside a row
+
+// x = hi + lo, hi on the tf32 grid (round to nearest, ties away: the truncated bits of x * (1 + 2^-12)), lo = x - hi EXACT in fp32.
+// The tensor core reads the top 19 bits of an operand register, i.e. it truncates lo to 11 significant bits itself: the product loses
+// 2^-22 relative, the same order as the dropped lo*lo term.  One FFMA + one LOP3 + one FADD -- sm_100 has no cvt.rna.tf32 instruction,
+// the PTX cvt expands to four half-rate ALU operations.
+__device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo) {
+    hi = __float_as_uint(__fmaf_rn(x, 0x1p-12f, x)) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += a * b with a = ah + al, b = bh + bl: the small cross terms first, al*bl dropped (2^-22 relative)
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
+                                           uint32_t bl0, uint32_t bl1) {
+    mma_tf32(c, al, bh0, bh1);
+    mma_tf32(c, ah, bl0, bl1);
+    mma_tf32(c, ah, bh0, bh1);
+}
+
+__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// W[O][K] (flat, row-major) -> rows of `out` with stride K+4
+template <int K, int O, int NT>
+__device__ __forceinline__ void tm_stage_nat(const float *__restrict__ Wg, float *__restrict__ dst, int tid) {
+    for (int i = tid; i < O * K; i += NT) {
+        const int o = i / K, k = i - o * K;
+        cp_async4(dst + o * (K + 4) + k, Wg + i);
+    }
+}
+// W[O][K] -> its transpose, rows of `in` with stride O+4
+template <int K, int O, int NT>
+__device__ __forceinline__ void tm_stage_tr(const float *__restrict__ Wg, float *__restrict__ dst, int tid) {
+    for (int i = tid; i < O * K; i += NT) {
+        const int o = i / K, k = i - o * K;
+        cp_async4(dst + k * (O + 4) + o, Wg + i);
+    }
+}
+
+// One contraction of the register chain: acc[j] += in (16 points x K, fragment layout) * Ws^T, Ws = rows of the N non-contracted
+// channels, stride K+4.  wl = Ws + s(g)*(K+4) + t.
+template <int K, int N>
+__device__ __forceinline__ void tm_layer(const float (&in)[K / 8][4], float (&acc)[N / 8][4], const float *__restrict__ wl) {
+    constexpr int LD = K + 4;
+#pragma unroll
+    for (int ks = 0; ks < K / 8; ++ks) {
+        uint32_t ah[4], al[4];
+        tf32_split(in[ks][0], ah[0], al[0]);  // a0 = (g,   t)
+        tf32_split(in[ks][2], ah[1], al[1]);  // a1 = (g+8, t)
+        tf32_split(in[ks][1], ah[2], al[2]);  // a2 = (g,   t+4)
+        tf32_split(in[ks][3], ah[3], al[3]);  // a3 = (g+8, t+4)
+#pragma unroll
+        for (int j = 0; j < N / 8; ++j) {
+            uint32_t bh0, bl0, bh1, bl1;
+            tf32_split(wl[j * 8 * LD + ks * 8], bh0, bl0);
+            tf32_split(wl[j * 8 * LD + ks * 8 + 4], bh1, bl1);
+            mma_3xtf32(acc[j], ah, al, bh0, bh1, bl0, bl1);
+        }
+    }
+}
+
+template <int NTL>
+__device__ __forceinline__ void tm_init_bias(float (&acc)[NTL][4], const float *__restrict__ bias, int t) {
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) {
+        const float b0 = bias[8 * j + t], b1 = bias[8 * j + t + 4];
+        acc[j][0] = b0, acc[j][1] = b1, acc[j][2] = b0, acc[j][3] = b1;
+    }
+}
+template <int NTL>
+__device__ __forceinline__ void tm_zero(float (&acc)[NTL][4]) {
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+}
+// ReLU in place; returns the gate bits (bit 4j + r)
+template <int NTL>
+__device__ __forceinline__ unsigned long long tm_relu(float (&v)[NTL][4]) {
+    unsigned long long m = 0;
+#pragma unroll
+    for (int j = 0; j < NTL; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const bool on = v[j][r] > 0.f;
+            v[j][r] = on ? v[j][r] : 0.f;
+            m |= (unsigned long long)on << (4 * j + r);
+        }
+    return m;
+}
+template <int NTL>
+__device__ __forceinline__ void tm_relu_only(float (&v)[NTL][4]) {
+#pragma unroll
+    for (int j = 0; j < NTL; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[j][r] = fmaxf(v[j][r], 0.f);
+}
+template <int NTL>
+__device__ __forceinline__ void tm_gate(float (&v)[NTL][4], unsigned long long m) {
+#pragma unroll
+    for (int j = 0; j < NTL; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[j][r] = ((m >> (4 * j + r)) & 1ull) ? v[j][r] : 0.f;
+}
+// fragment -> shared rows; row0 = act + (16*warp + g)*LD + column of the layer + t
+template <int NTL>
+__device__ __forceinline__ void tm_store_rows(float *__restrict__ row0, const float (&v)[NTL][4]) {
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) {
+        row0[8 * j] = v[j][0], row0[8 * j + 4] = v[j][1];
+        row0[8 * TM_ACT_LD + 8 * j] = v[j][2], row0[8 * TM_ACT_LD + 8 * j + 4] = v[j][3];
+    }
+}
+
+// layer 1 (K = 3) on the FP32 pipe, in fragment layout.  w1p: [32][4] = (w0, w1, w2, bias)
+__device__ __forceinline__ void tm_layer1(const float (&x0)[3], const float (&x1)[3], float (&a1)[4][4], const float *__restrict__ w1p, int t) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 wa = *reinterpret_cast<const float4 *>(w1p + (8 * j + t) * 4);
+        const float4 wb = *reinterpret_cast<const float4 *>(w1p + (8 * j + t + 4) * 4);
+        a1[j][0] = __fmaf_rn(wa.z, x0[2], __fmaf_rn(wa.y, x0[1], __fmaf_rn(wa.x, x0[0], wa.w)));
+        a1[j][1] = __fmaf_rn(wb.z, x0[2], __fmaf_rn(wb.y, x0[1], __fmaf_rn(wb.x, x0[0], wb.w)));
+        a1[j][2] = __fmaf_rn(wa.z, x1[2], __fmaf_rn(wa.y, x1[1], __fmaf_rn(wa.x, x1[0], wa.w)));
+        a1[j][3] = __fmaf_rn(wb.z, x1[2], __fmaf_rn(wb.y, x1[1], __fmaf_rn(wb.x, x1[0], wb.w)));
+    }
+}
+
+// ---- forward ------------------------------------------------------------------------------------------------------------------
+// shared-memory map of ONE sample's weights (floats); two of these (current sample / next sample being prefetched)
+constexpr int TMF_W1P = 0;                               // [32][4]
+constexpr int TMF_W2 = TMF_W1P + C1 * 4;                 // [64][36]
+constexpr int TMF_W3 = TMF_W2 + C2 * (C1 + 4);           // [128][68]
+constexpr int TMF_W4 = TMF_W3 + C3 * (C2 + 4);           // [64][132]
+constexpr int TMF_W5 = TMF_W4 + C4 * (C3 + 4);           // [8][68], rows 3..7 zero
+constexpr int TMF_B = TMF_W5 + 8 * (C4 + 4);             // b2[64] b3[128] b4[64] b5[8]
+constexpr int TMF_FLOATS = TMF_B + C2 + C3 + C4 + 8;
+constexpr size_t TMF_SMEM = (size_t)2 * TMF_FLOATS * sizeof(float);
+static_assert(TMF_SMEM <= 227 * 1024, "forward weights (double buffered) do not fit in shared memory");
+
+// stage sample b's weights into S: matrices with cp.async, the constant parts with plain stores
+template <int NT>
+__device__ __forceinline__ void tmf_stage(const TNArgs &a, int b, float *__restrict__ S, int tid) {
+    const float *wg = a.weights + (size_t)b * a.W;
+    for (int i = tid; i < C1 * 4; i += NT) {
+        const int o = i >> 2, c = i & 3;
+        if (c < 3) cp_async4(S + TMF_W1P + i, wg + a.offw[0] + o * 3 + c);
+        else if (a.offb[0] >= 0) cp_async4(S + TMF_W1P + i, wg + a.offb[0] + o);
+        else S[TMF_W1P + i] = 0.f;
+    }
+    tm_stage_nat<C1, C2, NT>(wg + a.offw[1], S + TMF_W2, tid);
+    tm_stage_nat<C2, C3, NT>(wg + a.offw[2], S + TMF_W3, tid);
+    tm_stage_nat<C3, C4, NT>(wg + a.offw[3], S + TMF_W4, tid);
+    tm_stage_nat<C4, 3, NT>(wg + a.offw[4], S + TMF_W5, tid);
+    for (int i = tid; i < 5 * (C4 + 4); i += NT) S[TMF_W5 + 3 * (C4 + 4) + i] = 0.f;
+    for (int i = tid; i < C2 + C3 + C4 + 8; i += NT) {
+        int l, o;
+        if (i < C2) l = 1, o = i;
+        else if (i < C2 + C3) l = 2, o = i - C2;
+        else if (i < C2 + C3 + C4) l = 3, o = i - C2 - C3;
+        else l = 4, o = i - C2 - C3 - C4;
+        if (a.offb[l] >= 0 && !(l == 4 && o >= 3)) cp_async4(S + TMF_B + i, wg + a.offb[l] + o);
+        else S[TMF_B + i] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(TMF_THREADS, 1) tn_mma_forward_kernel(const TNArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3, sg = (g >> 1) + 4 * (g & 1);
+    // flat list of (sample, 16-point unit), sample-major, split evenly over the CTAs
+    const int upn = (a.N + 15) >> 4;
+    const long long TU = (long long)a.B * upn;
+    const long long u0 = (long long)blockIdx.x * TU / gridDim.x, u1 = (long long)(blockIdx.x + 1) * TU / gridDim.x;
+    if (u0 >= u1) return;
+    const int bfirst = (int)(u0 / upn), blast = (int)((u1 - 1) / upn);
+    tmf_stage<TMF_THREADS>(a, bfirst, sm, tid);
+    cp_async_commit();
+    int buf = 0;
+    for (int b = bfirst; b <= blast; ++b, buf ^= 1) {
+        const float *S = sm + buf * TMF_FLOATS;
+        if (b < blast) {  // prefetch the next sample's weights under this sample's math
+            tmf_stage<TMF_THREADS>(a, b + 1, sm + (buf ^ 1) * TMF_FLOATS, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const long long s0 = u0 > (long long)b * upn ? u0 : (long long)b * upn;
+        const long long s1 = u1 < (long long)(b + 1) * upn ? u1 : (long long)(b + 1) * upn;
+        const float *pts = a.points + (size_t)b * a.pstride;
+        for (long long u = s0 + warp; u < s1; u += TMF_WARPS) {
+            const int r0 = (int)(u - (long long)b * upn) * 16 + g, r1 = r0 + 8;
+            float x0[3] = {0.f, 0.f, 0.f}, x1[3] = {0.f, 0.f, 0.f};
+            if (r0 < a.N) x0[0] = __ldg(pts + (size_t)r0 * 3), x0[1] = __ldg(pts + (size_t)r0 * 3 + 1), x0[2] = __ldg(pts + (size_t)r0 * 3 + 2);
+            if (r1 < a.N) x1[0] = __ldg(pts + (size_t)r1 * 3), x1[1] = __ldg(pts + (size_t)r1 * 3 + 1), x1[2] = __ldg(pts + (size_t)r1 * 3 + 2);
+            float a1[4][4];
+            tm_layer1(x0, x1, a1, S + TMF_W1P, t);
+            tm_relu_only<4>(a1);
+            float a2[8][4];
+            tm_init_bias<8>(a2, S + TMF_B, t);
+            tm_layer<C1, C2>(a1, a2, S + TMF_W2 + sg * (C1 + 4) + t);
+            tm_relu_only<8>(a2);
+            float a3[16][4];
+            tm_init_bias<16>(a3, S + TMF_B + C2, t);
+            tm_layer<C2, C3>(a2, a3, S + TMF_W3 + sg * (C2 + 4) + t);
+            tm_relu_only<16>(a3);
+            float a4[8][4];
+            tm_init_bias<8>(a4, S + TMF_B + C2 + C3, t);
+            tm_layer<C3, C4>(a3, a4, S + TMF_W4 + sg * (C3 + 4) + t);
+            tm_relu_only<8>(a4);
+            float y[1][4];
+            tm_init_bias<1>(y, S + TMF_B + C2 + C3 + C4, t);
+            tm_layer<C4, 8>(a4, y, S + TMF_W5 + sg * (C4 + 4) + t);
+            if (t < 3) {  // lane (g,t) holds coordinate t of rows r0 (y[0][0]) and r1 (y[0][2])
+                if (a.channels_first) {
+                    float *dst = a.out + ((size_t)b * 3 + t) * a.N;
+                    if (r0 < a.N) dst[r0] = y[0][0];
+                    if (r1 < a.N) dst[r1] = y[0][2];
+                } else {
+                    float *dst = a.out + (size_t)b * a.N * 3 + t;
+                    if (r0 < a.N) dst[(size_t)r0 * 3] = y[0][0];
+                    if (r1 < a.N) dst[(size_t)r1 * 3] = y[0][2];
+                }
+            }
+        }
+        __syncthreads();  // every reader of S is done before the staging of sample b+2 lands in it
+    }
+}
+
+// ---- backward -----------------------------------------------------------------------------------------------------------------
+constexpr int TMB_ACT = 0;                                  // [128][296]
+constexpr int TMB_WB0 = TMB_ACT + TN_T * TM_ACT_LD;         // 8704
+constexpr int TMB_WSZ = C3 * (C2 + 4);                      // 8704 >= 64*132, 128*68, 64*132
+constexpr int TMB_WB1 = TMB_WB0 + TMB_WSZ;
+constexpr int TMB_XS = TMB_WB1 + TMB_WSZ;                   // [128][4] (x, y, z, 0)
+constexpr int TMB_GS = TMB_XS + TN_T * 4;                   // [128][4] upstream gradient of the 3 output coordinates
+constexpr int TMB_W1P = TMB_GS + TN_T * 4;                  // [32][4]
+constexpr int TMB_W5 = TMB_W1P + C1 * 4;                    // [3][64]
+constexpr int TMB_B = TMB_W5 + 3 * C4;                      // b2[64] b3[128] b4[64]
+constexpr int TMB_FLOATS = TMB_B + C2 + C3 + C4;
+constexpr size_t TMB_SMEM = (size_t)TMB_FLOATS * sizeof(float);
+static_assert(TMB_SMEM + 2048 <= 227 * 1024, "backward tile does not fit in shared memory");
+static_assert(C4 * (C3 + 4) <= TMB_WSZ && C2 * (C3 + 4) <= TMB_WSZ, "weight buffer");
+
+// dW tile: acc[mi*NT+ni] += sum over the tile's 128 points of Z[p][zc + 16mi + g (+8)] * A[p][ac + 8ni + 2t (+1)]
+template <int MT, int NT>
+__device__ __forceinline__ void tm_wgrad(const float *__restrict__ act, int zc, int ac, float (&acc)[MT * NT][4], int g, int t) {
+    const float *zr = act + t * TM_ACT_LD + zc + g;
+    const float *ar = act + t * TM_ACT_LD + ac + g;
+#pragma unroll 2
+    for (int p0 = 0; p0 < TN_T; p0 += 8) {
+        uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+            tf32_split(zr[p0 * TM_ACT_LD + 16 * mi], ah[mi][0], al[mi][0]);                      // (o = g,   p = t)
+            tf32_split(zr[p0 * TM_ACT_LD + 16 * mi + 8], ah[mi][1], al[mi][1]);                  // (o = g+8, p = t)
+            tf32_split(zr[(p0 + 4) * TM_ACT_LD + 16 * mi], ah[mi][2], al[mi][2]);                // (o = g,   p = t+4)
+            tf32_split(zr[(p0 + 4) * TM_ACT_LD + 16 * mi + 8], ah[mi][3], al[mi][3]);            // (o = g+8, p = t+4)
+        }
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+            uint32_t bh0, bl0, bh1, bl1;
+            tf32_split(ar[p0 * TM_ACT_LD + 8 * ni], bh0, bl0);        // (p = t,   k = g)
+            tf32_split(ar[(p0 + 4) * TM_ACT_LD + 8 * ni], bh1, bl1);  // (p = t+4, k = g)
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi) mma_3xtf32(acc[mi * NT + ni], ah[mi], al[mi], bh0, bh1, bl0, bl1);
+        }
+    }
+}
+template <int MT, int NT>
+__device__ __forceinline__ void tm_fold(float (&pers)[MT * NT][4], const float (&acc)[MT * NT][4]) {
+#pragma unroll
+    for (int i = 0; i < MT * NT; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) pers[i][r] += acc[i][r];
+}
+// persistent fragment -> dW[O][K] (flat): rows o0 + 16mi + g (+8), columns k0 + 8ni + 2t (+1)
+template <int MT, int NT, int K>
+__device__ __forceinline__ void tm_store_dw(const float (&pers)[MT * NT][4], float *__restrict__ dst, int o0, int k0, int g, int t) {
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+            float *d = dst + (o0 + 16 * mi + g) * K + k0 + 8 * ni + 2 * t;
+            d[0] = pers[mi * NT + ni][0], d[1] = pers[mi * NT + ni][1];
+            d[8 * K] = pers[mi * NT + ni][2], d[8 * K + 1] = pers[mi * NT + ni][3];
+        }
+}
+// column sum over the tile's 128 rows
+__device__ __forceinline__ float tm_col_sum(const float *__restrict__ col) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+    for (int p = 0; p < TN_T; p += 4) {
+        s0 += col[p * TM_ACT_LD], s1 += col[(p + 1) * TM_ACT_LD];
+        s2 += col[(p + 2) * TM_ACT_LD], s3 += col[(p + 3) * TM_ACT_LD];
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+template <bool GRAD_POINTS>
+__global__ void __launch_bounds__(TMB_THREADS, 1) tn_mma_backward_kernel(const TNArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float *act = sm + TMB_ACT, *wb0 = sm + TMB_WB0, *wb1 = sm + TMB_WB1, *xs = sm + TMB_XS, *gs = sm + TMB_GS;
+    float *w1p = sm + TMB_W1P, *w5 = sm + TMB_W5, *bs = sm + TMB_B;
+    __shared__ int is_last;
+    __shared__ unsigned int slot_of[TN_MAX_GRID];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3, sg = (g >> 1) + 4 * (g & 1);
+    const int ntiles = (a.N + TN_T - 1) / TN_T;
+    const long long TT = (long long)a.B * ntiles;
+    const long long G = gridDim.x;
+    const long long f0 = (long long)blockIdx.x * TT / G, f1 = (long long)(blockIdx.x + 1) * TT / G;
+    const int first_sample = (int)(f0 / ntiles);
+
+    // persistent weight gradients of the current sample: dW4[64][128] (warp: 32 x 32), dW3[128][64] (32 x 32), dW2[64][32] (16 x 16)
+    float pw4[8][4], pw3[8][4], pw2[2][4];
+    // small gradients, one element per thread:  sA: db4 (tid 0-63) | db2 (64-127) | db1 (128-159) | db5 (160-162)
+    //                                           sB: dW1 (0-95) | db3 (128-255)        sC: dW5 (0-191)
+    float sA, sB, sC;
+    auto reset_acc = [&]() {
+        tm_zero<8>(pw4), tm_zero<8>(pw3), tm_zero<2>(pw2);
+        sA = sB = sC = 0.f;
+    };
+    auto flush = [&](int b) {
+        const long long s0 = (long long)b * ntiles, s1 = s0 + ntiles - 1;
+        const int c_lo = (int)(((s0 + 1) * G - 1) / TT), c_hi = (int)(((s1 + 1) * G - 1) / TT);
+        const bool shared_sample = c_lo != c_hi;
+        float *dst = shared_sample ? a.partial + ((size_t)blockIdx.x * a.S + (b - first_sample)) * a.W : a.gweights + (size_t)b * a.W;
+        tm_store_dw<2, 4, C3>(pw4, dst + a.offw[3], (warp & 1) * 32, (warp >> 1) * 32, g, t);
+        tm_store_dw<2, 4, C2>(pw3, dst + a.offw[2], (warp & 3) * 32, (warp >> 2) * 32, g, t);
+        tm_store_dw<1, 2, C1>(pw2, dst + a.offw[1], (warp & 3) * 16, (warp >> 2) * 16, g, t);
+        if (tid < 192) dst[a.offw[4] + tid] = sC;                     // dW5[c][k] at c*64 + k
+        if (tid < 96) dst[a.offw[0] + tid] = sB;                      // dW1[o][c] at o*3 + c
+        else if (tid >= 128 && a.offb[2] >= 0) dst[a.offb[2] + tid - 128] = sB;
+        if (tid < 64) { if (a.offb[3] >= 0) dst[a.offb[3] + tid] = sA; }
+        else if (tid < 128) { if (a.offb[1] >= 0) dst[a.offb[1] + tid - 64] = sA; }
+        else if (tid < 160) { if (a.offb[0] >= 0) dst[a.offb[0] + tid - 128] = sA; }
+        else if (tid < 163) { if (a.offb[4] >= 0) dst[a.offb[4] + tid - 160] = sA; }
+        if (shared_sample) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) is_last = (atomicAdd(a.counters + b, 1u) == (unsigned)(c_hi - c_lo));
+            __syncthreads();
+            if (is_last) {
+                __threadfence();
+                const int ncontrib = c_hi - c_lo + 1;
+                for (int q = tid; q < ncontrib; q += TMB_THREADS) {
+                    const int c = c_lo + q;
+                    const int fs = (int)(((long long)c * TT / G) / ntiles);
+                    slot_of[q] = (unsigned)(c * a.S + (b - fs));
+                }
+                __syncthreads();
+                float *gw = a.gweights + (size_t)b * a.W;
+                for (int i = tid; i < a.W; i += TMB_THREADS) {
+                    float v = 0.f;
+                    for (int q = 0; q < ncontrib; ++q) v += __ldcg(a.partial + (size_t)slot_of[q] * a.W + i);  // ascending CTA order
+                    gw[i] = v;
+                }
+            }
+            __syncthreads();
+        }
+    };
+
+    reset_acc();
+    int cur = -1;
+    for (long long f = f0; f < f1; ++f) {
+        const int b = (int)(f / ntiles), tl = (int)(f - (long long)b * ntiles);
+        const float *wg = a.weights + (size_t)b * a.W;
+        __syncthreads();  // previous tile fully consumed
+        if (b != cur) {
+            if (cur >= 0) {
+                flush(cur);
+                reset_acc();
+            }
+            for (int i = tid; i < C1 * 4; i += TMB_THREADS) {
+                const int o = i >> 2, c = i & 3;
+                w1p[i] = c < 3 ? __ldg(wg + a.offw[0] + o * 3 + c) : (a.offb[0] >= 0 ? __ldg(wg + a.offb[0] + o) : 0.f);
+            }
+            for (int i = tid; i < 3 * C4; i += TMB_THREADS) w5[i] = __ldg(wg + a.offw[4] + i);
+            for (int i = tid; i < C2 + C3 + C4; i += TMB_THREADS) {
+                int l, o;
+                if (i < C2) l = 1, o = i;
+                else if (i < C2 + C3) l = 2, o = i - C2;
+                else l = 3, o = i - C2 - C3;
+                bs[i] = a.offb[l] >= 0 ? __ldg(wg + a.offb[l] + o) : 0.f;
+            }
+            cur = b;
+        }
+        const int n0 = tl * TN_T;
+        // ---- t0: W2 -> wb0, W3 -> wb1; the tile's points and upstream gradients ----
+        tm_stage_nat<C1, C2, TMB_THREADS>(wg + a.offw[1], wb0, tid);
+        tm_stage_nat<C2, C3, TMB_THREADS>(wg + a.offw[2], wb1, tid);
+        cp_async_commit();
+        if (tid < TN_T) {
+            const int p = n0 + tid;
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+            if (p < a.N) {
+                const float *px = a.points + (size_t)b * a.pstride + (size_t)p * 3;
+                xv.x = __ldg(px), xv.y = __ldg(px + 1), xv.z = __ldg(px + 2);
+                if (a.channels_first) {
+                    const float *pg = a.gout + (size_t)b * 3 * a.N + p;
+                    gv.x = __ldg(pg), gv.y = __ldg(pg + a.N), gv.z = __ldg(pg + 2 * (size_t)a.N);
+                } else {
+                    const float *pg = a.gout + ((size_t)b * a.N + p) * 3;
+                    gv.x = __ldg(pg), gv.y = __ldg(pg + 1), gv.z = __ldg(pg + 2);
+                }
+            }
+            *reinterpret_cast<float4 *>(xs + tid * 4) = xv;
+            *reinterpret_cast<float4 *>(gs + tid * 4) = gv;
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        // ---- forward recompute, in registers; activations also go to shared memory for wgrad ----
+        float *row0 = act + (16 * warp + g) * TM_ACT_LD + t;
+        unsigned int m1, m2, m4;
+        unsigned long long m3;
+        float a2[8][4];
+        {
+            float a1[4][4];
+            {
+                const float4 p0 = *reinterpret_cast<const float4 *>(xs + (16 * warp + g) * 4);
+                const float4 p1 = *reinterpret_cast<const float4 *>(xs + (16 * warp + g + 8) * 4);
+                const float x0[3] = {p0.x, p0.y, p0.z}, x1[3] = {p1.x, p1.y, p1.z};
+                tm_layer1(x0, x1, a1, w1p, t);
+            }
+            m1 = (unsigned int)tm_relu<4>(a1);
+            tm_store_rows<4>(row0 + TM_A1, a1);
+            tm_init_bias<8>(a2, bs, t);
+            tm_layer<C1, C2>(a1, a2, wb0 + sg * (C1 + 4) + t);
+        }
+        m2 = (unsigned int)tm_relu<8>(a2);
+        tm_store_rows<8>(row0 + TM_A2, a2);
+        __syncthreads();  // wb0 (W2) free
+        tm_stage_nat<C3, C4, TMB_THREADS>(wg + a.offw[3], wb0, tid);  // W4 -> wb0, under layer 3
+        cp_async_commit();
+        float a4[8][4];
+        {
+            float a3[16][4];
+            tm_init_bias<16>(a3, bs + C2, t);
+            tm_layer<C2, C3>(a2, a3, wb1 + sg * (C2 + 4) + t);
+            m3 = tm_relu<16>(a3);
+            tm_store_rows<16>(row0 + TM_A3, a3);
+            cp_async_wait<0>();
+            __syncthreads();  // W4 landed; wb1 (W3) free
+            tm_stage_tr<C3, C4, TMB_THREADS>(wg + a.offw[3], wb1, tid);  // W4^T -> wb1, under layer 4
+            cp_async_commit();
+            tm_init_bias<8>(a4, bs + C2 + C3, t);
+            tm_layer<C3, C4>(a3, a4, wb0 + sg * (C3 + 4) + t);
+        }
+        m4 = (unsigned int)tm_relu<8>(a4);
+        tm_store_rows<8>(row0 + TM_A4, a4);
+        // ---- layer 5: Z5 = dY.  Z4 = gate4 * (dY W5) in fragment layout, K = 3 on the FP32 pipe ----
+        float z4[8][4];
+        {
+            const float4 g0 = *reinterpret_cast<const float4 *>(gs + (16 * warp + g) * 4);
+            const float4 g1 = *reinterpret_cast<const float4 *>(gs + (16 * warp + g + 8) * 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ca = 8 * j + t, cb = ca + 4;
+                const float wa0 = w5[ca], wa1 = w5[C4 + ca], wa2 = w5[2 * C4 + ca];
+                const float wb0_ = w5[cb], wb1_ = w5[C4 + cb], wb2_ = w5[2 * C4 + cb];
+                z4[j][0] = __fmaf_rn(g0.z, wa2, __fmaf_rn(g0.y, wa1, g0.x * wa0));
+                z4[j][1] = __fmaf_rn(g0.z, wb2_, __fmaf_rn(g0.y, wb1_, g0.x * wb0_));
+                z4[j][2] = __fmaf_rn(g1.z, wa2, __fmaf_rn(g1.y, wa1, g1.x * wa0));
+                z4[j][3] = __fmaf_rn(g1.z, wb2_, __fmaf_rn(g1.y, wb1_, g1.x * wb0_));
+            }
+            tm_gate<8>(z4, m4);
+        }
+        cp_async_wait<0>();
+        __syncthreads();  // A4 of the whole tile visible; W4^T landed; wb0 (W4) free
+        tm_stage_tr<C2, C3, TMB_THREADS>(wg + a.offw[2], wb0, tid);  // W3^T -> wb0
+        cp_async_commit();
+        if (tid < 192) {  // dW5[c][k] += sum_p dY[p][c] A4[p][k]
+            const int c = tid >> 6, k = tid & 63;
+            float s = 0.f;
+#pragma unroll 8
+            for (int p = 0; p < TN_T; ++p) s = __fmaf_rn(gs[p * 4 + c], act[p * TM_ACT_LD + TM_A4 + k], s);
+            sC += s;
+        }
+        if (tid >= 160 && tid < 163) {  // db5
+            float s = 0.f;
+            for (int p = 0; p < TN_T; ++p) s += gs[p * 4 + tid - 160];
+            sA += s;
+        }
+        __syncthreads();  // every reader of A4 is done
+        tm_store_rows<8>(row0 + TM_A4, z4);
+        __syncthreads();  // Z4 visible
+        // ---- layer 4: dW4 += Z4^T A3, db4; Z3 = gate3 * (Z4 W4) ----
+        {
+            float acc[8][4];
+            tm_zero<8>(acc);
+            tm_wgrad<2, 4>(act, TM_A4 + (warp & 1) * 32, TM_A3 + (warp >> 1) * 32, acc, g, t);
+            tm_fold<2, 4>(pw4, acc);
+        }
+        if (tid < 64) sA += tm_col_sum(act + TM_A4 + tid);
+        float z2[8][4];
+        {
+            float z3[16][4];
+            tm_zero<16>(z3);
+            tm_layer<C4, C3>(z4, z3, wb1 + sg * (C4 + 4) + t);
+            tm_gate<16>(z3, m3);
+            cp_async_wait<0>();
+            __syncthreads();  // every reader of A3 is done; W3^T landed; wb1 (W4^T) free
+            tm_store_rows<16>(row0 + TM_A3, z3);
+            tm_stage_tr<C1, C2, TMB_THREADS>(wg + a.offw[1], wb1, tid);  // W2^T -> wb1
+            cp_async_commit();
+            __syncthreads();  // Z3 visible
+            // ---- layer 3: dW3 += Z3^T A2, db3; Z2 = gate2 * (Z3 W3) ----
+            {
+                float acc[8][4];
+                tm_zero<8>(acc);
+                tm_wgrad<2, 4>(act, TM_A3 + (warp & 3) * 32, TM_A2 + (warp >> 2) * 32, acc, g, t);
+                tm_fold<2, 4>(pw3, acc);
+            }
+            if (tid >= 128) sB += tm_col_sum(act + TM_A3 + tid - 128);
+            tm_zero<8>(z2);
+            tm_layer<C3, C2>(z3, z2, wb0 + sg * (C3 + 4) + t);
+        }
+        tm_gate<8>(z2, m2);
+        cp_async_wait<0>();
+        __syncthreads();  // every reader of A2 is done; W2^T landed
+        tm_store_rows<8>(row0 + TM_A2, z2);
+        __syncthreads();  // Z2 visible
+        // ---- layer 2: dW2 += Z2^T A1, db2; Z1 = gate1 * (Z2 W2) ----
+        {
+            float acc[2][4];
+            tm_zero<2>(acc);
+            tm_wgrad<1, 2>(act, TM_A2 + (warp & 3) * 16, TM_A1 + (warp >> 2) * 16, acc, g, t);
+            tm_fold<1, 2>(pw2, acc);
+        }
+        if (tid >= 64 && tid < 128) sA += tm_col_sum(act + TM_A2 + tid - 64);
+        {
+            float z1[4][4];
+            tm_zero<4>(z1);
+            tm_layer<C2, C1>(z2, z1, wb1 + sg * (C2 + 4) + t);
+            tm_gate<4>(z1, m1);
+            __syncthreads();  // every reader of A1 is done
+            tm_store_rows<4>(row0 + TM_A1, z1);
+        }
+        __syncthreads();  // Z1 visible
+        // ---- layer 1: dW1 += Z1^T X, db1, optionally dX = Z1 W1 ----
+        if (tid < 96) {
+            const int o = tid / 3, c = tid - o * 3;
+            float s = 0.f;
+#pragma unroll 8
+            for (int p = 0; p < TN_T; ++p) s = __fmaf_rn(act[p * TM_ACT_LD + TM_A1 + o], xs[p * 4 + c], s);
+            sB += s;
+        } else if (tid >= 128 && tid < 160) {
+            sA += tm_col_sum(act + TM_A1 + tid - 128);
+        }
+        if (GRAD_POINTS) {
+            for (int i = tid; i < 3 * TN_T; i += TMB_THREADS) {
+                const int p = i / 3, c = i - p * 3;
+                float sx = 0.f;
+#pragma unroll 8
+                for (int o = 0; o < C1; ++o) sx = __fmaf_rn(act[p * TM_ACT_LD + TM_A1 + o], w1p[o * 4 + c], sx);
+                if (n0 + p < a.N) a.gpoints[((size_t)b * a.N + n0 + p) * 3 + c] = sx;
+            }
+        }
+    }
+    if (cur >= 0) flush(cur);
+}
+
+}  // namespace hp

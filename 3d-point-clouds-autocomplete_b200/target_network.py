@@ -31,6 +31,15 @@ def _c_dims(layer_out_channels):
     return (ctypes.c_int * len(dims))(*dims), len(dims) - 1
 
 
+def target_network_set_mode(mode: str) -> None:
+    """Arithmetic of the tuned 32,64,128,64 kernels, process-wide: "tf32x3" (default: error-compensated 3xTF32 on the tensor
+    cores, within 3e-6 of the reference's fp32 torch.mm chain) or "fp32" (FFMA chains on the CUDA cores)."""
+    modes = {"tf32x3": 0, "fp32": 1}
+    if mode not in modes:
+        raise ValueError(f"mode must be one of {sorted(modes)}")
+    _native.check(_native.load().hp_target_network_set_mode(modes[mode]), "hp_target_network_set_mode")
+
+
 def target_network_num_weights(layer_out_channels: Sequence[int], use_bias: bool = True) -> int:
     """Length of one sample's flat weight vector (19011 for 32,64,128,64 with bias)."""
     cd, nl = _c_dims(layer_out_channels)

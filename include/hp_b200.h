@@ -209,6 +209,14 @@ HP_API int hp_emd_cost_pairs_fast(int pairs, int n, int m, const float *first, c
  * (target_network.py:40-45); hp_target_network_num_weights() is its length (19011 for 32,64,128,64). */
 HP_API long long hp_target_network_num_weights(int n_layers, const int *dims_host, int use_bias);
 
+/* Arithmetic of the tuned 3,32,64,128,64,3 kernels (process-wide; other widths always run the generic FP32 kernels):
+ *   0 (default)  error-compensated 3xTF32 on the tensor cores (every operand split into hi + lo, three mma.sync per product,
+ *                fp32 accumulation; weight gradients accumulated per 128-point tile and summed in fp32): within 3e-6 of the
+ *                fp32 torch.mm chain of target_network.py:31-38 (measured, profiles/r02_tf32x3_study.txt; bar 1e-5);
+ *   1            plain fp32 FFMA chains on the CUDA cores (round-1 kernels).
+ * Returns HP_ERR_INVALID_ARGUMENT for any other value. */
+HP_API int hp_target_network_set_mode(int mode);
+
 /* out[s] = TargetNetwork(weights[s]).forward(points[s]) for s in [0,b): ReLU after every layer but the
  * last (target_network.py:31-38).  ONE launch for the whole batch, no activation goes to HBM.
  *   weights [b, W];  points [b, n, 3] with points_batch_stride = 3n floats, or one shared cloud

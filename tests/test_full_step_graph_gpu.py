@@ -1,0 +1,81 @@
+"""GPU: FullModelStepGraph (BASELINE config C4 as one CUDA graph: stock encoder + hypernetwork (fused head) + fused TargetNetwork +
+Chamfer fwd/bwd + backward + Adam) against the SAME step run eagerly with the reference's own FullModel class, its own per-sample
+TargetNetwork loop and its own pure-torch ChamferLoss (unmodified files from baseline/_ref) on the same inputs and the same
+TargetNetwork input points: losses along a short training trajectory and the parameters after it."""
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEV = "cuda:0"
+
+
+def test_graph_step_follows_the_reference_trainer(hp):
+    sys.path.insert(0, REPO)
+    from baseline import ref_loader
+
+    if ref_loader.ref_root() is None:
+        pytest.skip("baseline/_ref not staged")
+    tree = ref_loader.reference_tree()
+    cfg = ref_loader.full_model_config("config_completion.json.sample")
+    bsz, n_in, n_gt, steps, epoch = 6, 300, 512, 4, 3
+
+    def make(cls):
+        torch.manual_seed(1856)
+        m = cls(json.loads(json.dumps(cfg)))
+        m.apply(ref_loader.weights_init)
+        return m.to(DEV).train()
+
+    g = torch.Generator().manual_seed(4)
+    existing = (torch.rand(bsz, n_in, 3, generator=g) - 0.5).to(DEV)
+    gt = (torch.rand(bsz, n_gt, 3, generator=g) - 0.5).to(DEV)
+
+    # ---- the reference trainer's step (core/epoch_loops.py:14-39), eager, reference classes only ----
+    ref_model = make(tree.RefFullModel)
+    ref_opt = torch.optim.Adam(ref_model.parameters(), lr=1e-4)
+    ref_loss_fn = tree.RefChamferLoss().to(DEV)
+    torch.manual_seed(77)  # the TargetNetwork input points come from the global CPU RNG, sample by sample
+    ref_losses = []
+    for _ in range(steps):
+        ref_opt.zero_grad()
+        rec, _lv, _mu = ref_model(existing.clone(), None, list(gt.shape), epoch, DEV)
+        loss = torch.mean(0.05 * ref_loss_fn(gt, rec.permute(0, 2, 1)))
+        loss.backward()
+        ref_opt.step()
+        ref_losses.append(float(loss))
+
+    # ---- ours: one graph replay per step ----
+    model = make(tree.OurFullModel)
+    hp.fuse_hypernetwork_head(model.hyper_network)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    step = hp.FullModelStepGraph(model, opt, bsz, n_in, 0, n_gt, DEV, loss_coef=0.05)
+    # capture ran warm-up steps that moved the parameters and the Adam state: rewind both
+    with torch.no_grad():
+        for k, v in model.state_dict().items():
+            v.copy_(state0[k])
+        for st in opt.state.values():
+            for t in st.values():
+                if torch.is_tensor(t):
+                    t.zero_()
+    step.existing.copy_(existing.transpose(1, 2))
+    step.gt.copy_(gt)
+    torch.manual_seed(77)
+    ours = []
+    for _ in range(steps):
+        step.load_points(epoch)
+        step.replay()
+        ours.append(float(step.loss_r))
+    torch.cuda.synchronize()
+    # Chamfer: direct form here, expansion form there (1e-6 on the loss); the trajectories may drift apart by the usual fp32 noise
+    for i, (a, b) in enumerate(zip(ours, ref_losses)):
+        assert a == pytest.approx(b, rel=2e-4 if i else 1e-5), (i, ours, ref_losses)
+    assert ours[-1] < ours[0]  # it trains
+    for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref_model.named_parameters()):
+        assert n1 == n2
+        assert float((p1 - p2).abs().max()) <= 2e-3 * max(float(p2.abs().max()), 1e-6), n1
+    assert step.rec.shape == (bsz, n_gt, 3)

@@ -11,6 +11,8 @@ hp = importlib.import_module("3d-point-clouds-autocomplete_b200")
 LOC = [32, 64, 128, 64]
 N = 2048
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+hp.target_network_set_mode(os.environ.get("HP_TN_MODE", "tf32x3"))
+print("mode", os.environ.get("HP_TN_MODE", "tf32x3"))
 
 
 def timeit(fn, reps=reps, warm=3):
