@@ -86,5 +86,5 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=(), be
 
 if __name__ == "__main__":
     p = build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
-                      extra_flags=["-Xptxas", "-v"] if "--ptxas-v" in sys.argv else ())
+                      extra_flags=(["-Xptxas", "-v"] if "--ptxas-v" in sys.argv else []) + os.environ.get("HP_EXTRA_NVCC_FLAGS", "").split())
     print(p)

@@ -33,25 +33,28 @@ constexpr int TMB_THREADS = TMB_WARPS * 32;
 constexpr int TM_ACT_LD = 296;                // activation row stride: 32 + 64 + 128 + 64 + 8, == 8 (mod 32)
 constexpr int TM_A1 = 0, TM_A2 = 32, TM_A3 = 96, TM_A4 = 224;  // column of each layer's block inside a row
 
-// x = hi + lo, hi on the tf32 grid (round to nearest, ties away: the truncated bits of x * (1 + 2^-12)), lo = x - hi EXACT in fp32.
-// The tensor core reads the top 19 bits of an operand register, i.e. it truncates lo to 11 significant bits itself: the product loses
-// 2^-22 relative, the same order as the dropped lo*lo term.  One FFMA + one LOP3 + one FADD -- sm_100 has no cvt.rna.tf32 instruction,
-// the PTX cvt expands to four half-rate ALU operations.
+// Operand split for 3xTF32.  The tensor core reads only the top 19 bits of an operand register (it TRUNCATES fp32 to tf32), so
+//   hi: the fp32 value itself is passed -- the hardware sees trunc_tf32(x);
+//   lo: x - trunc_tf32(x), exact in fp32 (one LOP3 + one FADD), of which the hardware again keeps the top 11 significant bits.
+// x*y ~ hi_x*hi_y + hi_x*lo_y + lo_x*hi_y with a relative defect <= 2^-20 (mean 2^-22 per operand, towards zero) -- the same order
+// as the dropped lo*lo term.  sm_100 has no cvt.rna.tf32 instruction (the PTX cvt expands to four half-rate ALU operations), and
+// a round-to-nearest hi would cost a third operation per element for an error budget that is not needed (measured worst case of the
+// whole network against float64, tools/tn_error_margins.py: see DESIGN.md 4.3; bar 1e-5).
+#ifndef HP_TM_ROUNDED_SPLIT
+__device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo) {
+    hi = __float_as_uint(x);
+    lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
+}
+#else  // hi rounded to nearest (ties away): the truncated bits of x * (1 + 2^-12); FFMA + LOP3 + FADD
 __device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo) {
     hi = __float_as_uint(__fmaf_rn(x, 0x1p-12f, x)) & 0xffffe000u;
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
+#endif
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-// c += a * b with a = ah + al, b = bh + bl: the small cross terms first, al*bl dropped (2^-22 relative)
-__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
-                                           uint32_t bl0, uint32_t bl1) {
-    mma_tf32(c, al, bh0, bh1);
-    mma_tf32(c, ah, bl0, bl1);
-    mma_tf32(c, ah, bh0, bh1);
 }
 
 __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src) {
@@ -80,10 +83,12 @@ __device__ __forceinline__ void tm_stage_tr(const float *__restrict__ Wg, float 
 }
 
 // One contraction of the register chain: acc[j] += in (16 points x K, fragment layout) * Ws^T, Ws = rows of the N non-contracted
-// channels, stride K+4.  wl = Ws + s(g)*(K+4) + t.
+// channels, stride K+4.  wl = Ws + s(g)*(K+4) + t.  Channel tiles go in groups of JG: the three products of a group are issued
+// term by term (lo*hi of all tiles, hi*lo of all, hi*hi of all), so that back-to-back MMAs never share an accumulator.
 template <int K, int N>
 __device__ __forceinline__ void tm_layer(const float (&in)[K / 8][4], float (&acc)[N / 8][4], const float *__restrict__ wl) {
     constexpr int LD = K + 4;
+    constexpr int NTL = N / 8, JG = NTL >= 4 ? 4 : NTL;
 #pragma unroll
     for (int ks = 0; ks < K / 8; ++ks) {
         uint32_t ah[4], al[4];
@@ -92,11 +97,19 @@ __device__ __forceinline__ void tm_layer(const float (&in)[K / 8][4], float (&ac
         tf32_split(in[ks][1], ah[2], al[2]);  // a2 = (g,   t+4)
         tf32_split(in[ks][3], ah[3], al[3]);  // a3 = (g+8, t+4)
 #pragma unroll
-        for (int j = 0; j < N / 8; ++j) {
-            uint32_t bh0, bl0, bh1, bl1;
-            tf32_split(wl[j * 8 * LD + ks * 8], bh0, bl0);
-            tf32_split(wl[j * 8 * LD + ks * 8 + 4], bh1, bl1);
-            mma_3xtf32(acc[j], ah, al, bh0, bh1, bl0, bl1);
+        for (int j0 = 0; j0 < NTL; j0 += JG) {
+            uint32_t bh[JG][2], bl[JG][2];
+#pragma unroll
+            for (int j = 0; j < JG; ++j) {
+                tf32_split(wl[(j0 + j) * 8 * LD + ks * 8], bh[j][0], bl[j][0]);
+                tf32_split(wl[(j0 + j) * 8 * LD + ks * 8 + 4], bh[j][1], bl[j][1]);
+            }
+#pragma unroll
+            for (int j = 0; j < JG; ++j) mma_tf32(acc[j0 + j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+            for (int j = 0; j < JG; ++j) mma_tf32(acc[j0 + j], ah, bl[j][0], bl[j][1]);
+#pragma unroll
+            for (int j = 0; j < JG; ++j) mma_tf32(acc[j0 + j], ah, bh[j][0], bh[j][1]);
         }
     }
 }
@@ -177,7 +190,14 @@ constexpr int TMF_FLOATS = TMF_B + C2 + C3 + C4 + 8;
 constexpr size_t TMF_SMEM = (size_t)2 * TMF_FLOATS * sizeof(float);
 static_assert(TMF_SMEM <= 227 * 1024, "forward weights (double buffered) do not fit in shared memory");
 
-// stage sample b's weights into S: matrices with cp.async, the constant parts with plain stores
+// the parts of a weight buffer that do not depend on the sample: zero rows of W5, zero biases when the network has none
+template <int NT>
+__device__ __forceinline__ void tmf_fill_const(const TNArgs &a, float *__restrict__ S, int tid) {
+    for (int i = tid; i < 5 * (C4 + 4); i += NT) S[TMF_W5 + 3 * (C4 + 4) + i] = 0.f;
+    for (int i = tid; i < C1; i += NT) S[TMF_W1P + 4 * i + 3] = 0.f;
+    for (int i = tid; i < C2 + C3 + C4 + 8; i += NT) S[TMF_B + i] = 0.f;
+}
+// stage sample b's weights into S with cp.async
 template <int NT>
 __device__ __forceinline__ void tmf_stage(const TNArgs &a, int b, float *__restrict__ S, int tid) {
     const float *wg = a.weights + (size_t)b * a.W;
@@ -185,51 +205,57 @@ __device__ __forceinline__ void tmf_stage(const TNArgs &a, int b, float *__restr
         const int o = i >> 2, c = i & 3;
         if (c < 3) cp_async4(S + TMF_W1P + i, wg + a.offw[0] + o * 3 + c);
         else if (a.offb[0] >= 0) cp_async4(S + TMF_W1P + i, wg + a.offb[0] + o);
-        else S[TMF_W1P + i] = 0.f;
     }
     tm_stage_nat<C1, C2, NT>(wg + a.offw[1], S + TMF_W2, tid);
     tm_stage_nat<C2, C3, NT>(wg + a.offw[2], S + TMF_W3, tid);
     tm_stage_nat<C3, C4, NT>(wg + a.offw[3], S + TMF_W4, tid);
     tm_stage_nat<C4, 3, NT>(wg + a.offw[4], S + TMF_W5, tid);
-    for (int i = tid; i < 5 * (C4 + 4); i += NT) S[TMF_W5 + 3 * (C4 + 4) + i] = 0.f;
-    for (int i = tid; i < C2 + C3 + C4 + 8; i += NT) {
+    for (int i = tid; i < C2 + C3 + C4 + 3; i += NT) {
         int l, o;
         if (i < C2) l = 1, o = i;
         else if (i < C2 + C3) l = 2, o = i - C2;
         else if (i < C2 + C3 + C4) l = 3, o = i - C2 - C3;
         else l = 4, o = i - C2 - C3 - C4;
-        if (a.offb[l] >= 0 && !(l == 4 && o >= 3)) cp_async4(S + TMF_B + i, wg + a.offb[l] + o);
-        else S[TMF_B + i] = 0.f;
+        if (a.offb[l] >= 0) cp_async4(S + TMF_B + i, wg + a.offb[l] + o);
     }
+}
+// the mbarrier receives one arrival from this thread once all its cp.async so far have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __global__ void __launch_bounds__(TMF_THREADS, 1) tn_mma_forward_kernel(const TNArgs a) {
     extern __shared__ __align__(16) float sm[];
+    __shared__ uint64_t bars[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3, sg = (g >> 1) + 4 * (g & 1);
-    // flat list of (sample, 16-point unit), sample-major, split evenly over the CTAs
+    // flat list of (sample, 16-point unit), sample-major, split evenly over the CTAs; a CTA walks its range two samples at a time
+    // (one weight buffer each).  Warps take units of the pair with a fixed stride and wait for the buffer a unit needs on that
+    // buffer's mbarrier, so the second sample's weights stream in under the first sample's math and no warp waits for another.
     const int upn = (a.N + 15) >> 4;
     const long long TU = (long long)a.B * upn;
     const long long u0 = (long long)blockIdx.x * TU / gridDim.x, u1 = (long long)(blockIdx.x + 1) * TU / gridDim.x;
     if (u0 >= u1) return;
     const int bfirst = (int)(u0 / upn), blast = (int)((u1 - 1) / upn);
-    tmf_stage<TMF_THREADS>(a, bfirst, sm, tid);
-    cp_async_commit();
-    int buf = 0;
-    for (int b = bfirst; b <= blast; ++b, buf ^= 1) {
-        const float *S = sm + buf * TMF_FLOATS;
-        if (b < blast) {  // prefetch the next sample's weights under this sample's math
-            tmf_stage<TMF_THREADS>(a, b + 1, sm + (buf ^ 1) * TMF_FLOATS, tid);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+    if (tid == 0) mbar_init(&bars[0], TMF_THREADS), mbar_init(&bars[1], TMF_THREADS);
+    tmf_fill_const<TMF_THREADS>(a, sm, tid);
+    tmf_fill_const<TMF_THREADS>(a, sm + TMF_FLOATS, tid);
+    __syncthreads();
+    for (int bb = bfirst, round = 0; bb <= blast; bb += 2, ++round) {
+        if (round > 0) __syncthreads();  // every warp is done with both buffers
+        tmf_stage<TMF_THREADS>(a, bb, sm, tid);
+        cp_async_mbar_arrive(&bars[0]);
+        if (bb + 1 <= blast) {
+            tmf_stage<TMF_THREADS>(a, bb + 1, sm + TMF_FLOATS, tid);
+            cp_async_mbar_arrive(&bars[1]);
         }
-        __syncthreads();
-        const long long s0 = u0 > (long long)b * upn ? u0 : (long long)b * upn;
-        const long long s1 = u1 < (long long)(b + 1) * upn ? u1 : (long long)(b + 1) * upn;
-        const float *pts = a.points + (size_t)b * a.pstride;
+        const long long s0 = u0 > (long long)bb * upn ? u0 : (long long)bb * upn;
+        const long long s1 = u1 < (long long)(bb + 2) * upn ? u1 : (long long)(bb + 2) * upn;
         for (long long u = s0 + warp; u < s1; u += TMF_WARPS) {
+            const int b = (int)(u / upn), which = b - bb;
+            const float *S = sm + which * TMF_FLOATS;
+            mbar_wait(&bars[which], round & 1);
+            const float *pts = a.points + (size_t)b * a.pstride;
             const int r0 = (int)(u - (long long)b * upn) * 16 + g, r1 = r0 + 8;
             float x0[3] = {0.f, 0.f, 0.f}, x1[3] = {0.f, 0.f, 0.f};
             if (r0 < a.N) x0[0] = __ldg(pts + (size_t)r0 * 3), x0[1] = __ldg(pts + (size_t)r0 * 3 + 1), x0[2] = __ldg(pts + (size_t)r0 * 3 + 2);
@@ -264,7 +290,6 @@ __global__ void __launch_bounds__(TMF_THREADS, 1) tn_mma_forward_kernel(const TN
                 }
             }
         }
-        __syncthreads();  // every reader of S is done before the staging of sample b+2 lands in it
     }
 }
 
@@ -298,14 +323,24 @@ __device__ __forceinline__ void tm_wgrad(const float *__restrict__ act, int zc, 
             tf32_split(zr[(p0 + 4) * TM_ACT_LD + 16 * mi], ah[mi][2], al[mi][2]);                // (o = g,   p = t+4)
             tf32_split(zr[(p0 + 4) * TM_ACT_LD + 16 * mi + 8], ah[mi][3], al[mi][3]);            // (o = g+8, p = t+4)
         }
+        uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
         for (int ni = 0; ni < NT; ++ni) {
-            uint32_t bh0, bl0, bh1, bl1;
-            tf32_split(ar[p0 * TM_ACT_LD + 8 * ni], bh0, bl0);        // (p = t,   k = g)
-            tf32_split(ar[(p0 + 4) * TM_ACT_LD + 8 * ni], bh1, bl1);  // (p = t+4, k = g)
-#pragma unroll
-            for (int mi = 0; mi < MT; ++mi) mma_3xtf32(acc[mi * NT + ni], ah[mi], al[mi], bh0, bh1, bl0, bl1);
+            tf32_split(ar[p0 * TM_ACT_LD + 8 * ni], bh[ni][0], bl[ni][0]);        // (p = t,   k = g)
+            tf32_split(ar[(p0 + 4) * TM_ACT_LD + 8 * ni], bh[ni][1], bl[ni][1]);  // (p = t+4, k = g)
         }
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi * NT + ni], al[mi], bh[ni][0], bh[ni][1]);
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi * NT + ni], ah[mi], bl[ni][0], bl[ni][1]);
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi * NT + ni], ah[mi], bh[ni][0], bh[ni][1]);
     }
 }
 template <int MT, int NT>
