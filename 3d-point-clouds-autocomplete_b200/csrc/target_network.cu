@@ -835,10 +835,10 @@ extern "C" int hp_target_network_backward(int b, int n, int n_layers, const int 
         if (g_tn_mode == 0) {
             if (grad_points) {
                 HP_CUDA(ensure_dynamic_smem(tn_mma_backward_kernel<true>, TMB_SMEM, mattr1));
-                tn_mma_backward_kernel<true><<<(unsigned)grid, TMB_THREADS, TMB_SMEM, stream>>>(a);
+                tn_mma_backward_kernel<true><<<(unsigned)grid, TMB_ALL_THREADS, TMB_SMEM, stream>>>(a);
             } else {
                 HP_CUDA(ensure_dynamic_smem(tn_mma_backward_kernel<false>, TMB_SMEM, mattr0));
-                tn_mma_backward_kernel<false><<<(unsigned)grid, TMB_THREADS, TMB_SMEM, stream>>>(a);
+                tn_mma_backward_kernel<false><<<(unsigned)grid, TMB_ALL_THREADS, TMB_SMEM, stream>>>(a);
             }
             HP_LAUNCH_CHECK("tn_mma_backward_kernel");
             return HP_OK;

@@ -28,10 +28,6 @@ namespace hp {
 
 constexpr int TMF_WARPS = 12;                 // forward CTA: 384 threads (<= 168 registers each)
 constexpr int TMF_THREADS = TMF_WARPS * 32;
-constexpr int TMB_WARPS = 8;                  // backward CTA: 256 threads (<= 255 registers each)
-constexpr int TMB_THREADS = TMB_WARPS * 32;
-constexpr int TM_ACT_LD = 296;                // activation row stride: 32 + 64 + 128 + 64 + 8, == 8 (mod 32)
-constexpr int TM_A1 = 0, TM_A2 = 32, TM_A3 = 96, TM_A4 = 224;  // column of each layer's block inside a row
 
 // Operand split for 3xTF32.  The tensor core reads only the top 19 bits of an operand register (it TRUNCATES fp32 to tf32), so
 //   hi: the fp32 value itself is passed -- the hardware sees trunc_tf32(x);
@@ -155,16 +151,6 @@ __device__ __forceinline__ void tm_gate(float (&v)[NTL][4], unsigned long long m
 #pragma unroll
         for (int r = 0; r < 4; ++r) v[j][r] = ((m >> (4 * j + r)) & 1ull) ? v[j][r] : 0.f;
 }
-// fragment -> shared rows; row0 = act + (16*warp + g)*LD + column of the layer + t
-template <int NTL>
-__device__ __forceinline__ void tm_store_rows(float *__restrict__ row0, const float (&v)[NTL][4]) {
-#pragma unroll
-    for (int j = 0; j < NTL; ++j) {
-        row0[8 * j] = v[j][0], row0[8 * j + 4] = v[j][1];
-        row0[8 * TM_ACT_LD + 8 * j] = v[j][2], row0[8 * TM_ACT_LD + 8 * j + 4] = v[j][3];
-    }
-}
-
 // layer 1 (K = 3) on the FP32 pipe, in fragment layout.  w1p: [32][4] = (w0, w1, w2, bias)
 __device__ __forceinline__ void tm_layer1(const float (&x0)[3], const float (&x1)[3], float (&a1)[4][4], const float *__restrict__ w1p, int t) {
 #pragma unroll
@@ -294,9 +280,25 @@ __global__ void __launch_bounds__(TMF_THREADS, 1) tn_mma_forward_kernel(const TN
 }
 
 // ---- backward -----------------------------------------------------------------------------------------------------------------
+// One CTA of 12 warps per SM, 128-point tiles, two roles:
+//   * warps 0-7, the CHAIN: forward recompute and dgrad of 16 points each, in registers (as the forward kernel).  They store the
+//     tile's activations -- and later, in the same places, its pre-activation gradients Z_L -- to shared memory as [point][channel]
+//     rows (stride 296 == 8 mod 32), only because wgrad contracts over POINTS and therefore needs them transposed;
+//   * warps 8-11, the WGRAD helpers: dW_L[o][k] = sum_p Z_L[p][o] A_{L-1}[p][k] reads both operands straight from those rows as
+//     conflict-free tensor-core fragments.  A tile's sum is accumulated on the tensor cores, then added in fp32 to the sample's
+//     running gradient, which lives in TENSOR MEMORY (144 columns of the helper's own lanes, tcgen05.ld / tcgen05.st): no persistent
+//     registers, so all 12 warps fit at 168 registers.  The helpers also own the small gradients (biases, the 3-wide layers).
+// Per tile every warp issues the same number of MMAs (1728: chain 864 + 864, helper 768 + 768 + 192), three warps per scheduler.
+// Hand-over of a block of rows between the roles is a pair of named barriers (the writer arrives on FULL after its stores, the reader
+// syncs on it; the reader arrives on EMPTY when it is done, the writer syncs on it before it overwrites the block in place).
+constexpr int TMB_CHAIN_WARPS = 8, TMB_CHAIN_THREADS = 256;
+constexpr int TMB_HELP_THREADS = 128;
+constexpr int TMB_ALL_THREADS = TMB_CHAIN_THREADS + TMB_HELP_THREADS;  // 384
+constexpr int TM_ACT_LD = 296;                // activation row stride: 32 + 64 + 128 + 64 + 8, == 8 (mod 32)
+constexpr int TM_A1 = 0, TM_A2 = 32, TM_A3 = 96, TM_A4 = 224;  // column of each layer's block inside a row
 constexpr int TMB_ACT = 0;                                  // [128][296]
-constexpr int TMB_WB0 = TMB_ACT + TN_T * TM_ACT_LD;         // 8704
-constexpr int TMB_WSZ = C3 * (C2 + 4);                      // 8704 >= 64*132, 128*68, 64*132
+constexpr int TMB_WB0 = TMB_ACT + TN_T * TM_ACT_LD;
+constexpr int TMB_WSZ = C3 * (C2 + 4);                      // 8704 >= 64*132 (W4, W3^T), 128*68 (W3, W4^T)
 constexpr int TMB_WB1 = TMB_WB0 + TMB_WSZ;
 constexpr int TMB_XS = TMB_WB1 + TMB_WSZ;                   // [128][4] (x, y, z, 0)
 constexpr int TMB_GS = TMB_XS + TN_T * 4;                   // [128][4] upstream gradient of the 3 output coordinates
@@ -307,13 +309,70 @@ constexpr int TMB_FLOATS = TMB_B + C2 + C3 + C4;
 constexpr size_t TMB_SMEM = (size_t)TMB_FLOATS * sizeof(float);
 static_assert(TMB_SMEM + 2048 <= 227 * 1024, "backward tile does not fit in shared memory");
 static_assert(C4 * (C3 + 4) <= TMB_WSZ && C2 * (C3 + 4) <= TMB_WSZ, "weight buffer");
+// named barriers (0 is __syncthreads)
+enum : int { TMB_BAR_CHAIN = 1, TMB_BAR_TILE_EMPTY, TMB_BAR_A4_FULL, TMB_BAR_A4_EMPTY, TMB_BAR_Z4_FULL, TMB_BAR_A3_EMPTY,
+             TMB_BAR_Z3_FULL, TMB_BAR_A2_EMPTY, TMB_BAR_Z2_FULL, TMB_BAR_A1_EMPTY, TMB_BAR_Z1_FULL, TMB_BAR_HELPERS };
 
-// dW tile: acc[mi*NT+ni] += sum over the tile's 128 points of Z[p][zc + 16mi + g (+8)] * A[p][ac + 8ni + 2t (+1)]
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) {
+    __threadfence_block();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// ---- tensor memory as thread-private storage: each thread of a warp owns the columns of its own lane ----
+#define HP_R16(v, o) "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), \
+                     "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]), "=r"(v[o + 12]),            \
+                     "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15])
+#define HP_I16(v, o) "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]),        \
+                     "r"(v[o + 7]), "r"(v[o + 8]), "r"(v[o + 9]), "r"(v[o + 10]), "r"(v[o + 11]), "r"(v[o + 12]), "r"(v[o + 13]),   \
+                     "r"(v[o + 14]), "r"(v[o + 15])
+// N (a multiple of 16) consecutive columns of this thread's lane <-> registers
+template <int N>
+__device__ __forceinline__ void tmem_load(uint32_t taddr, uint32_t (&v)[N]) {
+#pragma unroll
+    for (int o = 0; o < N; o += 16)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : HP_R16(v, o)
+                     : "r"(taddr + o));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_store(uint32_t taddr, const uint32_t (&v)[N]) {
+#pragma unroll
+    for (int o = 0; o < N; o += 16)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr + o),
+                     HP_I16(v, o)
+                     : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// columns [taddr, taddr + 4*TILES) += acc (the tile's tensor-core sum joins the sample's running fp32 gradient)
+template <int TILES>
+__device__ __forceinline__ void tmem_accumulate(uint32_t taddr, const float (&acc)[TILES][4]) {
+#pragma unroll
+    for (int h = 0; h < TILES * 4; h += 16) {
+        uint32_t v[16];
+        tmem_load<16>(taddr + h, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + acc[(h + i) >> 2][(h + i) & 3]);
+        tmem_store<16>(taddr + h, v);
+    }
+}
+
+// fragment -> shared rows; row0 = act + (16*warp + g)*LD + column of the layer + t
+template <int NTL>
+__device__ __forceinline__ void tm_store_rows(float *__restrict__ row0, const float (&v)[NTL][4]) {
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) {
+        row0[8 * j] = v[j][0], row0[8 * j + 4] = v[j][1];
+        row0[8 * TM_ACT_LD + 8 * j] = v[j][2], row0[8 * TM_ACT_LD + 8 * j + 4] = v[j][3];
+    }
+}
+// dW tile on the tensor cores: acc[mi*NT+ni] += sum over the tile's 128 points of Z[p][zc + 16mi + g (+8)] * A[p][ac + 8ni + 2t (+1)]
 template <int MT, int NT>
 __device__ __forceinline__ void tm_wgrad(const float *__restrict__ act, int zc, int ac, float (&acc)[MT * NT][4], int g, int t) {
     const float *zr = act + t * TM_ACT_LD + zc + g;
     const float *ar = act + t * TM_ACT_LD + ac + g;
-#pragma unroll 2
+#pragma unroll 1
     for (int p0 = 0; p0 < TN_T; p0 += 8) {
         uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
@@ -343,24 +402,24 @@ __device__ __forceinline__ void tm_wgrad(const float *__restrict__ act, int zc, 
             for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi * NT + ni], ah[mi], bh[ni][0], bh[ni][1]);
     }
 }
-template <int MT, int NT>
-__device__ __forceinline__ void tm_fold(float (&pers)[MT * NT][4], const float (&acc)[MT * NT][4]) {
-#pragma unroll
-    for (int i = 0; i < MT * NT; ++i)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) pers[i][r] += acc[i][r];
-}
-// persistent fragment -> dW[O][K] (flat): rows o0 + 16mi + g (+8), columns k0 + 8ni + 2t (+1)
+// running gradient (tensor memory) -> dW[O][K] (flat): rows o0 + 16mi + g (+8), columns k0 + 8ni + 2t (+1); the columns are cleared
 template <int MT, int NT, int K>
-__device__ __forceinline__ void tm_store_dw(const float (&pers)[MT * NT][4], float *__restrict__ dst, int o0, int k0, int g, int t) {
+__device__ __forceinline__ void tm_flush_dw(uint32_t taddr, float *__restrict__ dst, int o0, int k0, int g, int t) {
 #pragma unroll
-    for (int mi = 0; mi < MT; ++mi)
+    for (int h = 0; h < MT * NT * 4; h += 16) {
+        uint32_t v[16];
+        tmem_load<16>(taddr + h, v);
 #pragma unroll
-        for (int ni = 0; ni < NT; ++ni) {
+        for (int q = 0; q < 4; ++q) {
+            const int tile = (h >> 2) + q, mi = tile / NT, ni = tile - mi * NT;
             float *d = dst + (o0 + 16 * mi + g) * K + k0 + 8 * ni + 2 * t;
-            d[0] = pers[mi * NT + ni][0], d[1] = pers[mi * NT + ni][1];
-            d[8 * K] = pers[mi * NT + ni][2], d[8 * K + 1] = pers[mi * NT + ni][3];
+            d[0] = __uint_as_float(v[4 * q]), d[1] = __uint_as_float(v[4 * q + 1]);
+            d[8 * K] = __uint_as_float(v[4 * q + 2]), d[8 * K + 1] = __uint_as_float(v[4 * q + 3]);
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0u;
+        tmem_store<16>(taddr + h, v);
+    }
 }
 // column sum over the tile's 128 rows
 __device__ __forceinline__ float tm_col_sum(const float *__restrict__ col) {
@@ -374,44 +433,63 @@ __device__ __forceinline__ float tm_col_sum(const float *__restrict__ col) {
 }
 
 template <bool GRAD_POINTS>
-__global__ void __launch_bounds__(TMB_THREADS, 1) tn_mma_backward_kernel(const TNArgs a) {
+__global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(const TNArgs a) {
     extern __shared__ __align__(16) float sm[];
     float *act = sm + TMB_ACT, *wb0 = sm + TMB_WB0, *wb1 = sm + TMB_WB1, *xs = sm + TMB_XS, *gs = sm + TMB_GS;
     float *w1p = sm + TMB_W1P, *w5 = sm + TMB_W5, *bs = sm + TMB_B;
     __shared__ int is_last;
+    __shared__ uint32_t tmem_base_slot;
     __shared__ unsigned int slot_of[TN_MAX_GRID];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3, sg = (g >> 1) + 4 * (g & 1);
+    const bool helper = warp >= TMB_CHAIN_WARPS;
+    const int ht = tid - TMB_CHAIN_THREADS, hw = warp - TMB_CHAIN_WARPS;  // helper thread / warp index
     const int ntiles = (a.N + TN_T - 1) / TN_T;
     const long long TT = (long long)a.B * ntiles;
     const long long G = gridDim.x;
     const long long f0 = (long long)blockIdx.x * TT / G, f1 = (long long)(blockIdx.x + 1) * TT / G;
     const int first_sample = (int)(f0 / ntiles);
 
-    // persistent weight gradients of the current sample: dW4[64][128] (warp: 32 x 32), dW3[128][64] (32 x 32), dW2[64][32] (16 x 16)
-    float pw4[8][4], pw3[8][4], pw2[2][4];
-    // small gradients, one element per thread:  sA: db4 (tid 0-63) | db2 (64-127) | db1 (128-159) | db5 (160-162)
-    //                                           sB: dW1 (0-95) | db3 (128-255)        sC: dW5 (0-191)
-    float sA, sB, sC;
-    auto reset_acc = [&]() {
-        tm_zero<8>(pw4), tm_zero<8>(pw3), tm_zero<2>(pw2);
-        sA = sB = sC = 0.f;
-    };
+    // tensor memory: 256 columns; helper warp hw owns lanes 32*hw.. of them (columns 0-63 dW4, 64-127 dW3, 128-143 dW2)
+    if (warp == TMB_CHAIN_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm = tmem_base_slot + ((uint32_t)(32 * (hw & 3)) << 16);
+    // helpers: small gradients, a few elements per thread
+    //   sC0: dW5[ht] | sC1: dW5[128 + ht] (ht < 64) | sB: db3[ht] | sA0: db4[ht] (ht < 64), db2[ht - 64] | sA1: db1[ht] (ht < 32), db5[ht - 32] (< 35)
+    //   sD: dW1[ht] (ht < 96)
+    float sC0 = 0.f, sC1 = 0.f, sB = 0.f, sA0 = 0.f, sA1 = 0.f, sD = 0.f;
+    if (helper) {
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+        for (int c = 0; c < 144; c += 16) tmem_store<16>(tm + c, z);
+    }
+    // Write the sample's gradient (helpers) and, when other CTAs also hold tiles of it, fold the partials (everybody).
     auto flush = [&](int b) {
         const long long s0 = (long long)b * ntiles, s1 = s0 + ntiles - 1;
         const int c_lo = (int)(((s0 + 1) * G - 1) / TT), c_hi = (int)(((s1 + 1) * G - 1) / TT);
         const bool shared_sample = c_lo != c_hi;
-        float *dst = shared_sample ? a.partial + ((size_t)blockIdx.x * a.S + (b - first_sample)) * a.W : a.gweights + (size_t)b * a.W;
-        tm_store_dw<2, 4, C3>(pw4, dst + a.offw[3], (warp & 1) * 32, (warp >> 1) * 32, g, t);
-        tm_store_dw<2, 4, C2>(pw3, dst + a.offw[2], (warp & 3) * 32, (warp >> 2) * 32, g, t);
-        tm_store_dw<1, 2, C1>(pw2, dst + a.offw[1], (warp & 3) * 16, (warp >> 2) * 16, g, t);
-        if (tid < 192) dst[a.offw[4] + tid] = sC;                     // dW5[c][k] at c*64 + k
-        if (tid < 96) dst[a.offw[0] + tid] = sB;                      // dW1[o][c] at o*3 + c
-        else if (tid >= 128 && a.offb[2] >= 0) dst[a.offb[2] + tid - 128] = sB;
-        if (tid < 64) { if (a.offb[3] >= 0) dst[a.offb[3] + tid] = sA; }
-        else if (tid < 128) { if (a.offb[1] >= 0) dst[a.offb[1] + tid - 64] = sA; }
-        else if (tid < 160) { if (a.offb[0] >= 0) dst[a.offb[0] + tid - 128] = sA; }
-        else if (tid < 163) { if (a.offb[4] >= 0) dst[a.offb[4] + tid - 160] = sA; }
+        if (helper) {
+            float *dst = shared_sample ? a.partial + ((size_t)blockIdx.x * a.S + (b - first_sample)) * a.W : a.gweights + (size_t)b * a.W;
+            tm_flush_dw<4, 4, C3>(tm, dst + a.offw[3], 0, hw * 32, g, t);
+            tm_flush_dw<4, 4, C2>(tm + 64, dst + a.offw[2], (hw & 1) * 64, (hw >> 1) * 32, g, t);
+            tm_flush_dw<4, 1, C1>(tm + 128, dst + a.offw[1], 0, hw * 8, g, t);
+            dst[a.offw[4] + ht] = sC0;
+            if (ht < 64) dst[a.offw[4] + 128 + ht] = sC1;
+            if (a.offb[2] >= 0) dst[a.offb[2] + ht] = sB;
+            if (ht < 64) { if (a.offb[3] >= 0) dst[a.offb[3] + ht] = sA0; }
+            else { if (a.offb[1] >= 0) dst[a.offb[1] + ht - 64] = sA0; }
+            if (ht < 32) { if (a.offb[0] >= 0) dst[a.offb[0] + ht] = sA1; }
+            else if (ht < 35) { if (a.offb[4] >= 0) dst[a.offb[4] + ht - 32] = sA1; }
+            if (ht < 96) dst[a.offw[0] + ht] = sD;
+            sC0 = sC1 = sB = sA0 = sA1 = sD = 0.f;
+        }
         if (shared_sample) {
             __threadfence();
             __syncthreads();
@@ -420,14 +498,14 @@ __global__ void __launch_bounds__(TMB_THREADS, 1) tn_mma_backward_kernel(const T
             if (is_last) {
                 __threadfence();
                 const int ncontrib = c_hi - c_lo + 1;
-                for (int q = tid; q < ncontrib; q += TMB_THREADS) {
+                for (int q = tid; q < ncontrib; q += TMB_ALL_THREADS) {
                     const int c = c_lo + q;
                     const int fs = (int)(((long long)c * TT / G) / ntiles);
                     slot_of[q] = (unsigned)(c * a.S + (b - fs));
                 }
                 __syncthreads();
                 float *gw = a.gweights + (size_t)b * a.W;
-                for (int i = tid; i < a.W; i += TMB_THREADS) {
+                for (int i = tid; i < a.W; i += TMB_ALL_THREADS) {
                     float v = 0.f;
                     for (int q = 0; q < ncontrib; ++q) v += __ldcg(a.partial + (size_t)slot_of[q] * a.W + i);  // ascending CTA order
                     gw[i] = v;
@@ -437,204 +515,243 @@ __global__ void __launch_bounds__(TMB_THREADS, 1) tn_mma_backward_kernel(const T
         }
     };
 
-    reset_acc();
     int cur = -1;
-    for (long long f = f0; f < f1; ++f) {
-        const int b = (int)(f / ntiles), tl = (int)(f - (long long)b * ntiles);
-        const float *wg = a.weights + (size_t)b * a.W;
-        __syncthreads();  // previous tile fully consumed
-        if (b != cur) {
-            if (cur >= 0) {
-                flush(cur);
-                reset_acc();
+    if (!helper) {
+        // =========================================== CHAIN ===========================================
+        for (long long f = f0; f < f1; ++f) {
+            const int b = (int)(f / ntiles), tl = (int)(f - (long long)b * ntiles);
+            const float *wg = a.weights + (size_t)b * a.W;
+            if (f != f0) named_sync(TMB_BAR_TILE_EMPTY, TMB_ALL_THREADS);  // the helpers are done with the previous tile
+            if (b != cur) {
+                if (cur >= 0) flush(cur);
+                for (int i = tid; i < C1 * 4; i += TMB_CHAIN_THREADS) {
+                    const int o = i >> 2, c = i & 3;
+                    w1p[i] = c < 3 ? __ldg(wg + a.offw[0] + o * 3 + c) : (a.offb[0] >= 0 ? __ldg(wg + a.offb[0] + o) : 0.f);
+                }
+                for (int i = tid; i < 3 * C4; i += TMB_CHAIN_THREADS) w5[i] = __ldg(wg + a.offw[4] + i);
+                for (int i = tid; i < C2 + C3 + C4; i += TMB_CHAIN_THREADS) {
+                    int l, o;
+                    if (i < C2) l = 1, o = i;
+                    else if (i < C2 + C3) l = 2, o = i - C2;
+                    else l = 3, o = i - C2 - C3;
+                    bs[i] = a.offb[l] >= 0 ? __ldg(wg + a.offb[l] + o) : 0.f;
+                }
+                cur = b;
             }
-            for (int i = tid; i < C1 * 4; i += TMB_THREADS) {
-                const int o = i >> 2, c = i & 3;
-                w1p[i] = c < 3 ? __ldg(wg + a.offw[0] + o * 3 + c) : (a.offb[0] >= 0 ? __ldg(wg + a.offb[0] + o) : 0.f);
+            const int n0 = tl * TN_T;
+            // ---- W2 -> wb0, W3 -> wb1; the tile's points and upstream gradients ----
+            tm_stage_nat<C1, C2, TMB_CHAIN_THREADS>(wg + a.offw[1], wb0, tid);
+            tm_stage_nat<C2, C3, TMB_CHAIN_THREADS>(wg + a.offw[2], wb1, tid);
+            cp_async_commit();
+            if (tid < TN_T) {
+                const int p = n0 + tid;
+                float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+                if (p < a.N) {
+                    const float *px = a.points + (size_t)b * a.pstride + (size_t)p * 3;
+                    xv.x = __ldg(px), xv.y = __ldg(px + 1), xv.z = __ldg(px + 2);
+                    if (a.channels_first) {
+                        const float *pg = a.gout + (size_t)b * 3 * a.N + p;
+                        gv.x = __ldg(pg), gv.y = __ldg(pg + a.N), gv.z = __ldg(pg + 2 * (size_t)a.N);
+                    } else {
+                        const float *pg = a.gout + ((size_t)b * a.N + p) * 3;
+                        gv.x = __ldg(pg), gv.y = __ldg(pg + 1), gv.z = __ldg(pg + 2);
+                    }
+                }
+                *reinterpret_cast<float4 *>(xs + tid * 4) = xv;
+                *reinterpret_cast<float4 *>(gs + tid * 4) = gv;
             }
-            for (int i = tid; i < 3 * C4; i += TMB_THREADS) w5[i] = __ldg(wg + a.offw[4] + i);
-            for (int i = tid; i < C2 + C3 + C4; i += TMB_THREADS) {
-                int l, o;
-                if (i < C2) l = 1, o = i;
-                else if (i < C2 + C3) l = 2, o = i - C2;
-                else l = 3, o = i - C2 - C3;
-                bs[i] = a.offb[l] >= 0 ? __ldg(wg + a.offb[l] + o) : 0.f;
+            cp_async_wait<0>();
+            named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);
+            // ---- forward recompute in registers; the activations also go to shared memory for wgrad ----
+            float *row0 = act + (16 * warp + g) * TM_ACT_LD + t;
+            unsigned int m1, m2, m4;
+            unsigned long long m3;
+            float a2[8][4];
+            {
+                float a1[4][4];
+                {
+                    const float4 p0 = *reinterpret_cast<const float4 *>(xs + (16 * warp + g) * 4);
+                    const float4 p1 = *reinterpret_cast<const float4 *>(xs + (16 * warp + g + 8) * 4);
+                    const float x0[3] = {p0.x, p0.y, p0.z}, x1[3] = {p1.x, p1.y, p1.z};
+                    tm_layer1(x0, x1, a1, w1p, t);
+                }
+                m1 = (unsigned int)tm_relu<4>(a1);
+                tm_store_rows<4>(row0 + TM_A1, a1);
+                tm_init_bias<8>(a2, bs, t);
+                tm_layer<C1, C2>(a1, a2, wb0 + sg * (C1 + 4) + t);
             }
-            cur = b;
+            m2 = (unsigned int)tm_relu<8>(a2);
+            tm_store_rows<8>(row0 + TM_A2, a2);
+            named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // wb0 (W2) free
+            tm_stage_nat<C3, C4, TMB_CHAIN_THREADS>(wg + a.offw[3], wb0, tid);  // W4 -> wb0, under layer 3
+            cp_async_commit();
+            float z4[8][4];
+            {
+                float a4[8][4];
+                {
+                    float a3[16][4];
+                    tm_init_bias<16>(a3, bs + C2, t);
+                    tm_layer<C2, C3>(a2, a3, wb1 + sg * (C2 + 4) + t);
+                    m3 = tm_relu<16>(a3);
+                    tm_store_rows<16>(row0 + TM_A3, a3);
+                    cp_async_wait<0>();
+                    named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // W4 landed; wb1 (W3) free
+                    tm_stage_tr<C3, C4, TMB_CHAIN_THREADS>(wg + a.offw[3], wb1, tid);  // W4^T -> wb1, under layer 4
+                    cp_async_commit();
+                    tm_init_bias<8>(a4, bs + C2 + C3, t);
+                    tm_layer<C3, C4>(a3, a4, wb0 + sg * (C3 + 4) + t);
+                }
+                m4 = (unsigned int)tm_relu<8>(a4);
+                tm_store_rows<8>(row0 + TM_A4, a4);
+            }
+            named_arrive(TMB_BAR_A4_FULL, TMB_ALL_THREADS);  // A1..A4, xs, gs of this warp's rows are in place
+            // ---- layer 5: Z5 = dY.  Z4 = gate4 * (dY W5) in fragment layout, K = 3 on the FP32 pipe ----
+            {
+                const float4 g0 = *reinterpret_cast<const float4 *>(gs + (16 * warp + g) * 4);
+                const float4 g1 = *reinterpret_cast<const float4 *>(gs + (16 * warp + g + 8) * 4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int ca = 8 * j + t, cb = ca + 4;
+                    const float wa0 = w5[ca], wa1 = w5[C4 + ca], wa2 = w5[2 * C4 + ca];
+                    const float wc0 = w5[cb], wc1 = w5[C4 + cb], wc2 = w5[2 * C4 + cb];
+                    z4[j][0] = __fmaf_rn(g0.z, wa2, __fmaf_rn(g0.y, wa1, g0.x * wa0));
+                    z4[j][1] = __fmaf_rn(g0.z, wc2, __fmaf_rn(g0.y, wc1, g0.x * wc0));
+                    z4[j][2] = __fmaf_rn(g1.z, wa2, __fmaf_rn(g1.y, wa1, g1.x * wa0));
+                    z4[j][3] = __fmaf_rn(g1.z, wc2, __fmaf_rn(g1.y, wc1, g1.x * wc0));
+                }
+                tm_gate<8>(z4, m4);
+            }
+            cp_async_wait<0>();
+            named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // W4^T landed; wb0 (W4) free
+            tm_stage_tr<C2, C3, TMB_CHAIN_THREADS>(wg + a.offw[2], wb0, tid);  // W3^T -> wb0
+            cp_async_commit();
+            named_sync(TMB_BAR_A4_EMPTY, TMB_ALL_THREADS);  // the helpers have read A4 (dW5)
+            tm_store_rows<8>(row0 + TM_A4, z4);
+            named_arrive(TMB_BAR_Z4_FULL, TMB_ALL_THREADS);
+            // ---- layer 4: Z3 = gate3 * (Z4 W4) while the helpers take dW4 = Z4^T A3 ----
+            float z2[8][4];
+            {
+                float z3[16][4];
+                tm_zero<16>(z3);
+                tm_layer<C4, C3>(z4, z3, wb1 + sg * (C4 + 4) + t);
+                tm_gate<16>(z3, m3);
+                cp_async_wait<0>();
+                named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // W3^T landed; wb1 (W4^T) free
+                tm_stage_tr<C1, C2, TMB_CHAIN_THREADS>(wg + a.offw[1], wb1, tid);  // W2^T -> wb1
+                cp_async_commit();
+                named_sync(TMB_BAR_A3_EMPTY, TMB_ALL_THREADS);  // the helpers have read A3 (and Z4)
+                tm_store_rows<16>(row0 + TM_A3, z3);
+                named_arrive(TMB_BAR_Z3_FULL, TMB_ALL_THREADS);
+                // ---- layer 3: Z2 = gate2 * (Z3 W3) ----
+                tm_zero<8>(z2);
+                tm_layer<C3, C2>(z3, z2, wb0 + sg * (C3 + 4) + t);
+            }
+            tm_gate<8>(z2, m2);
+            cp_async_wait<0>();
+            named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // W2^T landed
+            named_sync(TMB_BAR_A2_EMPTY, TMB_ALL_THREADS);
+            tm_store_rows<8>(row0 + TM_A2, z2);
+            named_arrive(TMB_BAR_Z2_FULL, TMB_ALL_THREADS);
+            // ---- layer 2: Z1 = gate1 * (Z2 W2) ----
+            {
+                float z1[4][4];
+                tm_zero<4>(z1);
+                tm_layer<C2, C1>(z2, z1, wb1 + sg * (C2 + 4) + t);
+                tm_gate<4>(z1, m1);
+                named_sync(TMB_BAR_A1_EMPTY, TMB_ALL_THREADS);
+                tm_store_rows<4>(row0 + TM_A1, z1);
+            }
+            named_arrive(TMB_BAR_Z1_FULL, TMB_ALL_THREADS);
+            named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // every chain warp is done with wb1 / w1p / w5 / bs before the next tile restages
         }
-        const int n0 = tl * TN_T;
-        // ---- t0: W2 -> wb0, W3 -> wb1; the tile's points and upstream gradients ----
-        tm_stage_nat<C1, C2, TMB_THREADS>(wg + a.offw[1], wb0, tid);
-        tm_stage_nat<C2, C3, TMB_THREADS>(wg + a.offw[2], wb1, tid);
-        cp_async_commit();
-        if (tid < TN_T) {
-            const int p = n0 + tid;
-            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
-            if (p < a.N) {
-                const float *px = a.points + (size_t)b * a.pstride + (size_t)p * 3;
-                xv.x = __ldg(px), xv.y = __ldg(px + 1), xv.z = __ldg(px + 2);
-                if (a.channels_first) {
-                    const float *pg = a.gout + (size_t)b * 3 * a.N + p;
-                    gv.x = __ldg(pg), gv.y = __ldg(pg + a.N), gv.z = __ldg(pg + 2 * (size_t)a.N);
-                } else {
-                    const float *pg = a.gout + ((size_t)b * a.N + p) * 3;
-                    gv.x = __ldg(pg), gv.y = __ldg(pg + 1), gv.z = __ldg(pg + 2);
+    } else {
+        // =========================================== WGRAD HELPERS ===========================================
+        for (long long f = f0; f < f1; ++f) {
+            const int b = (int)(f / ntiles), tl = (int)(f - (long long)b * ntiles);
+            if (b != cur) {
+                if (cur >= 0) flush(cur);
+                cur = b;
+            }
+            const int n0 = tl * TN_T;
+            // ---- layer 5: dW5[c][k] += sum_p dY[p][c] A4[p][k], db5 ----
+            named_sync(TMB_BAR_A4_FULL, TMB_ALL_THREADS);
+            {
+                const int c0 = ht >> 6, k0 = ht & 63;  // elements ht and 128 + ht (row 2) of dW5[3][64]
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                for (int p = 0; p < TN_T; ++p) {
+                    const float av = act[p * TM_ACT_LD + TM_A4 + k0];
+                    s0 = __fmaf_rn(gs[p * 4 + c0], av, s0);
+                    s1 = __fmaf_rn(gs[p * 4 + 2], av, s1);
+                }
+                sC0 += s0;
+                if (ht < 64) sC1 += s1;
+                if (ht >= 32 && ht < 35) {
+                    float s = 0.f;
+                    for (int p = 0; p < TN_T; ++p) s += gs[p * 4 + ht - 32];
+                    sA1 += s;
                 }
             }
-            *reinterpret_cast<float4 *>(xs + tid * 4) = xv;
-            *reinterpret_cast<float4 *>(gs + tid * 4) = gv;
-        }
-        cp_async_wait<0>();
-        __syncthreads();
-        // ---- forward recompute, in registers; activations also go to shared memory for wgrad ----
-        float *row0 = act + (16 * warp + g) * TM_ACT_LD + t;
-        unsigned int m1, m2, m4;
-        unsigned long long m3;
-        float a2[8][4];
-        {
-            float a1[4][4];
+            named_arrive(TMB_BAR_A4_EMPTY, TMB_ALL_THREADS);
+            // ---- layer 4: dW4 += Z4^T A3, db4 ----
+            named_sync(TMB_BAR_Z4_FULL, TMB_ALL_THREADS);
             {
-                const float4 p0 = *reinterpret_cast<const float4 *>(xs + (16 * warp + g) * 4);
-                const float4 p1 = *reinterpret_cast<const float4 *>(xs + (16 * warp + g + 8) * 4);
-                const float x0[3] = {p0.x, p0.y, p0.z}, x1[3] = {p1.x, p1.y, p1.z};
-                tm_layer1(x0, x1, a1, w1p, t);
+                float acc[16][4];
+                tm_zero<16>(acc);
+                tm_wgrad<4, 4>(act, TM_A4, TM_A3 + hw * 32, acc, g, t);
+                if (ht < 64) sA0 += tm_col_sum(act + TM_A4 + ht);
+                named_arrive(TMB_BAR_A3_EMPTY, TMB_ALL_THREADS);
+                tmem_accumulate<16>(tm, acc);
             }
-            m1 = (unsigned int)tm_relu<4>(a1);
-            tm_store_rows<4>(row0 + TM_A1, a1);
-            tm_init_bias<8>(a2, bs, t);
-            tm_layer<C1, C2>(a1, a2, wb0 + sg * (C1 + 4) + t);
-        }
-        m2 = (unsigned int)tm_relu<8>(a2);
-        tm_store_rows<8>(row0 + TM_A2, a2);
-        __syncthreads();  // wb0 (W2) free
-        tm_stage_nat<C3, C4, TMB_THREADS>(wg + a.offw[3], wb0, tid);  // W4 -> wb0, under layer 3
-        cp_async_commit();
-        float a4[8][4];
-        {
-            float a3[16][4];
-            tm_init_bias<16>(a3, bs + C2, t);
-            tm_layer<C2, C3>(a2, a3, wb1 + sg * (C2 + 4) + t);
-            m3 = tm_relu<16>(a3);
-            tm_store_rows<16>(row0 + TM_A3, a3);
-            cp_async_wait<0>();
-            __syncthreads();  // W4 landed; wb1 (W3) free
-            tm_stage_tr<C3, C4, TMB_THREADS>(wg + a.offw[3], wb1, tid);  // W4^T -> wb1, under layer 4
-            cp_async_commit();
-            tm_init_bias<8>(a4, bs + C2 + C3, t);
-            tm_layer<C3, C4>(a3, a4, wb0 + sg * (C3 + 4) + t);
-        }
-        m4 = (unsigned int)tm_relu<8>(a4);
-        tm_store_rows<8>(row0 + TM_A4, a4);
-        // ---- layer 5: Z5 = dY.  Z4 = gate4 * (dY W5) in fragment layout, K = 3 on the FP32 pipe ----
-        float z4[8][4];
-        {
-            const float4 g0 = *reinterpret_cast<const float4 *>(gs + (16 * warp + g) * 4);
-            const float4 g1 = *reinterpret_cast<const float4 *>(gs + (16 * warp + g + 8) * 4);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int ca = 8 * j + t, cb = ca + 4;
-                const float wa0 = w5[ca], wa1 = w5[C4 + ca], wa2 = w5[2 * C4 + ca];
-                const float wb0_ = w5[cb], wb1_ = w5[C4 + cb], wb2_ = w5[2 * C4 + cb];
-                z4[j][0] = __fmaf_rn(g0.z, wa2, __fmaf_rn(g0.y, wa1, g0.x * wa0));
-                z4[j][1] = __fmaf_rn(g0.z, wb2_, __fmaf_rn(g0.y, wb1_, g0.x * wb0_));
-                z4[j][2] = __fmaf_rn(g1.z, wa2, __fmaf_rn(g1.y, wa1, g1.x * wa0));
-                z4[j][3] = __fmaf_rn(g1.z, wb2_, __fmaf_rn(g1.y, wb1_, g1.x * wb0_));
-            }
-            tm_gate<8>(z4, m4);
-        }
-        cp_async_wait<0>();
-        __syncthreads();  // A4 of the whole tile visible; W4^T landed; wb0 (W4) free
-        tm_stage_tr<C2, C3, TMB_THREADS>(wg + a.offw[2], wb0, tid);  // W3^T -> wb0
-        cp_async_commit();
-        if (tid < 192) {  // dW5[c][k] += sum_p dY[p][c] A4[p][k]
-            const int c = tid >> 6, k = tid & 63;
-            float s = 0.f;
-#pragma unroll 8
-            for (int p = 0; p < TN_T; ++p) s = __fmaf_rn(gs[p * 4 + c], act[p * TM_ACT_LD + TM_A4 + k], s);
-            sC += s;
-        }
-        if (tid >= 160 && tid < 163) {  // db5
-            float s = 0.f;
-            for (int p = 0; p < TN_T; ++p) s += gs[p * 4 + tid - 160];
-            sA += s;
-        }
-        __syncthreads();  // every reader of A4 is done
-        tm_store_rows<8>(row0 + TM_A4, z4);
-        __syncthreads();  // Z4 visible
-        // ---- layer 4: dW4 += Z4^T A3, db4; Z3 = gate3 * (Z4 W4) ----
-        {
-            float acc[8][4];
-            tm_zero<8>(acc);
-            tm_wgrad<2, 4>(act, TM_A4 + (warp & 1) * 32, TM_A3 + (warp >> 1) * 32, acc, g, t);
-            tm_fold<2, 4>(pw4, acc);
-        }
-        if (tid < 64) sA += tm_col_sum(act + TM_A4 + tid);
-        float z2[8][4];
-        {
-            float z3[16][4];
-            tm_zero<16>(z3);
-            tm_layer<C4, C3>(z4, z3, wb1 + sg * (C4 + 4) + t);
-            tm_gate<16>(z3, m3);
-            cp_async_wait<0>();
-            __syncthreads();  // every reader of A3 is done; W3^T landed; wb1 (W4^T) free
-            tm_store_rows<16>(row0 + TM_A3, z3);
-            tm_stage_tr<C1, C2, TMB_THREADS>(wg + a.offw[1], wb1, tid);  // W2^T -> wb1
-            cp_async_commit();
-            __syncthreads();  // Z3 visible
-            // ---- layer 3: dW3 += Z3^T A2, db3; Z2 = gate2 * (Z3 W3) ----
+            // ---- layer 3: dW3 += Z3^T A2, db3 ----
+            named_sync(TMB_BAR_Z3_FULL, TMB_ALL_THREADS);
             {
-                float acc[8][4];
-                tm_zero<8>(acc);
-                tm_wgrad<2, 4>(act, TM_A3 + (warp & 3) * 32, TM_A2 + (warp >> 2) * 32, acc, g, t);
-                tm_fold<2, 4>(pw3, acc);
+                float acc[16][4];
+                tm_zero<16>(acc);
+                tm_wgrad<4, 4>(act, TM_A3 + (hw & 1) * 64, TM_A2 + (hw >> 1) * 32, acc, g, t);
+                sB += tm_col_sum(act + TM_A3 + ht);
+                named_arrive(TMB_BAR_A2_EMPTY, TMB_ALL_THREADS);
+                tmem_accumulate<16>(tm + 64, acc);
             }
-            if (tid >= 128) sB += tm_col_sum(act + TM_A3 + tid - 128);
-            tm_zero<8>(z2);
-            tm_layer<C3, C2>(z3, z2, wb0 + sg * (C3 + 4) + t);
-        }
-        tm_gate<8>(z2, m2);
-        cp_async_wait<0>();
-        __syncthreads();  // every reader of A2 is done; W2^T landed
-        tm_store_rows<8>(row0 + TM_A2, z2);
-        __syncthreads();  // Z2 visible
-        // ---- layer 2: dW2 += Z2^T A1, db2; Z1 = gate1 * (Z2 W2) ----
-        {
-            float acc[2][4];
-            tm_zero<2>(acc);
-            tm_wgrad<1, 2>(act, TM_A2 + (warp & 3) * 16, TM_A1 + (warp >> 2) * 16, acc, g, t);
-            tm_fold<1, 2>(pw2, acc);
-        }
-        if (tid >= 64 && tid < 128) sA += tm_col_sum(act + TM_A2 + tid - 64);
-        {
-            float z1[4][4];
-            tm_zero<4>(z1);
-            tm_layer<C2, C1>(z2, z1, wb1 + sg * (C2 + 4) + t);
-            tm_gate<4>(z1, m1);
-            __syncthreads();  // every reader of A1 is done
-            tm_store_rows<4>(row0 + TM_A1, z1);
-        }
-        __syncthreads();  // Z1 visible
-        // ---- layer 1: dW1 += Z1^T X, db1, optionally dX = Z1 W1 ----
-        if (tid < 96) {
-            const int o = tid / 3, c = tid - o * 3;
-            float s = 0.f;
-#pragma unroll 8
-            for (int p = 0; p < TN_T; ++p) s = __fmaf_rn(act[p * TM_ACT_LD + TM_A1 + o], xs[p * 4 + c], s);
-            sB += s;
-        } else if (tid >= 128 && tid < 160) {
-            sA += tm_col_sum(act + TM_A1 + tid - 128);
-        }
-        if (GRAD_POINTS) {
-            for (int i = tid; i < 3 * TN_T; i += TMB_THREADS) {
-                const int p = i / 3, c = i - p * 3;
-                float sx = 0.f;
-#pragma unroll 8
-                for (int o = 0; o < C1; ++o) sx = __fmaf_rn(act[p * TM_ACT_LD + TM_A1 + o], w1p[o * 4 + c], sx);
-                if (n0 + p < a.N) a.gpoints[((size_t)b * a.N + n0 + p) * 3 + c] = sx;
+            // ---- layer 2: dW2 += Z2^T A1, db2 ----
+            named_sync(TMB_BAR_Z2_FULL, TMB_ALL_THREADS);
+            {
+                float acc[4][4];
+                tm_zero<4>(acc);
+                tm_wgrad<4, 1>(act, TM_A2, TM_A1 + hw * 8, acc, g, t);
+                if (ht >= 64) sA0 += tm_col_sum(act + TM_A2 + ht - 64);
+                named_arrive(TMB_BAR_A1_EMPTY, TMB_ALL_THREADS);
+                tmem_accumulate<4>(tm + 128, acc);
             }
+            // ---- layer 1: dW1 += Z1^T X, db1, optionally dX = Z1 W1 ----
+            named_sync(TMB_BAR_Z1_FULL, TMB_ALL_THREADS);
+            if (ht < 96) {
+                const int o = ht / 3, c = ht - o * 3;
+                float s = 0.f;
+#pragma unroll 8
+                for (int p = 0; p < TN_T; ++p) s = __fmaf_rn(act[p * TM_ACT_LD + TM_A1 + o], xs[p * 4 + c], s);
+                sD += s;
+            }
+            if (ht < 32) sA1 += tm_col_sum(act + TM_A1 + ht);
+            if (GRAD_POINTS) {
+                for (int i = ht; i < 3 * TN_T; i += TMB_HELP_THREADS) {
+                    const int p = i / 3, c = i - p * 3;
+                    float sx = 0.f;
+#pragma unroll 8
+                    for (int o = 0; o < C1; ++o) sx = __fmaf_rn(act[p * TM_ACT_LD + TM_A1 + o], w1p[o * 4 + c], sx);
+                    if (n0 + p < a.N) a.gpoints[((size_t)b * a.N + n0 + p) * 3 + c] = sx;
+                }
+            }
+            if (f + 1 < f1) named_arrive(TMB_BAR_TILE_EMPTY, TMB_ALL_THREADS);
         }
     }
     if (cur >= 0) flush(cur);
+    // tensor memory goes back once every helper has read its columns
+    if (helper) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        named_sync(TMB_BAR_HELPERS, TMB_HELP_THREADS);
+        if (warp == TMB_CHAIN_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base_slot) : "memory");
+    }
 }
 
 }  // namespace hp
