@@ -11,7 +11,8 @@ import os
 import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "lib", "libhp_b200.so")
+# HP_B200_LIB: load another build of the same sources instead (A/B measurements of compile-time variants, tools/ only)
+LIB_PATH = os.environ.get("HP_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libhp_b200.so")
 
 HP_OK = 0
 HP_ERR_INVALID_ARGUMENT, HP_ERR_CUDA, HP_ERR_UNSUPPORTED, HP_ERR_WORKSPACE = 1, 2, 3, 4

@@ -26,7 +26,13 @@
 
 namespace hp {
 
-constexpr int TMF_WARPS = 12;                 // forward CTA: 384 threads (<= 168 registers each)
+#ifndef HP_TMF_WARPS
+#define HP_TMF_WARPS 12
+#endif
+#ifndef HP_TM_JG
+#define HP_TM_JG 4
+#endif
+constexpr int TMF_WARPS = HP_TMF_WARPS;                 // forward CTA: 384 threads (<= 168 registers each)
 constexpr int TMF_THREADS = TMF_WARPS * 32;
 
 // Operand split for 3xTF32.  The tensor core reads only the top 19 bits of an operand register (it TRUNCATES fp32 to tf32), so
@@ -84,7 +90,7 @@ __device__ __forceinline__ void tm_stage_tr(const float *__restrict__ Wg, float 
 template <int K, int N>
 __device__ __forceinline__ void tm_layer(const float (&in)[K / 8][4], float (&acc)[N / 8][4], const float *__restrict__ wl) {
     constexpr int LD = K + 4;
-    constexpr int NTL = N / 8, JG = NTL >= 4 ? 4 : NTL;
+    constexpr int NTL = N / 8, JG = NTL >= HP_TM_JG ? HP_TM_JG : NTL;
 #pragma unroll
     for (int ks = 0; ks < K / 8; ++ks) {
         uint32_t ah[4], al[4];
@@ -100,10 +106,14 @@ __device__ __forceinline__ void tm_layer(const float (&in)[K / 8][4], float (&ac
                 tf32_split(wl[(j0 + j) * 8 * LD + ks * 8], bh[j][0], bl[j][0]);
                 tf32_split(wl[(j0 + j) * 8 * LD + ks * 8 + 4], bh[j][1], bl[j][1]);
             }
+#if !defined(HP_TM_TERMS) || HP_TM_TERMS >= 3
 #pragma unroll
             for (int j = 0; j < JG; ++j) mma_tf32(acc[j0 + j], al, bh[j][0], bh[j][1]);
+#endif
+#if !defined(HP_TM_TERMS) || HP_TM_TERMS >= 2
 #pragma unroll
             for (int j = 0; j < JG; ++j) mma_tf32(acc[j0 + j], ah, bl[j][0], bl[j][1]);
+#endif
 #pragma unroll
             for (int j = 0; j < JG; ++j) mma_tf32(acc[j0 + j], ah, bh[j][0], bh[j][1]);
         }
@@ -297,18 +307,17 @@ constexpr int TMB_ALL_THREADS = TMB_CHAIN_THREADS + TMB_HELP_THREADS;  // 384
 constexpr int TM_ACT_LD = 296;                // activation row stride: 32 + 64 + 128 + 64 + 8, == 8 (mod 32)
 constexpr int TM_A1 = 0, TM_A2 = 32, TM_A3 = 96, TM_A4 = 224;  // column of each layer's block inside a row
 constexpr int TMB_ACT = 0;                                  // [128][296]
-constexpr int TMB_WB0 = TMB_ACT + TN_T * TM_ACT_LD;
-constexpr int TMB_WSZ = C3 * (C2 + 4);                      // 8704 >= 64*132 (W4, W3^T), 128*68 (W3, W4^T)
-constexpr int TMB_WB1 = TMB_WB0 + TMB_WSZ;
-constexpr int TMB_XS = TMB_WB1 + TMB_WSZ;                   // [128][4] (x, y, z, 0)
+constexpr int TMB_W2 = TMB_ACT + TN_T * TM_ACT_LD;          // [64][32]   the sample's matrices, dense and XOR-swizzled (tm_layer_sw),
+constexpr int TMB_W3 = TMB_W2 + C2 * C1;                    // [128][64]  resident for all tiles of the sample: ONE copy serves the
+constexpr int TMB_W4 = TMB_W3 + C3 * C2;                    // [64][128]  forward (along rows) and dgrad (down columns)
+constexpr int TMB_XS = TMB_W4 + C4 * C3;                    // [128][4] (x, y, z, 0)
 constexpr int TMB_GS = TMB_XS + TN_T * 4;                   // [128][4] upstream gradient of the 3 output coordinates
 constexpr int TMB_W1P = TMB_GS + TN_T * 4;                  // [32][4]
 constexpr int TMB_W5 = TMB_W1P + C1 * 4;                    // [3][64]
 constexpr int TMB_B = TMB_W5 + 3 * C4;                      // b2[64] b3[128] b4[64]
 constexpr int TMB_FLOATS = TMB_B + C2 + C3 + C4;
 constexpr size_t TMB_SMEM = (size_t)TMB_FLOATS * sizeof(float);
-static_assert(TMB_SMEM + 2048 <= 227 * 1024, "backward tile does not fit in shared memory");
-static_assert(C4 * (C3 + 4) <= TMB_WSZ && C2 * (C3 + 4) <= TMB_WSZ, "weight buffer");
+static_assert(TMB_SMEM + 64 <= 227 * 1024, "backward tile does not fit in shared memory");
 // named barriers (0 is __syncthreads)
 enum : int { TMB_BAR_CHAIN = 1, TMB_BAR_TILE_EMPTY, TMB_BAR_A4_FULL, TMB_BAR_A4_EMPTY, TMB_BAR_Z4_FULL, TMB_BAR_A3_EMPTY,
              TMB_BAR_Z3_FULL, TMB_BAR_A2_EMPTY, TMB_BAR_Z2_FULL, TMB_BAR_A1_EMPTY, TMB_BAR_Z1_FULL, TMB_BAR_HELPERS };
@@ -432,14 +441,69 @@ __device__ __forceinline__ float tm_col_sum(const float *__restrict__ col) {
     return (s0 + s1) + (s2 + s3);
 }
 
+// ---- one swizzled copy of W[O][K] for both contractions: element (r, c) lives at r*K + (c ^ 4*(r & 7)) ----
+template <int K, int O, int NT>
+__device__ __forceinline__ void tm_stage_sw(const float *__restrict__ Wg, float *__restrict__ dst, int tid) {
+    for (int i = tid; i < O * K; i += NT) {
+        const int o = i / K, k = i - o * K;
+        cp_async4(dst + o * K + (k ^ (4 * (o & 7))), Wg + i);
+    }
+}
+// tm_layer on the swizzled copy.  KC = contraction length, N = produced channels.
+//   DGRAD = false: W is [N][KC], the contraction runs along a row: fragment rows 8j + s(g), columns 8ks + t (+4): conflict-free;
+//   DGRAD = true:  W is [KC][N], the contraction runs down a column: rows 8ks + t (+4), columns 8j + s(g): two lanes per bank.
+template <int KC, int N, bool DGRAD>
+__device__ __forceinline__ void tm_layer_sw(const float (&in)[KC / 8][4], float (&acc)[N / 8][4], const float *__restrict__ W, int sg, int t) {
+    constexpr int NTL = N / 8, JG = NTL >= HP_TM_JG ? HP_TM_JG : NTL;
+    static_assert(NTL >= 4 && NTL % 4 == 0, "channel tiles");
+    // FWD: row s(g) of a tile, swizzle 4*s(g): bit 2 moves t into t or t+4, bits 3-4 flip the contraction step (per ks, below)
+    const float *f0 = W + sg * KC + t + 4 * (sg & 1), *f1 = W + sg * KC + t + 4 * (1 - (sg & 1));
+    const int fx = 8 * (sg >> 1);
+    // DGRAD: row 8ks + t (+4), swizzle 4*t (+16): bit 2 flips s(g), bit 3 swaps even/odd channel tiles, bit 4 (second row) tiles j, j^2
+    const float *dbase = W + t * N + (sg ^ (4 * (t & 1)));
+    const float *dE = dbase + 8 * (t >> 1), *dO = dbase - 8 * (t >> 1);
+#pragma unroll
+    for (int ks = 0; ks < KC / 8; ++ks) {
+        uint32_t ah[4], al[4];
+        tf32_split(in[ks][0], ah[0], al[0]);  // a0 = (g,   t)
+        tf32_split(in[ks][2], ah[1], al[1]);  // a1 = (g+8, t)
+        tf32_split(in[ks][1], ah[2], al[2]);  // a2 = (g,   t+4)
+        tf32_split(in[ks][3], ah[3], al[3]);  // a3 = (g+8, t+4)
+        const int fo = (8 * ks) ^ fx;
+#pragma unroll
+        for (int j0 = 0; j0 < NTL; j0 += JG) {
+            uint32_t bh[JG][2], bl[JG][2];
+#pragma unroll
+            for (int j = 0; j < JG; ++j) {
+                const int jj = j0 + j;
+                float w0, w1;
+                if (!DGRAD) {
+                    w0 = f0[jj * 8 * KC + fo], w1 = f1[jj * 8 * KC + fo];
+                } else {
+                    const float *d = (jj & 1) ? dO : dE;
+                    w0 = d[(8 * ks) * N + 8 * jj], w1 = d[(8 * ks + 4) * N + 8 * (jj ^ 2)];
+                }
+                tf32_split(w0, bh[j][0], bl[j][0]);
+                tf32_split(w1, bh[j][1], bl[j][1]);
+            }
+#pragma unroll
+            for (int j = 0; j < JG; ++j) mma_tf32(acc[j0 + j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+            for (int j = 0; j < JG; ++j) mma_tf32(acc[j0 + j], ah, bl[j][0], bl[j][1]);
+#pragma unroll
+            for (int j = 0; j < JG; ++j) mma_tf32(acc[j0 + j], ah, bh[j][0], bh[j][1]);
+        }
+    }
+}
+
 template <bool GRAD_POINTS>
 __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(const TNArgs a) {
     extern __shared__ __align__(16) float sm[];
-    float *act = sm + TMB_ACT, *wb0 = sm + TMB_WB0, *wb1 = sm + TMB_WB1, *xs = sm + TMB_XS, *gs = sm + TMB_GS;
+    float *act = sm + TMB_ACT, *W2s = sm + TMB_W2, *W3s = sm + TMB_W3, *W4s = sm + TMB_W4, *xs = sm + TMB_XS, *gs = sm + TMB_GS;
     float *w1p = sm + TMB_W1P, *w5 = sm + TMB_W5, *bs = sm + TMB_B;
     __shared__ int is_last;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ unsigned int slot_of[TN_MAX_GRID];
+    unsigned int *slot_of = reinterpret_cast<unsigned int *>(act);  // [TN_MAX_GRID], only inside flush (no tile is live then)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3, sg = (g >> 1) + 4 * (g & 1);
     const bool helper = warp >= TMB_CHAIN_WARPS;
@@ -524,6 +588,11 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
             if (f != f0) named_sync(TMB_BAR_TILE_EMPTY, TMB_ALL_THREADS);  // the helpers are done with the previous tile
             if (b != cur) {
                 if (cur >= 0) flush(cur);
+                // every chain warp is past the previous tile (TILE_EMPTY / flush): restage the sample's weights
+                tm_stage_sw<C1, C2, TMB_CHAIN_THREADS>(wg + a.offw[1], W2s, tid);
+                tm_stage_sw<C2, C3, TMB_CHAIN_THREADS>(wg + a.offw[2], W3s, tid);
+                tm_stage_sw<C3, C4, TMB_CHAIN_THREADS>(wg + a.offw[3], W4s, tid);
+                cp_async_commit();
                 for (int i = tid; i < C1 * 4; i += TMB_CHAIN_THREADS) {
                     const int o = i >> 2, c = i & 3;
                     w1p[i] = c < 3 ? __ldg(wg + a.offw[0] + o * 3 + c) : (a.offb[0] >= 0 ? __ldg(wg + a.offb[0] + o) : 0.f);
@@ -536,15 +605,14 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                     else l = 3, o = i - C2 - C3;
                     bs[i] = a.offb[l] >= 0 ? __ldg(wg + a.offb[l] + o) : 0.f;
                 }
+                cp_async_wait<0>();
+                named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);
                 cur = b;
             }
             const int n0 = tl * TN_T;
-            // ---- W2 -> wb0, W3 -> wb1; the tile's points and upstream gradients ----
-            tm_stage_nat<C1, C2, TMB_CHAIN_THREADS>(wg + a.offw[1], wb0, tid);
-            tm_stage_nat<C2, C3, TMB_CHAIN_THREADS>(wg + a.offw[2], wb1, tid);
-            cp_async_commit();
-            if (tid < TN_T) {
-                const int p = n0 + tid;
+            // ---- this warp's 16 points and their upstream gradients (the helpers read them from shared memory too) ----
+            if (lane < 16) {
+                const int p = n0 + 16 * warp + lane;
                 float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
                 if (p < a.N) {
                     const float *px = a.points + (size_t)b * a.pstride + (size_t)p * 3;
@@ -557,11 +625,10 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                         gv.x = __ldg(pg), gv.y = __ldg(pg + 1), gv.z = __ldg(pg + 2);
                     }
                 }
-                *reinterpret_cast<float4 *>(xs + tid * 4) = xv;
-                *reinterpret_cast<float4 *>(gs + tid * 4) = gv;
+                *reinterpret_cast<float4 *>(xs + (16 * warp + lane) * 4) = xv;
+                *reinterpret_cast<float4 *>(gs + (16 * warp + lane) * 4) = gv;
             }
-            cp_async_wait<0>();
-            named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);
+            __syncwarp();
             // ---- forward recompute in registers; the activations also go to shared memory for wgrad ----
             float *row0 = act + (16 * warp + g) * TM_ACT_LD + t;
             unsigned int m1, m2, m4;
@@ -578,28 +645,21 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 m1 = (unsigned int)tm_relu<4>(a1);
                 tm_store_rows<4>(row0 + TM_A1, a1);
                 tm_init_bias<8>(a2, bs, t);
-                tm_layer<C1, C2>(a1, a2, wb0 + sg * (C1 + 4) + t);
+                tm_layer_sw<C1, C2, false>(a1, a2, W2s, sg, t);
             }
             m2 = (unsigned int)tm_relu<8>(a2);
             tm_store_rows<8>(row0 + TM_A2, a2);
-            named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // wb0 (W2) free
-            tm_stage_nat<C3, C4, TMB_CHAIN_THREADS>(wg + a.offw[3], wb0, tid);  // W4 -> wb0, under layer 3
-            cp_async_commit();
             float z4[8][4];
             {
                 float a4[8][4];
                 {
                     float a3[16][4];
                     tm_init_bias<16>(a3, bs + C2, t);
-                    tm_layer<C2, C3>(a2, a3, wb1 + sg * (C2 + 4) + t);
+                    tm_layer_sw<C2, C3, false>(a2, a3, W3s, sg, t);
                     m3 = tm_relu<16>(a3);
                     tm_store_rows<16>(row0 + TM_A3, a3);
-                    cp_async_wait<0>();
-                    named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // W4 landed; wb1 (W3) free
-                    tm_stage_tr<C3, C4, TMB_CHAIN_THREADS>(wg + a.offw[3], wb1, tid);  // W4^T -> wb1, under layer 4
-                    cp_async_commit();
                     tm_init_bias<8>(a4, bs + C2 + C3, t);
-                    tm_layer<C3, C4>(a3, a4, wb0 + sg * (C3 + 4) + t);
+                    tm_layer_sw<C3, C4, false>(a3, a4, W4s, sg, t);
                 }
                 m4 = (unsigned int)tm_relu<8>(a4);
                 tm_store_rows<8>(row0 + TM_A4, a4);
@@ -621,10 +681,6 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 }
                 tm_gate<8>(z4, m4);
             }
-            cp_async_wait<0>();
-            named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // W4^T landed; wb0 (W4) free
-            tm_stage_tr<C2, C3, TMB_CHAIN_THREADS>(wg + a.offw[2], wb0, tid);  // W3^T -> wb0
-            cp_async_commit();
             named_sync(TMB_BAR_A4_EMPTY, TMB_ALL_THREADS);  // the helpers have read A4 (dW5)
             tm_store_rows<8>(row0 + TM_A4, z4);
             named_arrive(TMB_BAR_Z4_FULL, TMB_ALL_THREADS);
@@ -633,22 +689,16 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
             {
                 float z3[16][4];
                 tm_zero<16>(z3);
-                tm_layer<C4, C3>(z4, z3, wb1 + sg * (C4 + 4) + t);
+                tm_layer_sw<C4, C3, true>(z4, z3, W4s, sg, t);
                 tm_gate<16>(z3, m3);
-                cp_async_wait<0>();
-                named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // W3^T landed; wb1 (W4^T) free
-                tm_stage_tr<C1, C2, TMB_CHAIN_THREADS>(wg + a.offw[1], wb1, tid);  // W2^T -> wb1
-                cp_async_commit();
                 named_sync(TMB_BAR_A3_EMPTY, TMB_ALL_THREADS);  // the helpers have read A3 (and Z4)
                 tm_store_rows<16>(row0 + TM_A3, z3);
                 named_arrive(TMB_BAR_Z3_FULL, TMB_ALL_THREADS);
                 // ---- layer 3: Z2 = gate2 * (Z3 W3) ----
                 tm_zero<8>(z2);
-                tm_layer<C3, C2>(z3, z2, wb0 + sg * (C3 + 4) + t);
+                tm_layer_sw<C3, C2, true>(z3, z2, W3s, sg, t);
             }
             tm_gate<8>(z2, m2);
-            cp_async_wait<0>();
-            named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // W2^T landed
             named_sync(TMB_BAR_A2_EMPTY, TMB_ALL_THREADS);
             tm_store_rows<8>(row0 + TM_A2, z2);
             named_arrive(TMB_BAR_Z2_FULL, TMB_ALL_THREADS);
@@ -656,13 +706,12 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
             {
                 float z1[4][4];
                 tm_zero<4>(z1);
-                tm_layer<C2, C1>(z2, z1, wb1 + sg * (C2 + 4) + t);
+                tm_layer_sw<C2, C1, true>(z2, z1, W2s, sg, t);
                 tm_gate<4>(z1, m1);
                 named_sync(TMB_BAR_A1_EMPTY, TMB_ALL_THREADS);
                 tm_store_rows<4>(row0 + TM_A1, z1);
             }
             named_arrive(TMB_BAR_Z1_FULL, TMB_ALL_THREADS);
-            named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);  // every chain warp is done with wb1 / w1p / w5 / bs before the next tile restages
         }
     } else {
         // =========================================== WGRAD HELPERS ===========================================
