@@ -277,6 +277,27 @@ __device__ __forceinline__ float tn_row_dot(const float *__restrict__ z, const f
     return s;
 }
 
+// Fold the per-CTA partial gradients of a sample that several CTAs share: g[i] = sum over the contributing slots in ascending CTA
+// order (deterministic).  Eight elements per thread in flight: the loop is bound by L2 latency, not bandwidth.
+template <int NT>
+__device__ __forceinline__ void tn_fold_partials(const float *__restrict__ partial, const unsigned int *__restrict__ slot_of, int ncontrib,
+                                                 int W, float *__restrict__ g, int tid) {
+    for (int i0 = tid; i0 < W; i0 += 8 * NT) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = 0.f;
+        for (int q = 0; q < ncontrib; ++q) {
+            const float *src = partial + (size_t)slot_of[q] * W;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (i0 + u * NT < W) v[u] += __ldcg(src + i0 + u * NT);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (i0 + u * NT < W) g[i0 + u * NT] = v[u];
+    }
+}
+
 // ---- fast path: 3 -> 32 -> 64 -> 128 -> 64 -> 3 -----------------------------------------------------------
 constexpr int C1 = 32, C2 = 64, C3 = 128, C4 = 64;
 // forward shared-memory map (floats)
@@ -437,11 +458,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_backward_kernel(const TNArgs
                 }
                 __syncthreads();
                 float *g = a.gweights + (size_t)b * a.W;
-                for (int i = tid; i < a.W; i += TN_THREADS) {
-                    float v = 0.f;
-                    for (int q = 0; q < ncontrib; ++q) v += __ldcg(a.partial + (size_t)slot_of[q] * a.W + i);  // ascending CTA order
-                    g[i] = v;
-                }
+                tn_fold_partials<TN_THREADS>(a.partial, slot_of, ncontrib, a.W, g, tid);
             }
             __syncthreads();  // is_last reusable
         }
@@ -715,6 +732,15 @@ static int tn_generic_args(TNGenArgs &g, int n_layers, const int *dims, size_t &
 }  // namespace hp
 
 using namespace hp;
+
+#ifdef HP_TM_TRACE
+extern "C" __attribute__((visibility("default"))) int hp_debug_tn_trace(unsigned long long *out_host) {
+    return (int)cudaMemcpyFromSymbol(out_host, hp::g_tm_trace, sizeof(hp::g_tm_trace));
+}
+extern "C" __attribute__((visibility("default"))) int hp_debug_tn_cta(unsigned long long *out_host) {
+    return (int)cudaMemcpyFromSymbol(out_host, hp::g_tm_cta, sizeof(hp::g_tm_cta));
+}
+#endif
 
 extern "C" int hp_target_network_set_mode(int mode) {
     HP_REQUIRE(mode == 0 || mode == 1, "hp_target_network_set_mode: mode %d is neither 0 (3xTF32 tensor cores) nor 1 (FP32 pipe)", mode);

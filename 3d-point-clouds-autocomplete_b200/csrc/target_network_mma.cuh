@@ -220,7 +220,11 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifdef HP_TMF_MAXNREG
+__global__ void __launch_bounds__(TMF_THREADS, 1) __maxnreg__(HP_TMF_MAXNREG) tn_mma_forward_kernel(const TNArgs a) {
+#else
 __global__ void __launch_bounds__(TMF_THREADS, 1) tn_mma_forward_kernel(const TNArgs a) {
+#endif
     extern __shared__ __align__(16) float sm[];
     __shared__ uint64_t bars[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -234,6 +238,13 @@ __global__ void __launch_bounds__(TMF_THREADS, 1) tn_mma_forward_kernel(const TN
     if (u0 >= u1) return;
     const int bfirst = (int)(u0 / upn), blast = (int)((u1 - 1) / upn);
     if (tid == 0) mbar_init(&bars[0], TMF_THREADS), mbar_init(&bars[1], TMF_THREADS);
+#ifdef HP_TMF_TMEM_PROBE
+    __shared__ uint32_t probe_slot;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&probe_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+#endif
     tmf_fill_const<TMF_THREADS>(a, sm, tid);
     tmf_fill_const<TMF_THREADS>(a, sm + TMF_FLOATS, tid);
     __syncthreads();
@@ -287,6 +298,10 @@ __global__ void __launch_bounds__(TMF_THREADS, 1) tn_mma_forward_kernel(const TN
             }
         }
     }
+#ifdef HP_TMF_TMEM_PROBE
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(probe_slot) : "memory");
+#endif
 }
 
 // ---- backward -----------------------------------------------------------------------------------------------------------------
@@ -379,6 +394,9 @@ __device__ __forceinline__ void tm_store_rows(float *__restrict__ row0, const fl
 // dW tile on the tensor cores: acc[mi*NT+ni] += sum over the tile's 128 points of Z[p][zc + 16mi + g (+8)] * A[p][ac + 8ni + 2t (+1)]
 template <int MT, int NT>
 __device__ __forceinline__ void tm_wgrad(const float *__restrict__ act, int zc, int ac, float (&acc)[MT * NT][4], int g, int t) {
+#ifdef HP_TMB_NO_WGRAD
+    return;
+#endif
     const float *zr = act + t * TM_ACT_LD + zc + g;
     const float *ar = act + t * TM_ACT_LD + ac + g;
 #pragma unroll 1
@@ -496,6 +514,30 @@ __device__ __forceinline__ void tm_layer_sw(const float (&in)[KC / 8][4], float 
     }
 }
 
+#ifdef HP_TM_TRACE
+__device__ unsigned long long g_tm_cta[256][4];  // per CTA: kernel entry, first tile, after the last tile, exit
+__device__ __forceinline__ void tm_cta_stamp(int ev) {
+    if (threadIdx.x == 0) {
+        unsigned long long tns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+        g_tm_cta[blockIdx.x][ev] = tns;
+    }
+}
+#define TM_CTA(ev) tm_cta_stamp(ev)
+__device__ unsigned long long g_tm_trace[2][64][16];  // [role][tile][event] %globaltimer stamps of CTA 0 (chain warp 0 / helper warp 8)
+__device__ __forceinline__ void tm_trace(int role, int tile, int ev, int lane) {
+    if (blockIdx.x == 0 && lane == 0 && tile < 64) {
+        unsigned long long tns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+        g_tm_trace[role][tile][ev] = tns;
+    }
+}
+#define TM_TRACE(role, ev) do { if ((role) == 0 ? warp == 0 : warp == TMB_CHAIN_WARPS) tm_trace(role, (int)(f - f0), ev, lane); } while (0)
+#else
+#define TM_TRACE(role, ev) do { } while (0)
+#define TM_CTA(ev) do { } while (0)
+#endif
+
 template <bool GRAD_POINTS>
 __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(const TNArgs a) {
     extern __shared__ __align__(16) float sm[];
@@ -513,6 +555,7 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
     const long long G = gridDim.x;
     const long long f0 = (long long)blockIdx.x * TT / G, f1 = (long long)(blockIdx.x + 1) * TT / G;
     const int first_sample = (int)(f0 / ntiles);
+    TM_CTA(0);
 
     // tensor memory: 256 columns; helper warp hw owns lanes 32*hw.. of them (columns 0-63 dW4, 64-127 dW3, 128-143 dW2)
     if (warp == TMB_CHAIN_WARPS) {
@@ -569,22 +612,37 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 }
                 __syncthreads();
                 float *gw = a.gweights + (size_t)b * a.W;
-                for (int i = tid; i < a.W; i += TMB_ALL_THREADS) {
-                    float v = 0.f;
-                    for (int q = 0; q < ncontrib; ++q) v += __ldcg(a.partial + (size_t)slot_of[q] * a.W + i);  // ascending CTA order
-                    gw[i] = v;
-                }
+                tn_fold_partials<TMB_ALL_THREADS>(a.partial, slot_of, ncontrib, a.W, gw, tid);
             }
             __syncthreads();
         }
     };
 
     int cur = -1;
+    TM_CTA(1);
     if (!helper) {
         // =========================================== CHAIN ===========================================
         for (long long f = f0; f < f1; ++f) {
             const int b = (int)(f / ntiles), tl = (int)(f - (long long)b * ntiles);
             const float *wg = a.weights + (size_t)b * a.W;
+            TM_TRACE(0, 0);
+            const int n0 = tl * TN_T;
+            // this warp's 16 points and their upstream gradients: loaded before the wait below, stored (the helpers read them too) after it
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+            if (lane < 16) {
+                const int p = n0 + 16 * warp + lane;
+                if (p < a.N) {
+                    const float *px = a.points + (size_t)b * a.pstride + (size_t)p * 3;
+                    xv.x = __ldg(px), xv.y = __ldg(px + 1), xv.z = __ldg(px + 2);
+                    if (a.channels_first) {
+                        const float *pg = a.gout + (size_t)b * 3 * a.N + p;
+                        gv.x = __ldg(pg), gv.y = __ldg(pg + a.N), gv.z = __ldg(pg + 2 * (size_t)a.N);
+                    } else {
+                        const float *pg = a.gout + ((size_t)b * a.N + p) * 3;
+                        gv.x = __ldg(pg), gv.y = __ldg(pg + 1), gv.z = __ldg(pg + 2);
+                    }
+                }
+            }
             if (f != f0) named_sync(TMB_BAR_TILE_EMPTY, TMB_ALL_THREADS);  // the helpers are done with the previous tile
             if (b != cur) {
                 if (cur >= 0) flush(cur);
@@ -609,26 +667,13 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 named_sync(TMB_BAR_CHAIN, TMB_CHAIN_THREADS);
                 cur = b;
             }
-            const int n0 = tl * TN_T;
-            // ---- this warp's 16 points and their upstream gradients (the helpers read them from shared memory too) ----
+            TM_TRACE(0, 1);
             if (lane < 16) {
-                const int p = n0 + 16 * warp + lane;
-                float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
-                if (p < a.N) {
-                    const float *px = a.points + (size_t)b * a.pstride + (size_t)p * 3;
-                    xv.x = __ldg(px), xv.y = __ldg(px + 1), xv.z = __ldg(px + 2);
-                    if (a.channels_first) {
-                        const float *pg = a.gout + (size_t)b * 3 * a.N + p;
-                        gv.x = __ldg(pg), gv.y = __ldg(pg + a.N), gv.z = __ldg(pg + 2 * (size_t)a.N);
-                    } else {
-                        const float *pg = a.gout + ((size_t)b * a.N + p) * 3;
-                        gv.x = __ldg(pg), gv.y = __ldg(pg + 1), gv.z = __ldg(pg + 2);
-                    }
-                }
                 *reinterpret_cast<float4 *>(xs + (16 * warp + lane) * 4) = xv;
                 *reinterpret_cast<float4 *>(gs + (16 * warp + lane) * 4) = gv;
             }
             __syncwarp();
+            TM_TRACE(0, 2);
             // ---- forward recompute in registers; the activations also go to shared memory for wgrad ----
             float *row0 = act + (16 * warp + g) * TM_ACT_LD + t;
             unsigned int m1, m2, m4;
@@ -664,6 +709,7 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 m4 = (unsigned int)tm_relu<8>(a4);
                 tm_store_rows<8>(row0 + TM_A4, a4);
             }
+            TM_TRACE(0, 3);
             named_arrive(TMB_BAR_A4_FULL, TMB_ALL_THREADS);  // A1..A4, xs, gs of this warp's rows are in place
             // ---- layer 5: Z5 = dY.  Z4 = gate4 * (dY W5) in fragment layout, K = 3 on the FP32 pipe ----
             {
@@ -681,7 +727,9 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 }
                 tm_gate<8>(z4, m4);
             }
+            TM_TRACE(0, 4);
             named_sync(TMB_BAR_A4_EMPTY, TMB_ALL_THREADS);  // the helpers have read A4 (dW5)
+            TM_TRACE(0, 5);
             tm_store_rows<8>(row0 + TM_A4, z4);
             named_arrive(TMB_BAR_Z4_FULL, TMB_ALL_THREADS);
             // ---- layer 4: Z3 = gate3 * (Z4 W4) while the helpers take dW4 = Z4^T A3 ----
@@ -691,7 +739,9 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 tm_zero<16>(z3);
                 tm_layer_sw<C4, C3, true>(z4, z3, W4s, sg, t);
                 tm_gate<16>(z3, m3);
+                TM_TRACE(0, 6);
                 named_sync(TMB_BAR_A3_EMPTY, TMB_ALL_THREADS);  // the helpers have read A3 (and Z4)
+                TM_TRACE(0, 7);
                 tm_store_rows<16>(row0 + TM_A3, z3);
                 named_arrive(TMB_BAR_Z3_FULL, TMB_ALL_THREADS);
                 // ---- layer 3: Z2 = gate2 * (Z3 W3) ----
@@ -699,7 +749,9 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 tm_layer_sw<C3, C2, true>(z3, z2, W3s, sg, t);
             }
             tm_gate<8>(z2, m2);
+            TM_TRACE(0, 8);
             named_sync(TMB_BAR_A2_EMPTY, TMB_ALL_THREADS);
+            TM_TRACE(0, 9);
             tm_store_rows<8>(row0 + TM_A2, z2);
             named_arrive(TMB_BAR_Z2_FULL, TMB_ALL_THREADS);
             // ---- layer 2: Z1 = gate1 * (Z2 W2) ----
@@ -708,10 +760,13 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 tm_zero<4>(z1);
                 tm_layer_sw<C2, C1, true>(z2, z1, W2s, sg, t);
                 tm_gate<4>(z1, m1);
+                TM_TRACE(0, 10);
                 named_sync(TMB_BAR_A1_EMPTY, TMB_ALL_THREADS);
+                TM_TRACE(0, 11);
                 tm_store_rows<4>(row0 + TM_A1, z1);
             }
             named_arrive(TMB_BAR_Z1_FULL, TMB_ALL_THREADS);
+            TM_TRACE(0, 12);
         }
     } else {
         // =========================================== WGRAD HELPERS ===========================================
@@ -723,16 +778,19 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
             }
             const int n0 = tl * TN_T;
             // ---- layer 5: dW5[c][k] += sum_p dY[p][c] A4[p][k], db5 ----
+            TM_TRACE(1, 0);
             named_sync(TMB_BAR_A4_FULL, TMB_ALL_THREADS);
+            TM_TRACE(1, 1);
             {
                 const int c0 = ht >> 6, k0 = ht & 63;  // elements ht and 128 + ht (row 2) of dW5[3][64]
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-                for (int p = 0; p < TN_T; ++p) {
-                    const float av = act[p * TM_ACT_LD + TM_A4 + k0];
-                    s0 = __fmaf_rn(gs[p * 4 + c0], av, s0);
-                    s1 = __fmaf_rn(gs[p * 4 + 2], av, s1);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+                for (int p = 0; p < TN_T; p += 2) {
+                    const float av = act[p * TM_ACT_LD + TM_A4 + k0], aw = act[(p + 1) * TM_ACT_LD + TM_A4 + k0];
+                    s0 = __fmaf_rn(gs[p * 4 + c0], av, s0), s2 = __fmaf_rn(gs[p * 4 + 4 + c0], aw, s2);
+                    s1 = __fmaf_rn(gs[p * 4 + 2], av, s1), s3 = __fmaf_rn(gs[p * 4 + 6], aw, s3);
                 }
+                s0 += s2, s1 += s3;
                 sC0 += s0;
                 if (ht < 64) sC1 += s1;
                 if (ht >= 32 && ht < 35) {
@@ -743,7 +801,9 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
             }
             named_arrive(TMB_BAR_A4_EMPTY, TMB_ALL_THREADS);
             // ---- layer 4: dW4 += Z4^T A3, db4 ----
+            TM_TRACE(1, 2);
             named_sync(TMB_BAR_Z4_FULL, TMB_ALL_THREADS);
+            TM_TRACE(1, 3);
             {
                 float acc[16][4];
                 tm_zero<16>(acc);
@@ -753,7 +813,9 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 tmem_accumulate<16>(tm, acc);
             }
             // ---- layer 3: dW3 += Z3^T A2, db3 ----
+            TM_TRACE(1, 4);
             named_sync(TMB_BAR_Z3_FULL, TMB_ALL_THREADS);
+            TM_TRACE(1, 5);
             {
                 float acc[16][4];
                 tm_zero<16>(acc);
@@ -763,7 +825,9 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 tmem_accumulate<16>(tm + 64, acc);
             }
             // ---- layer 2: dW2 += Z2^T A1, db2 ----
+            TM_TRACE(1, 6);
             named_sync(TMB_BAR_Z2_FULL, TMB_ALL_THREADS);
+            TM_TRACE(1, 7);
             {
                 float acc[4][4];
                 tm_zero<4>(acc);
@@ -773,13 +837,20 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 tmem_accumulate<4>(tm + 128, acc);
             }
             // ---- layer 1: dW1 += Z1^T X, db1, optionally dX = Z1 W1 ----
+            TM_TRACE(1, 8);
             named_sync(TMB_BAR_Z1_FULL, TMB_ALL_THREADS);
+            TM_TRACE(1, 9);
             if (ht < 96) {
                 const int o = ht / 3, c = ht - o * 3;
-                float s = 0.f;
-#pragma unroll 8
-                for (int p = 0; p < TN_T; ++p) s = __fmaf_rn(act[p * TM_ACT_LD + TM_A1 + o], xs[p * 4 + c], s);
-                sD += s;
+                float s = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+#pragma unroll 2
+                for (int p = 0; p < TN_T; p += 4) {
+                    s = __fmaf_rn(act[p * TM_ACT_LD + TM_A1 + o], xs[p * 4 + c], s);
+                    s2 = __fmaf_rn(act[(p + 1) * TM_ACT_LD + TM_A1 + o], xs[p * 4 + 4 + c], s2);
+                    s3 = __fmaf_rn(act[(p + 2) * TM_ACT_LD + TM_A1 + o], xs[p * 4 + 8 + c], s3);
+                    s4 = __fmaf_rn(act[(p + 3) * TM_ACT_LD + TM_A1 + o], xs[p * 4 + 12 + c], s4);
+                }
+                sD += (s + s2) + (s3 + s4);
             }
             if (ht < 32) sA1 += tm_col_sum(act + TM_A1 + ht);
             if (GRAD_POINTS) {
@@ -791,10 +862,13 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                     if (n0 + p < a.N) a.gpoints[((size_t)b * a.N + n0 + p) * 3 + c] = sx;
                 }
             }
+            TM_TRACE(1, 10);
             if (f + 1 < f1) named_arrive(TMB_BAR_TILE_EMPTY, TMB_ALL_THREADS);
         }
     }
+    TM_CTA(2);
     if (cur >= 0) flush(cur);
+    TM_CTA(3);
     // tensor memory goes back once every helper has read its columns
     if (helper) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
