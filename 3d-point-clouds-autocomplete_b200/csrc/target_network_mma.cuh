@@ -567,9 +567,9 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm = tmem_base_slot + ((uint32_t)(32 * (hw & 3)) << 16);
     // helpers: small gradients, a few elements per thread
-    //   sC0: dW5[ht] | sC1: dW5[128 + ht] (ht < 64) | sB: db3[ht] | sA0: db4[ht] (ht < 64), db2[ht - 64] | sA1: db1[ht] (ht < 32), db5[ht - 32] (< 35)
+    //   sC0..2: dW5[0..2][ht] (ht < 64) | sB: db3[ht] | sA0: db4[ht] (ht < 64), db2[ht - 64] | sA1: db1[ht] (ht < 32), db5[ht - 64] (64 <= ht < 67)
     //   sD: dW1[ht] (ht < 96)
-    float sC0 = 0.f, sC1 = 0.f, sB = 0.f, sA0 = 0.f, sA1 = 0.f, sD = 0.f;
+    float sC0 = 0.f, sC1 = 0.f, sC2 = 0.f, sB = 0.f, sA0 = 0.f, sA1 = 0.f, sD = 0.f;
     if (helper) {
         uint32_t z[16];
 #pragma unroll
@@ -587,15 +587,14 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
             tm_flush_dw<4, 4, C3>(tm, dst + a.offw[3], 0, hw * 32, g, t);
             tm_flush_dw<4, 4, C2>(tm + 64, dst + a.offw[2], (hw & 1) * 64, (hw >> 1) * 32, g, t);
             tm_flush_dw<4, 1, C1>(tm + 128, dst + a.offw[1], 0, hw * 8, g, t);
-            dst[a.offw[4] + ht] = sC0;
-            if (ht < 64) dst[a.offw[4] + 128 + ht] = sC1;
+            if (ht < 64) dst[a.offw[4] + ht] = sC0, dst[a.offw[4] + 64 + ht] = sC1, dst[a.offw[4] + 128 + ht] = sC2;
             if (a.offb[2] >= 0) dst[a.offb[2] + ht] = sB;
             if (ht < 64) { if (a.offb[3] >= 0) dst[a.offb[3] + ht] = sA0; }
             else { if (a.offb[1] >= 0) dst[a.offb[1] + ht - 64] = sA0; }
             if (ht < 32) { if (a.offb[0] >= 0) dst[a.offb[0] + ht] = sA1; }
-            else if (ht < 35) { if (a.offb[4] >= 0) dst[a.offb[4] + ht - 32] = sA1; }
+            else if (ht >= 64 && ht < 67) { if (a.offb[4] >= 0) dst[a.offb[4] + ht - 64] = sA1; }
             if (ht < 96) dst[a.offw[0] + ht] = sD;
-            sC0 = sC1 = sB = sA0 = sA1 = sD = 0.f;
+            sC0 = sC1 = sC2 = sB = sA0 = sA1 = sD = 0.f;
         }
         if (shared_sample) {
             __threadfence();
@@ -643,8 +642,9 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                     }
                 }
             }
-            if (f != f0) named_sync(TMB_BAR_TILE_EMPTY, TMB_ALL_THREADS);  // the helpers are done with the previous tile
-            if (b != cur) {
+            bool waited = (f == f0);
+            if (b != cur) {  // new sample: everything of the previous tile must be over before the weights change
+                if (!waited) named_sync(TMB_BAR_TILE_EMPTY, TMB_ALL_THREADS), waited = true;
                 if (cur >= 0) flush(cur);
                 // every chain warp is past the previous tile (TILE_EMPTY / flush): restage the sample's weights
                 tm_stage_sw<C1, C2, TMB_CHAIN_THREADS>(wg + a.offw[1], W2s, tid);
@@ -668,31 +668,30 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 cur = b;
             }
             TM_TRACE(0, 1);
+            // ---- layers 1 and 2 in registers while the helpers finish the previous tile (its rows are still theirs) ----
+            unsigned int m1, m2, m4;
+            unsigned long long m3;
+            float a2[8][4];
+            float a1[4][4];
+            {
+                const float x0[3] = {__shfl_sync(0xffffffffu, xv.x, g), __shfl_sync(0xffffffffu, xv.y, g), __shfl_sync(0xffffffffu, xv.z, g)};
+                const float x1[3] = {__shfl_sync(0xffffffffu, xv.x, g + 8), __shfl_sync(0xffffffffu, xv.y, g + 8),
+                                     __shfl_sync(0xffffffffu, xv.z, g + 8)};
+                tm_layer1(x0, x1, a1, w1p, t);
+            }
+            m1 = (unsigned int)tm_relu<4>(a1);
+            tm_init_bias<8>(a2, bs, t);
+            tm_layer_sw<C1, C2, false>(a1, a2, W2s, sg, t);
+            m2 = (unsigned int)tm_relu<8>(a2);
+            if (!waited) named_sync(TMB_BAR_TILE_EMPTY, TMB_ALL_THREADS);  // the helpers are done with the previous tile
+            TM_TRACE(0, 2);
+            float *row0 = act + (16 * warp + g) * TM_ACT_LD + t;
             if (lane < 16) {
                 *reinterpret_cast<float4 *>(xs + (16 * warp + lane) * 4) = xv;
                 *reinterpret_cast<float4 *>(gs + (16 * warp + lane) * 4) = gv;
             }
             __syncwarp();
-            TM_TRACE(0, 2);
-            // ---- forward recompute in registers; the activations also go to shared memory for wgrad ----
-            float *row0 = act + (16 * warp + g) * TM_ACT_LD + t;
-            unsigned int m1, m2, m4;
-            unsigned long long m3;
-            float a2[8][4];
-            {
-                float a1[4][4];
-                {
-                    const float4 p0 = *reinterpret_cast<const float4 *>(xs + (16 * warp + g) * 4);
-                    const float4 p1 = *reinterpret_cast<const float4 *>(xs + (16 * warp + g + 8) * 4);
-                    const float x0[3] = {p0.x, p0.y, p0.z}, x1[3] = {p1.x, p1.y, p1.z};
-                    tm_layer1(x0, x1, a1, w1p, t);
-                }
-                m1 = (unsigned int)tm_relu<4>(a1);
-                tm_store_rows<4>(row0 + TM_A1, a1);
-                tm_init_bias<8>(a2, bs, t);
-                tm_layer_sw<C1, C2, false>(a1, a2, W2s, sg, t);
-            }
-            m2 = (unsigned int)tm_relu<8>(a2);
+            tm_store_rows<4>(row0 + TM_A1, a1);
             tm_store_rows<8>(row0 + TM_A2, a2);
             float z4[8][4];
             {
@@ -781,23 +780,21 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
             TM_TRACE(1, 0);
             named_sync(TMB_BAR_A4_FULL, TMB_ALL_THREADS);
             TM_TRACE(1, 1);
-            {
-                const int c0 = ht >> 6, k0 = ht & 63;  // elements ht and 128 + ht (row 2) of dW5[3][64]
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            if (ht < 64) {  // dW5[0..2][ht]
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
 #pragma unroll 4
                 for (int p = 0; p < TN_T; p += 2) {
-                    const float av = act[p * TM_ACT_LD + TM_A4 + k0], aw = act[(p + 1) * TM_ACT_LD + TM_A4 + k0];
-                    s0 = __fmaf_rn(gs[p * 4 + c0], av, s0), s2 = __fmaf_rn(gs[p * 4 + 4 + c0], aw, s2);
-                    s1 = __fmaf_rn(gs[p * 4 + 2], av, s1), s3 = __fmaf_rn(gs[p * 4 + 6], aw, s3);
+                    const float av = act[p * TM_ACT_LD + TM_A4 + ht], aw = act[(p + 1) * TM_ACT_LD + TM_A4 + ht];
+                    const float4 ga = *reinterpret_cast<const float4 *>(gs + p * 4), gb = *reinterpret_cast<const float4 *>(gs + p * 4 + 4);
+                    s0 = __fmaf_rn(ga.x, av, s0), s1 = __fmaf_rn(ga.y, av, s1), s2 = __fmaf_rn(ga.z, av, s2);
+                    u0 = __fmaf_rn(gb.x, aw, u0), u1 = __fmaf_rn(gb.y, aw, u1), u2 = __fmaf_rn(gb.z, aw, u2);
                 }
-                s0 += s2, s1 += s3;
-                sC0 += s0;
-                if (ht < 64) sC1 += s1;
-                if (ht >= 32 && ht < 35) {
-                    float s = 0.f;
-                    for (int p = 0; p < TN_T; ++p) s += gs[p * 4 + ht - 32];
-                    sA1 += s;
-                }
+                sC0 += s0 + u0, sC1 += s1 + u1, sC2 += s2 + u2;
+            } else if (ht < 67) {  // db5
+                float s = 0.f, u = 0.f;
+#pragma unroll 4
+                for (int p = 0; p < TN_T; p += 2) s += gs[p * 4 + ht - 64], u += gs[p * 4 + 4 + ht - 64];
+                sA1 += s + u;
             }
             named_arrive(TMB_BAR_A4_EMPTY, TMB_ALL_THREADS);
             // ---- layer 4: dW4 += Z4^T A3, db4 ----
