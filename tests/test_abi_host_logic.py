@@ -58,3 +58,13 @@ def test_argument_validation_reports_errors_without_touching_the_gpu(hp, lib):
         hp._native.check(INVALID, "demo")
     assert lib.hp_error_string(hp._native.HP_ERR_WORKSPACE) == b"workspace too small"
     assert lib.hp_version() == 100
+
+
+def test_target_network_mode_switch_validates(hp, lib):
+    INVALID = hp._native.HP_ERR_INVALID_ARGUMENT
+    assert lib.hp_target_network_set_mode(7) == INVALID
+    assert b"neither 0" in lib.hp_last_error_message()
+    assert lib.hp_target_network_set_mode(1) == hp._native.HP_OK   # fp32 FFMA kernels
+    assert lib.hp_target_network_set_mode(0) == hp._native.HP_OK   # back to the default (3xTF32 on the tensor cores)
+    with pytest.raises(ValueError):
+        hp.target_network_set_mode("bf16")

@@ -95,6 +95,32 @@ def test_forward_backward_vs_oracle_fast_shape(hp, oracle, b, n, use_bias):
     assert torch.equal(wd2.grad, wd.grad)
 
 
+def test_both_arithmetic_modes_hold_the_bar(hp, oracle):
+    """The default (error-compensated 3xTF32 on the tensor cores) and the fp32 FFMA kernels against the same oracle; a sample
+    whose tiles are shared by several CTAs (n = 2500: partial-gradient fold) and a ragged tail tile."""
+    b, n = 5, 2500
+    w, x, go = _inputs(b, n, FAST, True, seed=77)
+    oy = oracle.target_network_forward(w.numpy(), x.numpy(), FAST, True)
+    ogw, ogx = oracle.target_network_backward_f64(w.numpy(), x.numpy(), go.numpy(), FAST, True)
+    got = {}
+    try:
+        for mode in ("fp32", "tf32x3"):
+            hp.target_network_set_mode(mode)
+            wd = w.to(DEV).requires_grad_(True)
+            xd = x.to(DEV).requires_grad_(True)
+            y = hp.target_network_forward(wd, xd, FAST, True)
+            (y * go.to(DEV)).sum().backward()
+            assert _rel_err(y.detach().cpu().numpy(), oy) < 1e-5, mode
+            assert _rel_err(wd.grad.cpu().numpy(), ogw) < 1e-5, mode
+            assert _rel_err(xd.grad.cpu().numpy(), ogx) < 1e-5, mode
+            y2 = hp.target_network_forward(wd.detach(), xd.detach(), FAST, True)
+            assert torch.equal(y2, y.detach()), mode  # run-to-run identical (no atomics anywhere)
+            got[mode] = y.detach()
+    finally:
+        hp.target_network_set_mode("tf32x3")
+    assert not torch.equal(got["fp32"], got["tf32x3"])  # the switch does select different kernels
+
+
 def test_channels_first_and_shared_cloud(hp, oracle):
     b, n = 6, 515
     w, x, go = _inputs(b, n, FAST, True, seed=9)
