@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_backward_kernel(const TNArgs
 
 }  // namespace hp
 #include "target_network_mma.cuh"
+#include "target_network_tc5.cuh"
 namespace hp {
 
 // ---- generic path: any widths ------------------------------------------------------------------------
@@ -675,7 +676,8 @@ __global__ void __launch_bounds__(TNG_THREADS) tn_generic_backward_kernel(const 
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
-// 0: 3xTF32 on the tensor cores (target_network_mma.cuh, default); 1: the FP32-pipe kernels above
+// 0: 3xTF32 on the tensor cores (target_network_mma.cuh, default); 1: the FP32-pipe kernels above;
+// 2: as 0 with the FORWARD on tcgen05 (target_network_tc5.cuh)
 static int g_tn_mode = 0;
 
 static bool tn_is_fast_shape(int n_layers, const int *dims) {
@@ -743,7 +745,7 @@ extern "C" __attribute__((visibility("default"))) int hp_debug_tn_cta(unsigned l
 #endif
 
 extern "C" int hp_target_network_set_mode(int mode) {
-    HP_REQUIRE(mode == 0 || mode == 1, "hp_target_network_set_mode: mode %d is neither 0 (3xTF32 tensor cores) nor 1 (FP32 pipe)", mode);
+    HP_REQUIRE(mode >= 0 && mode <= 2, "hp_target_network_set_mode: mode %d is neither 0 (3xTF32 tensor cores) nor 1 (FP32 pipe) nor 2 (0 with the forward on tcgen05)", mode);
     g_tn_mode = mode;
     return HP_OK;
 }
@@ -773,6 +775,15 @@ extern "C" int hp_target_network_forward(int b, int n, int n_layers, const int *
     cudaStream_t stream = (cudaStream_t)stream_v;
     a.weights = weights, a.points = points, a.pstride = points_batch_stride, a.out = out;
     a.B = b, a.N = n, a.channels_first = channels_first ? 1 : 0;
+    if (tn_is_fast_shape(n_layers, dims) && g_tn_mode == 2) {
+        const long long tiles = (long long)b * ((n + TN_T - 1) / TN_T), sms = sm_count();
+        const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+        static SmemAttrCache tattr;
+        HP_CUDA(ensure_dynamic_smem(tn_tc5_forward_kernel, T5_SMEM, tattr));
+        tn_tc5_forward_kernel<<<grid, T5_THREADS, T5_SMEM, stream>>>(a);
+        HP_LAUNCH_CHECK("tn_tc5_forward_kernel");
+        return HP_OK;
+    }
     if (tn_is_fast_shape(n_layers, dims) && g_tn_mode == 0) {
         const long long units = (long long)b * ((n + 15) / 16), sms = sm_count();
         const unsigned grid = (unsigned)(units < sms ? units : sms);
@@ -858,7 +869,7 @@ extern "C" int hp_target_network_backward(int b, int n, int n_layers, const int 
         // the counter region moves with b, so a reused workspace cannot be trusted to be zero there
         HP_CUDA(cudaMemsetAsync(a.counters, 0, (size_t)b * sizeof(unsigned int), stream));
         static SmemAttrCache attr0, attr1, mattr0, mattr1;
-        if (g_tn_mode == 0) {
+        if (g_tn_mode != 1) {
             if (grad_points) {
                 HP_CUDA(ensure_dynamic_smem(tn_mma_backward_kernel<true>, TMB_SMEM, mattr1));
                 tn_mma_backward_kernel<true><<<(unsigned)grid, TMB_ALL_THREADS, TMB_SMEM, stream>>>(a);
