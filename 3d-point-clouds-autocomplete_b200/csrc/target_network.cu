@@ -676,8 +676,8 @@ __global__ void __launch_bounds__(TNG_THREADS) tn_generic_backward_kernel(const 
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
-// 0: 3xTF32 on the tensor cores (target_network_mma.cuh, default); 1: the FP32-pipe kernels above;
-// 2: as 0 with the FORWARD on tcgen05 (target_network_tc5.cuh)
+// 0 (default): 3xTF32 on the tensor cores -- forward on tcgen05 (target_network_tc5.cuh), backward on mma.sync (target_network_mma.cuh);
+// 1: the FP32-pipe kernels above;  2: as 0 with the forward on mma.sync as well
 static int g_tn_mode = 0;
 
 static bool tn_is_fast_shape(int n_layers, const int *dims) {
@@ -745,7 +745,7 @@ extern "C" __attribute__((visibility("default"))) int hp_debug_tn_cta(unsigned l
 #endif
 
 extern "C" int hp_target_network_set_mode(int mode) {
-    HP_REQUIRE(mode >= 0 && mode <= 2, "hp_target_network_set_mode: mode %d is neither 0 (3xTF32 tensor cores) nor 1 (FP32 pipe) nor 2 (0 with the forward on tcgen05)", mode);
+    HP_REQUIRE(mode >= 0 && mode <= 2, "hp_target_network_set_mode: mode %d is neither 0 (3xTF32: tcgen05 forward, mma.sync backward) nor 1 (FP32 pipe) nor 2 (3xTF32, mma.sync only)", mode);
     g_tn_mode = mode;
     return HP_OK;
 }
@@ -775,7 +775,7 @@ extern "C" int hp_target_network_forward(int b, int n, int n_layers, const int *
     cudaStream_t stream = (cudaStream_t)stream_v;
     a.weights = weights, a.points = points, a.pstride = points_batch_stride, a.out = out;
     a.B = b, a.N = n, a.channels_first = channels_first ? 1 : 0;
-    if (tn_is_fast_shape(n_layers, dims) && g_tn_mode == 2) {
+    if (tn_is_fast_shape(n_layers, dims) && g_tn_mode == 0) {
         const long long tiles = (long long)b * ((n + TN_T - 1) / TN_T), sms = sm_count();
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
         static SmemAttrCache tattr;
@@ -784,7 +784,7 @@ extern "C" int hp_target_network_forward(int b, int n, int n_layers, const int *
         HP_LAUNCH_CHECK("tn_tc5_forward_kernel");
         return HP_OK;
     }
-    if (tn_is_fast_shape(n_layers, dims) && g_tn_mode == 0) {
+    if (tn_is_fast_shape(n_layers, dims) && g_tn_mode == 2) {
         const long long units = (long long)b * ((n + 15) / 16), sms = sm_count();
         const unsigned grid = (unsigned)(units < sms ? units : sms);
         static SmemAttrCache mattr;

@@ -42,14 +42,27 @@ template <int KTOT>
 __device__ __forceinline__ int t5_canon(int n, int k) {
     return ((n >> 3) * (KTOT >> 2) + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3);
 }
+// W[N][KTOT] (global, row-major) -> hi / lo in canonical order.  Threads walk the CANONICAL positions, so a warp's 32 stores fill one
+// 128-byte core matrix (conflict-free) and its 32 loads are eight 16-byte row pieces; 32 loads in flight per thread (L2 latency).
 template <int KTOT, int N>
 __device__ __forceinline__ void t5_stage_matrix(const float *__restrict__ Wg, float *__restrict__ hi, float *__restrict__ lo, int tid) {
-    for (int i = tid; i < N * KTOT; i += T5_THREADS) {
-        const int n = i / KTOT, k = i - n * KTOT;
-        const float w = __ldg(Wg + i);
-        const int c = t5_canon<KTOT>(n, k);
-        hi[c] = w;
-        lo[c] = w - __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+    constexpr int BATCH = 32, TOTAL = N * KTOT;
+    for (int c0 = tid; c0 < TOTAL; c0 += BATCH * T5_THREADS) {
+        float w[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int c = c0 + u * T5_THREADS;  // canonical position: ((group * KTOT/4 + chunk) * 8 + row) * 4 + kk
+            const int kk = c & 3, r = (c >> 2) & 7, cm = c >> 5, chunk = cm % (KTOT / 4), group = cm / (KTOT / 4);
+            w[u] = c < TOTAL ? __ldg(Wg + (group * 8 + r) * KTOT + chunk * 4 + kk) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int c = c0 + u * T5_THREADS;
+            if (c < TOTAL) {
+                hi[c] = w[u];
+                lo[c] = w[u] - __uint_as_float(__float_as_uint(w[u]) & 0xffffe000u);
+            }
+        }
     }
 }
 // shared-memory matrix descriptor of the K = 8 slice `ks` of a canonical [N][KTOT] matrix
@@ -91,19 +104,52 @@ __device__ __forceinline__ void t5_layer(uint32_t d, uint32_t a_hi, uint32_t a_l
         t5_mma(d, a_hi + 8 * i, bh, idesc, 1u);
     }
 }
-// one 16-column chunk of an accumulator -> bias + ReLU -> hi / lo A operands of the next layer
-__device__ __forceinline__ void t5_epilogue16(uint32_t src, uint32_t dst_hi, uint32_t dst_lo, const float *__restrict__ bias) {
-    uint32_t v[16], lo[16];
-    tmem_load<16>(src, v);
+// tensor-memory <-> registers without a wait per instruction: N columns of this thread's lane, one wait for all of them
+template <int N>
+__device__ __forceinline__ void tmem_load_nowait(uint32_t taddr, uint32_t (&v)[N]) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float x = fmaxf(__uint_as_float(v[i]) + bias[i], 0.f);
-        v[i] = __float_as_uint(x);
-        lo[i] = __float_as_uint(x - __uint_as_float(v[i] & 0xffffe000u));
-    }
-    tmem_store<16>(dst_hi, v);
-    tmem_store<16>(dst_lo, lo);
+    for (int o = 0; o < N; o += 16)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : HP_R16(v, o)
+                     : "r"(taddr + o));
 }
+template <int N>
+__device__ __forceinline__ void tmem_store_nowait(uint32_t taddr, const uint32_t (&v)[N]) {
+#pragma unroll
+    for (int o = 0; o < N; o += 16)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr + o),
+                     HP_I16(v, o)
+                     : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// NC columns of an accumulator -> bias + ReLU -> hi / lo A operands of the next layer (hi may go back in place)
+template <int NC>
+__device__ __forceinline__ void t5_epilogue(uint32_t src, uint32_t dst_hi, uint32_t dst_lo, const float *__restrict__ bias) {
+    uint32_t v[NC], lo[NC];
+    tmem_load_nowait<NC>(src, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < NC; i += 4) {
+        const float4 b4 = *reinterpret_cast<const float4 *>(bias + i);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float x = fmaxf(__uint_as_float(v[i + u]) + bb[u], 0.f);
+            v[i + u] = __float_as_uint(x);
+            lo[i + u] = __float_as_uint(x - __uint_as_float(v[i + u] & 0xffffe000u));
+        }
+    }
+    tmem_store_nowait<NC>(dst_hi, v);
+    tmem_store_nowait<NC>(dst_lo, lo);
+    tmem_wait_st();
+}
+
+#ifdef HP_TM_TRACE
+#define T5_TRACE(role, tile, ev) do { if (blockIdx.x == 0 && lane == 0 && (tile) < 64) { unsigned long long tns_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns_)); g_tm_trace[role][tile][ev] = tns_; } } while (0)
+#else
+#define T5_TRACE(role, tile, ev) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(T5_THREADS, 1) tn_tc5_forward_kernel(const TNArgs a) {
     extern __shared__ __align__(128) float sm[];
@@ -115,6 +161,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tn_tc5_forward_kernel(const TNA
     const int ntiles = (a.N + TN_T - 1) / TN_T;
     const long long TT = (long long)a.B * ntiles;
     const long long f0 = (long long)blockIdx.x * TT / gridDim.x, f1 = (long long)(blockIdx.x + 1) * TT / gridDim.x;
+    TM_CTA(0);
     if (tid == 0) {
         mbar_init(&ready[0], 128), mbar_init(&ready[1], 128);
         mbar_init(&done[0], 1), mbar_init(&done[1], 1);
@@ -155,6 +202,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tn_tc5_forward_kernel(const TNA
         }
         fence_proxy_async();  // generic-proxy stores above -> async-proxy (tensor core) reads
         __syncthreads();
+        if (f == f0) TM_CTA(1);
 
         if (mma_warp) {
             if (lane == 0) {
@@ -162,8 +210,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tn_tc5_forward_kernel(const TNA
                     const int live = (t0 + 1 < fe) ? 2 : 1;
                     for (int step = 0; step < 4; ++step) {
                         for (int s = 0; s < live; ++s) {
+                            T5_TRACE(1, (int)(t0 - f0) + s, step * 3);
                             mbar_wait(&ready[s], ready_phase[s]);
                             ready_phase[s] ^= 1;
+                            T5_TRACE(1, (int)(t0 - f0) + s, step * 3 + 1);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             const uint32_t R0 = tmem + 256 * s, R1 = R0 + 128;
                             if (step == 0) t5_layer<C1, C2>(R0, R1, R1 + 32, sm + T5_W2H, sm + T5_W2L, 0, C1 / 8, false);
@@ -171,6 +221,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tn_tc5_forward_kernel(const TNA
                             else if (step == 2) t5_layer<C3, C4>(R1 + 64, R0, R1, sm + T5_W4H, sm + T5_W4L, 0, 8, false);
                             else t5_layer<C3, C4>(R1 + 64, R0 + 64, R1, sm + T5_W4H, sm + T5_W4L, 8, 8, true);
                             t5_commit(&done[s]);
+                            T5_TRACE(1, (int)(t0 - f0) + s, step * 3 + 2);
                         }
                     }
                 }
@@ -183,82 +234,81 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tn_tc5_forward_kernel(const TNA
             for (long long t0 = f + slot; t0 < fe; t0 += 2) {
                 const int tl = (int)(t0 - (long long)b * ntiles);
                 const int p = tl * TN_T + p_in_tile;
+                if (warp == 0) T5_TRACE(0, (int)(t0 - f0), 0);
                 // ---- layer 1 on the FP32 pipe -> A1 hi | lo ----
                 float x0 = 0.f, x1 = 0.f, x2 = 0.f;
                 if (p < a.N) {
                     const float *px = a.points + (size_t)b * a.pstride + (size_t)p * 3;
                     x0 = __ldg(px), x1 = __ldg(px + 1), x2 = __ldg(px + 2);
                 }
+                {
+                    uint32_t hi[C1], lo[C1];
 #pragma unroll
-                for (int c0 = 0; c0 < C1; c0 += 16) {
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float4 w = *reinterpret_cast<const float4 *>(w1p + (c0 + i) * 4);
+                    for (int i = 0; i < C1; ++i) {
+                        const float4 w = *reinterpret_cast<const float4 *>(w1p + i * 4);
                         const float v = fmaxf(__fmaf_rn(w.z, x2, __fmaf_rn(w.y, x1, __fmaf_rn(w.x, x0, w.w))), 0.f);
                         hi[i] = __float_as_uint(v);
                         lo[i] = __float_as_uint(v - __uint_as_float(hi[i] & 0xffffe000u));
                     }
-                    tmem_store<16>(R1 + c0, hi);
-                    tmem_store<16>(R1 + 32 + c0, lo);
+                    tmem_store_nowait<C1>(R1, hi);
+                    tmem_store_nowait<C1>(R1 + 32, lo);
+                    tmem_wait_st();
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 t5_mbar_arrive(&ready[slot]);
+                if (warp == 0) T5_TRACE(0, (int)(t0 - f0), 1);
                 // ---- layer 2 accumulator -> A2 hi | lo ----
                 mbar_wait(&done[slot], done_phase), done_phase ^= 1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int c0 = 0; c0 < C2; c0 += 16) t5_epilogue16(R0 + c0, R1 + c0, R1 + 64 + c0, bs + c0);
+                if (warp == 0) T5_TRACE(0, (int)(t0 - f0), 2);
+                t5_epilogue<C2>(R0, R1, R1 + 64, bs);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 t5_mbar_arrive(&ready[slot]);
+                if (warp == 0) T5_TRACE(0, (int)(t0 - f0), 3);
                 // ---- layer 3 accumulator, channels 0-63 -> A3a (hi in place, lo over the dead A2) ----
                 mbar_wait(&done[slot], done_phase), done_phase ^= 1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 16) t5_epilogue16(R0 + c0, R0 + c0, R1 + c0, bs + C2 + c0);
+                if (warp == 0) T5_TRACE(0, (int)(t0 - f0), 4);
+                t5_epilogue<64>(R0, R0, R1, bs + C2);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 t5_mbar_arrive(&ready[slot]);
+                if (warp == 0) T5_TRACE(0, (int)(t0 - f0), 5);
                 // ---- channels 64-127 -> A3b: hi in place now, lo once the MMAs over A3a have read R1[0,64) ----
                 {
-                    uint32_t lo[64];
+                    uint32_t v[64], lo[64];
+                    tmem_load_nowait<64>(R0 + 64, v);
+                    tmem_wait_ld();
 #pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_load<16>(R0 + 64 + c0, v);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float x = fmaxf(__uint_as_float(v[i]) + bs[C2 + 64 + c0 + i], 0.f);
-                            v[i] = __float_as_uint(x);
-                            lo[c0 + i] = __float_as_uint(x - __uint_as_float(v[i] & 0xffffe000u));
-                        }
-                        tmem_store<16>(R0 + 64 + c0, v);
+                    for (int i = 0; i < 64; ++i) {
+                        const float x = fmaxf(__uint_as_float(v[i]) + bs[C2 + 64 + i], 0.f);
+                        v[i] = __float_as_uint(x);
+                        lo[i] = __float_as_uint(x - __uint_as_float(v[i] & 0xffffe000u));
                     }
+                    tmem_store_nowait<64>(R0 + 64, v);
                     mbar_wait(&done[slot], done_phase), done_phase ^= 1;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 16) {
-                        uint32_t v[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = lo[c0 + i];
-                        tmem_store<16>(R1 + c0, v);
-                    }
+                    tmem_store_nowait<64>(R1, lo);
+                    tmem_wait_st();
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 t5_mbar_arrive(&ready[slot]);
+                if (warp == 0) T5_TRACE(0, (int)(t0 - f0), 6);
                 // ---- layer 4 accumulator -> bias + ReLU -> layer 5 on the FP32 pipe -> out ----
                 mbar_wait(&done[slot], done_phase), done_phase ^= 1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (warp == 0) T5_TRACE(0, (int)(t0 - f0), 7);
                 float y0 = bs[C2 + C3 + C4], y1 = bs[C2 + C3 + C4 + 1], y2 = bs[C2 + C3 + C4 + 2];
+                {
+                    uint32_t v[C4];
+                    tmem_load_nowait<C4>(R1 + 64, v);
+                    tmem_wait_ld();
 #pragma unroll
-                for (int c0 = 0; c0 < C4; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_load<16>(R1 + 64 + c0, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float x = fmaxf(__uint_as_float(v[i]) + bs[C2 + C3 + c0 + i], 0.f);
-                        y0 = __fmaf_rn(x, w5[c0 + i], y0), y1 = __fmaf_rn(x, w5[C4 + c0 + i], y1), y2 = __fmaf_rn(x, w5[2 * C4 + c0 + i], y2);
+                    for (int i = 0; i < C4; ++i) {
+                        const float x = fmaxf(__uint_as_float(v[i]) + bs[C2 + C3 + i], 0.f);
+                        y0 = __fmaf_rn(x, w5[i], y0), y1 = __fmaf_rn(x, w5[C4 + i], y1), y2 = __fmaf_rn(x, w5[2 * C4 + i], y2);
                     }
                 }
+                if (warp == 0) T5_TRACE(0, (int)(t0 - f0), 8);
                 if (p < a.N) {
                     if (a.channels_first) {
                         float *dst = a.out + (size_t)b * 3 * a.N + p;
@@ -272,8 +322,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tn_tc5_forward_kernel(const TNA
         }
         f = fe;
     }
+    TM_CTA(2);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    TM_CTA(3);
     if (mma_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 

@@ -34,8 +34,9 @@ def _c_dims(layer_out_channels):
 
 def target_network_set_mode(mode: str) -> None:
     """Arithmetic of the tuned 32,64,128,64 kernels, process-wide: "tf32x3" (default: error-compensated 3xTF32 on the tensor
-    cores, within 3e-6 of the reference's fp32 torch.mm chain) or "fp32" (FFMA chains on the CUDA cores)."""
-    modes = {"tf32x3": 0, "fp32": 1, "tcgen05": 2}
+    cores, within 3e-6 of the reference's fp32 torch.mm chain; forward on tcgen05 with the activations in tensor memory, backward on
+    mma.sync), "mma.sync" (the same arithmetic with the forward on mma.sync as well) or "fp32" (FFMA chains on the CUDA cores)."""
+    modes = {"tf32x3": 0, "fp32": 1, "mma.sync": 2}
     if mode not in modes:
         raise ValueError(f"mode must be one of {sorted(modes)}")
     _native.check(_native.load().hp_target_network_set_mode(modes[mode]), "hp_target_network_set_mode")

@@ -210,10 +210,13 @@ HP_API int hp_emd_cost_pairs_fast(int pairs, int n, int m, const float *first, c
 HP_API long long hp_target_network_num_weights(int n_layers, const int *dims_host, int use_bias);
 
 /* Arithmetic of the tuned 3,32,64,128,64,3 kernels (process-wide; other widths always run the generic FP32 kernels):
- *   0 (default)  error-compensated 3xTF32 on the tensor cores (every operand split into hi + lo, three mma.sync per product,
- *                fp32 accumulation; weight gradients accumulated per 128-point tile and summed in fp32): within 3e-6 of the
- *                fp32 torch.mm chain of target_network.py:31-38 (measured, profiles/r02_tf32x3_study.txt; bar 1e-5);
- *   1            plain fp32 FFMA chains on the CUDA cores (round-1 kernels).
+ *   0 (default)  error-compensated 3xTF32 on the tensor cores (every operand split into hi + lo, three tensor-core products per fp32
+ *                product, fp32 accumulation; weight gradients accumulated per 128-point tile and summed in fp32): within 3e-6 of the
+ *                fp32 torch.mm chain of target_network.py:31-38 (measured, profiles/r02_tn_error_margins.txt; bar 1e-5).  The forward
+ *                runs on tcgen05 (kind::tf32, accumulators and activations in tensor memory: it allocates all 512 columns of the
+ *                SM's tensor memory while it runs), the backward on mma.sync with the running gradient in tensor memory;
+ *   1            plain fp32 FFMA chains on the CUDA cores (round-1 kernels);
+ *   2            as 0 with the forward on mma.sync as well (no tcgen05.mma).
  * Returns HP_ERR_INVALID_ARGUMENT for any other value. */
 HP_API int hp_target_network_set_mode(int mode);
 

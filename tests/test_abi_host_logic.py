@@ -65,6 +65,7 @@ def test_target_network_mode_switch_validates(hp, lib):
     assert lib.hp_target_network_set_mode(7) == INVALID
     assert b"neither 0" in lib.hp_last_error_message()
     assert lib.hp_target_network_set_mode(1) == hp._native.HP_OK   # fp32 FFMA kernels
-    assert lib.hp_target_network_set_mode(0) == hp._native.HP_OK   # back to the default (3xTF32 on the tensor cores)
+    assert lib.hp_target_network_set_mode(2) == hp._native.HP_OK   # 3xTF32 on mma.sync only
+    assert lib.hp_target_network_set_mode(0) == hp._native.HP_OK   # back to the default (3xTF32: tcgen05 forward, mma.sync backward)
     with pytest.raises(ValueError):
         hp.target_network_set_mode("bf16")

@@ -96,15 +96,15 @@ def test_forward_backward_vs_oracle_fast_shape(hp, oracle, b, n, use_bias):
 
 
 def test_both_arithmetic_modes_hold_the_bar(hp, oracle):
-    """The default (error-compensated 3xTF32 on the tensor cores) and the fp32 FFMA kernels against the same oracle; a sample
-    whose tiles are shared by several CTAs (n = 2500: partial-gradient fold) and a ragged tail tile."""
+    """The default (error-compensated 3xTF32: tcgen05 forward, mma.sync backward), the all-mma.sync variant and the fp32 FFMA kernels
+    against the same oracle; a sample whose tiles are shared by several CTAs (n = 2500: partial-gradient fold) and a ragged tail tile."""
     b, n = 5, 2500
     w, x, go = _inputs(b, n, FAST, True, seed=77)
     oy = oracle.target_network_forward(w.numpy(), x.numpy(), FAST, True)
     ogw, ogx = oracle.target_network_backward_f64(w.numpy(), x.numpy(), go.numpy(), FAST, True)
     got = {}
     try:
-        for mode in ("fp32", "tf32x3"):
+        for mode in ("fp32", "mma.sync", "tf32x3"):
             hp.target_network_set_mode(mode)
             wd = w.to(DEV).requires_grad_(True)
             xd = x.to(DEV).requires_grad_(True)
@@ -118,7 +118,7 @@ def test_both_arithmetic_modes_hold_the_bar(hp, oracle):
             got[mode] = y.detach()
     finally:
         hp.target_network_set_mode("tf32x3")
-    assert not torch.equal(got["fp32"], got["tf32x3"])  # the switch does select different kernels
+    assert not torch.equal(got["fp32"], got["tf32x3"]) and not torch.equal(got["mma.sync"], got["tf32x3"])  # the switch selects kernels
 
 
 def test_channels_first_and_shared_cloud(hp, oracle):

@@ -32,7 +32,7 @@ def f64_forward(w, x, loc, use_bias):
     return h
 
 
-for mode in ("tf32x3", "fp32"):
+for mode in ("tf32x3", "mma.sync", "fp32"):
     hp.target_network_set_mode(mode)
     worst = [0.0, 0.0, 0.0]
     for (b, n, seed) in [(4, 2048, 1), (8, 2048, 2), (70, 256, 3), (160, 130, 4), (2, 4096, 5), (3, 2048, 6)]:
