@@ -86,6 +86,13 @@ __device__ __forceinline__ void t5_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
+// one lane of a converged warp (elect.sync): the issuing thread of tcgen05.mma / tcgen05.commit.  The whole warp walks the issue loop
+// with warp-uniform operands, so the descriptors stay in uniform registers instead of being moved there per instruction.
+__device__ __forceinline__ bool t5_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void t5_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -97,6 +104,7 @@ template <int KTOT, int N>
 __device__ __forceinline__ void t5_layer(uint32_t d, uint32_t a_hi, uint32_t a_lo, const float *Wh, const float *Wl, int ks0, int nks,
                                          bool accumulate) {
     constexpr uint32_t idesc = t5_idesc(N);
+#pragma unroll 4
     for (int i = 0; i < nks; ++i) {
         const uint64_t bh = t5_bdesc<KTOT>(Wh, ks0 + i), bl = t5_bdesc<KTOT>(Wl, ks0 + i);
         t5_mma(d, a_lo + 8 * i, bh, idesc, (accumulate || i > 0) ? 1u : 0u);
@@ -205,28 +213,28 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tn_tc5_forward_kernel(const TNA
         if (f == f0) TM_CTA(1);
 
         if (mma_warp) {
-            if (lane == 0) {
-                for (long long t0 = f; t0 < fe; t0 += 2) {
-                    const int live = (t0 + 1 < fe) ? 2 : 1;
-                    for (int step = 0; step < 4; ++step) {
-                        for (int s = 0; s < live; ++s) {
-                            T5_TRACE(1, (int)(t0 - f0) + s, step * 3);
-                            mbar_wait(&ready[s], ready_phase[s]);
-                            ready_phase[s] ^= 1;
-                            T5_TRACE(1, (int)(t0 - f0) + s, step * 3 + 1);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint32_t R0 = tmem + 256 * s, R1 = R0 + 128;
+            for (long long t0 = f; t0 < fe; t0 += 2) {
+                const int live = (t0 + 1 < fe) ? 2 : 1;
+                for (int step = 0; step < 4; ++step) {
+                    for (int s = 0; s < live; ++s) {
+                        T5_TRACE(1, (int)(t0 - f0) + s, step * 3);
+                        mbar_wait(&ready[s], ready_phase[s]);
+                        ready_phase[s] ^= 1;
+                        T5_TRACE(1, (int)(t0 - f0) + s, step * 3 + 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t R0 = tmem + 256 * s, R1 = R0 + 128;
+                        if (t5_elect_one()) {
                             if (step == 0) t5_layer<C1, C2>(R0, R1, R1 + 32, sm + T5_W2H, sm + T5_W2L, 0, C1 / 8, false);
                             else if (step == 1) t5_layer<C2, C3>(R0, R1, R1 + 64, sm + T5_W3H, sm + T5_W3L, 0, C2 / 8, false);
                             else if (step == 2) t5_layer<C3, C4>(R1 + 64, R0, R1, sm + T5_W4H, sm + T5_W4L, 0, 8, false);
                             else t5_layer<C3, C4>(R1 + 64, R0 + 64, R1, sm + T5_W4H, sm + T5_W4L, 8, 8, true);
                             t5_commit(&done[s]);
-                            T5_TRACE(1, (int)(t0 - f0) + s, step * 3 + 2);
                         }
+                        __syncwarp();
+                        T5_TRACE(1, (int)(t0 - f0) + s, step * 3 + 2);
                     }
                 }
             }
-            __syncwarp();
         } else {
             const uint32_t lanes = (uint32_t)(32 * (warp & 3)) << 16;
             const uint32_t R0 = tmem + lanes + 256 * slot, R1 = R0 + 128;
