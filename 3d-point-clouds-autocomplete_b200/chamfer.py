@@ -268,6 +268,43 @@ def _device_one(device: torch.device) -> torch.Tensor:
     return t
 
 
+_shape_cache = {}
+
+
+def _step_shape_info(lib, b: int, n: int, m: int):
+    """(supported, workspace bytes) of the fused step for a shape: two C calls, cached (the eager module is host-bound)."""
+    key = (b, n, m)
+    info = _shape_cache.get(key)
+    if info is None:
+        info = _shape_cache[key] = (bool(lib.hp_chamfer_step_supported(b, n, m)), int(lib.hp_chamfer_workspace_bytes(b, n, m)))
+    return info
+
+
+def _chamfer_step_lean(xyz1: torch.Tensor, xyz2: torch.Tensor):
+    """``chamfer_step`` for an upstream gradient of one, trimmed for the eager module: the caller has validated the inputs and the
+    shape; ONE float allocation holds loss | grad1 | grad2 | dist1 | dist2 and one int allocation both index maps (the module only
+    hands out the first three), no per-call size queries.  Returns the float buffer (loss at [0]) and where the gradients sit in it."""
+    b, n, m = xyz1.size(0), xyz1.size(1), xyz2.size(1)
+    dev = xyz1.device
+    lib = _native.load()
+    nf1, nf2 = b * n * 3, b * m * 3
+    o_g1 = 4
+    o_g2 = o_g1 + ((nf1 + 3) & ~3)
+    o_d1 = o_g2 + ((nf2 + 3) & ~3)
+    o_d2 = o_d1 + ((b * n + 3) & ~3)
+    out = torch.empty(o_d2 + b * m, dtype=torch.float32, device=dev)  # every section starts 16-byte aligned
+    idx = torch.empty(((b * n + 3) & ~3) + b * m, dtype=torch.int32, device=dev)
+    base, ibase = out.data_ptr(), idx.data_ptr()
+    p_g1, p_g2, p_d1, p_d2 = base + 4 * o_g1, base + 4 * o_g2, base + 4 * o_d1, base + 4 * o_d2
+    with on_device_of(xyz1) as stream:
+        ws = zeroed_workspace(dev, stream, _step_shape_info(lib, b, n, m)[1], "chamfer")
+        rc = lib.hp_chamfer_step(b, n, xyz1.data_ptr(), m, xyz2.data_ptr(), _device_one(dev).data_ptr(), p_d1, ibase, p_d2,
+                                 ibase + 4 * ((b * n + 3) & ~3), base, p_g1, p_g2, ws.data_ptr(), ws.numel(), stream)
+        if rc != 0:
+            check_with_workspace(rc, "hp_chamfer_step", ws)
+    return out, (o_g1, nf1, o_g2, nf2, b, n, m)
+
+
 class _ChamferLossFusedFunction(Function):
     """The training-step form: when a gradient will be asked for, the forward runs the fused two-kernel step (ring kernel +
     sectioned tail) for an upstream gradient of one -- loss AND both gradients -- and the backward only scales them by the
@@ -276,14 +313,17 @@ class _ChamferLossFusedFunction(Function):
 
     @staticmethod
     def forward(ctx, xyz1, xyz2):
-        loss, _d1, _i1, _d2, _i2, g1, g2 = chamfer_step(xyz1, xyz2, _device_one(xyz1.device))
-        ctx.save_for_backward(g1, g2)
-        return loss.reshape(())
+        out, where = _chamfer_step_lean(xyz1, xyz2)
+        ctx.save_for_backward(out)
+        ctx.where = where
+        return out[0]
 
     @staticmethod
     def backward(ctx, grad_loss):
-        g1, g2 = ctx.saved_tensors
-        return g1 * grad_loss, g2 * grad_loss
+        (out,) = ctx.saved_tensors
+        o_g1, nf1, o_g2, nf2, b, n, m = ctx.where
+        scaled = out[o_g1:o_g2 + nf2] * grad_loss  # both gradients sit side by side: one launch
+        return scaled[:nf1].view(b, n, 3), scaled[o_g2 - o_g1:o_g2 - o_g1 + nf2].view(b, m, 3)
 
 
 class ChamferLoss(nn.Module):
@@ -310,7 +350,11 @@ class ChamferLoss(nn.Module):
         xyz1, xyz2 = gts.contiguous(), preds.contiguous()
         needs_grad = torch.is_grad_enabled() and (xyz1.requires_grad or xyz2.requires_grad)
         if needs_grad and xyz1.dim() == 3 and xyz2.dim() == 3 and xyz1.size(0) == xyz2.size(0) and xyz1.size(0) > 0 \
-                and chamfer_step_supported(xyz1.size(0), xyz1.size(1), xyz2.size(1)):
+                and xyz1.size(1) > 0 and xyz2.size(1) > 0 \
+                and _step_shape_info(_native.load(), xyz1.size(0), xyz1.size(1), xyz2.size(1))[0]:
+            check_points(xyz1, "gts")
+            check_points(xyz2, "preds")
+            check_same_device(xyz1, xyz2)
             return _ChamferLossFusedFunction.apply(xyz1, xyz2)
         return _ChamferLossFunction.apply(xyz1, xyz2)
 
