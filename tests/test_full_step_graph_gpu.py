@@ -77,10 +77,14 @@ def test_graph_step_follows_the_reference_trainer(hp):
     for i, (a, b) in enumerate(zip(ours, ref_losses)):
         assert a == pytest.approx(b, rel=2e-3 if i else 1e-5), (i, ours, ref_losses)
     assert ours[-1] < ours[0]  # it trains
+    # Parameters: Adam moves every weight by about lr per step whatever the size of its gradient, so a weight whose gradient is itself
+    # fp32 noise (zero-initialised biases, dead channels) can end anywhere within the total travel of the two runs, 2 * steps * lr; that
+    # is the per-element bound.  Taken together the parameters must agree far better than that (measured 2e-4 of their norm).
+    num = den = 0.0
     for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref_model.named_parameters()):
         assert n1 == n2
-        # Adam moves every parameter by about lr per step whatever the size of its gradient, so where a gradient is itself fp32 noise
-        # (the zero-initialised biases of the first layers) the two runs may differ by a fraction of the total travel steps * lr = 4e-4
-        # (measured: up to 8 % of it, varying from run to run with the encoder's cuDNN algorithm choice)
-        assert float((p1 - p2).abs().max()) <= 2e-3 * float(p2.abs().max()) + 0.25 * steps * 1e-4, n1
+        assert float((p1 - p2).abs().max()) <= 2.1 * steps * 1e-4, n1
+        num += float((p1 - p2).double().pow(2).sum())
+        den += float(p2.double().pow(2).sum())
+    assert (num / den) ** 0.5 <= 2e-3, (num / den) ** 0.5
     assert step.rec.shape == (bsz, n_gt, 3)
