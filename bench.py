@@ -272,12 +272,12 @@ def _other_paths(torch, hp, dev, fp32_peak, mufu_peak, hbm_peak_gbs, flush, stre
     out["target_network_fwd+bwd_B64_N2048"] = {
         "ms": ms, "algorithmic_tflops": flop / ms / 1e9, "frac_fp32_peak": flop / (ms * 1e-3) / fp32_peak,
         "executed_frac_fp32_peak": executed / (ms * 1e-3) / fp32_peak,
-        "arithmetic": "error-compensated 3xTF32 on mma.sync (three tensor-core products per fp32 product, fp32 accumulation; the running weight "
-                      "gradient lives in tensor memory): within 3e-6 of the fp32 chain, bar 1e-5 (tests, tools/tn_error_margins.py)",
+        "arithmetic": "error-compensated 3xTF32 (three tensor-core products per fp32 product, fp32 accumulation): forward on tcgen05 with the "
+                      "activations in tensor memory, backward on mma.sync with the running weight gradient in tensor memory: within 3e-6 of the fp32 chain, bar 1e-5 (tests, tools/tn_error_margins.py)",
         "mma_tf32_peak_tflops_measured": tf32_peak / 1e12,
         "frac_of_3xtf32_tensor_bound": 3.0 * executed / (ms * 1e-3) / tf32_peak,
-        "what": "frac_fp32_peak is north_star's yardstick (algorithmic FLOP over the FP32 FFMA peak); the kernels themselves are bound by the "
-                "tensor pipe: executed FLOP x 3 products over the measured mma.sync tf32 peak"}
+        "what": "frac_fp32_peak is north_star's yardstick (algorithmic FLOP over the FP32 FFMA peak); frac_of_3xtf32_tensor_bound = "
+                "executed FLOP x 3 products over the measured LEGACY mma.sync tf32 peak (the backward's pipe; the tcgen05 forward has 4x that)"}
     hp.target_network_set_mode("fp32")
     try:
         tng1 = hp.TargetNetworkStepGraph(tb, tn, LOC, True, dev, channels_first=True)
@@ -700,7 +700,8 @@ def run_ours(args):
                     "pipelined_independent_steps_ms_per_step": pipe_ms,
                     "pipelined_api": "ChamferHostPipeline.submit/result (4 buffer sets, one stream each; loss AND both gradients copied "
                                      "back): a THROUGHPUT over independent steps, not the latency of a trainer's dependent loop"},
-            "eager_api": {"ms_per_step": statistics.mean(eager_ms), "value": PAIRS_PER_STEP / (statistics.mean(eager_ms) * 1e-3),
+            "eager_api": {"ms_per_step": statistics.median(eager_ms), "value": PAIRS_PER_STEP / (statistics.median(eager_ms) * 1e-3),
+                          "mean_ms_per_step": statistics.mean(eager_ms),
                           "note": "ChamferLoss()(preds, gts); loss.backward() through torch autograd, no graph: CPU launch path bound"},
             "gpu_launches": step.launches_per_replay * args.steps,  # timed `value` region only
             "roofline": roofline,
