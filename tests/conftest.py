@@ -92,6 +92,8 @@ def _zero_restored_workspaces_stay_zero(request):
     torch.cuda.synchronize()
     dirty = []
     for key, ws in list(glue._workspaces.items()):
+        if key[2] != "chamfer":  # the TargetNetwork scratch makes no such promise (its call initialises what it needs)
+            continue
         if bool(ws.any()):
             nz = torch.nonzero(ws.view(-1))[:8].view(-1).tolist()
             dirty.append((key, int(ws.numel()), nz))
