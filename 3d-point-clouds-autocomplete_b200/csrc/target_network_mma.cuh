@@ -399,7 +399,7 @@ __device__ __forceinline__ void tm_wgrad(const float *__restrict__ act, int zc, 
 #endif
     const float *zr = act + t * TM_ACT_LD + zc + g;
     const float *ar = act + t * TM_ACT_LD + ac + g;
-#pragma unroll 1
+#pragma unroll(MT * NT >= 16 ? 1 : 4)
     for (int p0 = 0; p0 < TN_T; p0 += 8) {
         uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm = tmem_base_slot + ((uint32_t)(32 * (hw & 3)) << 16);
     // helpers: small gradients, a few elements per thread
-    //   sC0..2: dW5[0..2][ht] (ht < 64) | sB: db3[ht] | sA0: db4[ht] (ht < 64), db2[ht - 64] | sA1: db1[ht] (ht < 32), db5[ht - 64] (64 <= ht < 67)
+    //   sC0..2: dW5[0..2][ht] (ht < 64) | sB: db3[ht] | sA0: db4[ht] (ht < 64), db2[ht - 64] | sA1: db1[ht - 96] (ht >= 96), db5[ht - 64] (64 <= ht < 67)
     //   sD: dW1[ht] (ht < 96)
     float sC0 = 0.f, sC1 = 0.f, sC2 = 0.f, sB = 0.f, sA0 = 0.f, sA1 = 0.f, sD = 0.f;
     if (helper) {
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
             if (a.offb[2] >= 0) dst[a.offb[2] + ht] = sB;
             if (ht < 64) { if (a.offb[3] >= 0) dst[a.offb[3] + ht] = sA0; }
             else { if (a.offb[1] >= 0) dst[a.offb[1] + ht - 64] = sA0; }
-            if (ht < 32) { if (a.offb[0] >= 0) dst[a.offb[0] + ht] = sA1; }
+            if (ht >= 96) { if (a.offb[0] >= 0) dst[a.offb[0] + ht - 96] = sA1; }
             else if (ht >= 64 && ht < 67) { if (a.offb[4] >= 0) dst[a.offb[4] + ht - 64] = sA1; }
             if (ht < 96) dst[a.offw[0] + ht] = sD;
             sC0 = sC1 = sC2 = sB = sA0 = sA1 = sD = 0.f;
@@ -849,7 +849,7 @@ __global__ void __launch_bounds__(TMB_ALL_THREADS, 1) tn_mma_backward_kernel(con
                 }
                 sD += (s + s2) + (s3 + s4);
             }
-            if (ht < 32) sA1 += tm_col_sum(act + TM_A1 + ht);
+            if (ht >= 96) sA1 += tm_col_sum(act + TM_A1 + ht - 96);  // db1 on the fourth helper warp, beside dW1 on the other three
             if (GRAD_POINTS) {
                 for (int i = ht; i < 3 * TN_T; i += TMB_HELP_THREADS) {
                     const int p = i / 3, c = i - p * 3;
