@@ -392,7 +392,7 @@ __device__ __forceinline__ void tm_store_rows(float *__restrict__ row0, const fl
     }
 }
 // dW tile on the tensor cores: acc[mi*NT+ni] += sum over the tile's 128 points of Z[p][zc + 16mi + g (+8)] * A[p][ac + 8ni + 2t (+1)]
-template <int MT, int NT>
+template <int MT, int NT, int PTS = TN_T>
 __device__ __forceinline__ void tm_wgrad(const float *__restrict__ act, int zc, int ac, float (&acc)[MT * NT][4], int g, int t) {
 #ifdef HP_TMB_NO_WGRAD
     return;
@@ -400,7 +400,7 @@ __device__ __forceinline__ void tm_wgrad(const float *__restrict__ act, int zc, 
     const float *zr = act + t * TM_ACT_LD + zc + g;
     const float *ar = act + t * TM_ACT_LD + ac + g;
 #pragma unroll(MT * NT >= 16 ? 1 : 4)
-    for (int p0 = 0; p0 < TN_T; p0 += 8) {
+    for (int p0 = 0; p0 < PTS; p0 += 8) {
         uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi) {
@@ -431,7 +431,8 @@ __device__ __forceinline__ void tm_wgrad(const float *__restrict__ act, int zc, 
 }
 // running gradient (tensor memory) -> dW[O][K] (flat): rows o0 + 16mi + g (+8), columns k0 + 8ni + 2t (+1); the columns are cleared
 template <int MT, int NT, int K>
-__device__ __forceinline__ void tm_flush_dw(uint32_t taddr, float *__restrict__ dst, int o0, int k0, int g, int t) {
+__device__ __forceinline__ void tm_flush_dw(uint32_t taddr, float *__restrict__ dst, int o0, int k0, int g, int t,
+                                            const float *__restrict__ addend = nullptr) {
 #pragma unroll
     for (int h = 0; h < MT * NT * 4; h += 16) {
         uint32_t v[16];
@@ -439,20 +440,24 @@ __device__ __forceinline__ void tm_flush_dw(uint32_t taddr, float *__restrict__ 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int tile = (h >> 2) + q, mi = tile / NT, ni = tile - mi * NT;
-            float *d = dst + (o0 + 16 * mi + g) * K + k0 + 8 * ni + 2 * t;
-            d[0] = __uint_as_float(v[4 * q]), d[1] = __uint_as_float(v[4 * q + 1]);
-            d[8 * K] = __uint_as_float(v[4 * q + 2]), d[8 * K + 1] = __uint_as_float(v[4 * q + 3]);
+            const int off = (o0 + 16 * mi + g) * K + k0 + 8 * ni + 2 * t;
+            float x0 = __uint_as_float(v[4 * q]), x1 = __uint_as_float(v[4 * q + 1]), x2 = __uint_as_float(v[4 * q + 2]),
+                  x3 = __uint_as_float(v[4 * q + 3]);
+            if (addend) x0 += addend[off], x1 += addend[off + 1], x2 += addend[off + 8 * K], x3 += addend[off + 8 * K + 1];
+            dst[off] = x0, dst[off + 1] = x1;
+            dst[off + 8 * K] = x2, dst[off + 8 * K + 1] = x3;
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0u;
         tmem_store<16>(taddr + h, v);
     }
 }
-// column sum over the tile's 128 rows
+// column sum over the tile's rows
+template <int PTS = TN_T>
 __device__ __forceinline__ float tm_col_sum(const float *__restrict__ col) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 4
-    for (int p = 0; p < TN_T; p += 4) {
+    for (int p = 0; p < PTS; p += 4) {
         s0 += col[p * TM_ACT_LD], s1 += col[(p + 1) * TM_ACT_LD];
         s2 += col[(p + 2) * TM_ACT_LD], s3 += col[(p + 3) * TM_ACT_LD];
     }
