@@ -220,11 +220,7 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-#ifdef HP_TMF_MAXNREG
-__global__ void __launch_bounds__(TMF_THREADS, 1) __maxnreg__(HP_TMF_MAXNREG) tn_mma_forward_kernel(const TNArgs a) {
-#else
 __global__ void __launch_bounds__(TMF_THREADS, 1) tn_mma_forward_kernel(const TNArgs a) {
-#endif
     extern __shared__ __align__(16) float sm[];
     __shared__ uint64_t bars[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -238,13 +234,6 @@ __global__ void __launch_bounds__(TMF_THREADS, 1) tn_mma_forward_kernel(const TN
     if (u0 >= u1) return;
     const int bfirst = (int)(u0 / upn), blast = (int)((u1 - 1) / upn);
     if (tid == 0) mbar_init(&bars[0], TMF_THREADS), mbar_init(&bars[1], TMF_THREADS);
-#ifdef HP_TMF_TMEM_PROBE
-    __shared__ uint32_t probe_slot;
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&probe_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-#endif
     tmf_fill_const<TMF_THREADS>(a, sm, tid);
     tmf_fill_const<TMF_THREADS>(a, sm + TMF_FLOATS, tid);
     __syncthreads();
@@ -298,10 +287,6 @@ __global__ void __launch_bounds__(TMF_THREADS, 1) tn_mma_forward_kernel(const TN
             }
         }
     }
-#ifdef HP_TMF_TMEM_PROBE
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(probe_slot) : "memory");
-#endif
 }
 
 // ---- backward -----------------------------------------------------------------------------------------------------------------

@@ -160,7 +160,7 @@ __device__ __forceinline__ void t5_epilogue(uint32_t src, uint32_t dst_hi, uint3
 #endif
 
 __global__ void __launch_bounds__(T5_THREADS, 1) tn_tc5_forward_kernel(const TNArgs a) {
-    extern __shared__ __align__(128) float sm[];
+    extern __shared__ __align__(16) float sm[];  // no-swizzle descriptors need 16-byte alignment only
     __shared__ uint64_t ready[2], done[2];  // per slot: epilogue -> MMA (128 arrivals), MMA -> epilogue (one commit)
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
