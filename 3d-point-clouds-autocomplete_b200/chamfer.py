@@ -203,13 +203,17 @@ def chamfer_step_supported(b: int, n: int, m: int) -> bool:
     return bool(_native.load().hp_chamfer_step_supported(b, n, m))
 
 
-def chamfer_step(xyz1: torch.Tensor, xyz2: torch.Tensor, grad_loss: torch.Tensor):
+def chamfer_step(xyz1: torch.Tensor, xyz2: torch.Tensor, grad_loss: torch.Tensor, out=None):
     """One training step of the fused loss: ``loss = ChamferLoss()(xyz2, xyz1); loss.backward(grad_loss)`` in two kernels
     (ring forward + one tail kernel that unpacks, reduces the loss, inverts the index maps in shared memory and gathers
     both gradients).  ``grad_loss`` is a device scalar known before the step is enqueued (the trainer's loss
     coefficient, core/epoch_loops.py:25-26).  Returns (loss[1], dist1, idx1, dist2, idx2, grad_xyz1, grad_xyz2),
     bit-identical to ``chamfer_forward(want_inverse=True)`` + ``chamfer_backward``; shapes the tail kernel cannot
-    hold in shared memory take exactly that three-kernel path."""
+    hold in shared memory take exactly that three-kernel path.
+
+    ``out``: optional tuple of seven preallocated contiguous tensors of exactly those shapes and dtypes (e.g. batch
+    slices of larger buffers) that receive the results instead of fresh allocations; only for shapes with
+    ``chamfer_step_supported``."""
     check_points(xyz1, "xyz1")
     check_points(xyz2, "xyz2")
     check_same_device(xyz1, xyz2)
@@ -218,18 +222,29 @@ def chamfer_step(xyz1: torch.Tensor, xyz2: torch.Tensor, grad_loss: torch.Tensor
     b, n, m = xyz1.size(0), xyz1.size(1), xyz2.size(1)
     lib = _native.load()
     if b == 0 or n == 0 or m == 0 or not lib.hp_chamfer_step_supported(b, n, m):
+        if out is not None:
+            raise RuntimeError(f"chamfer_step: out= needs a shape of the fused step (b={b} n={n} m={m} is not)")
         loss, d1, i1, d2, i2, inv = chamfer_forward(xyz1, xyz2, want_inverse=True)
         g1, g2 = chamfer_backward(xyz1, xyz2, i1, i2, grad_loss, inv)
         return loss, d1, i1, d2, i2, g1, g2
     dev = xyz1.device
     g = grad_loss.to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
-    dist1 = torch.empty((b, n), dtype=torch.float32, device=dev)
-    idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
-    dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
-    idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
-    loss = torch.empty((1,), dtype=torch.float32, device=dev)
-    grad1 = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
-    grad2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+    if out is not None:
+        loss, dist1, idx1, dist2, idx2, grad1, grad2 = out
+        want = (((1,), torch.float32), ((b, n), torch.float32), ((b, n), torch.int32), ((b, m), torch.float32),
+                ((b, m), torch.int32), ((b, n, 3), torch.float32), ((b, m, 3), torch.float32))
+        for t, (shape, dtype) in zip(out, want):
+            if tuple(t.shape) != shape or t.dtype != dtype or t.device != dev or not t.is_contiguous():
+                raise RuntimeError(f"chamfer_step: out tensor {tuple(t.shape)} {t.dtype} on {t.device} does not match "
+                                   f"contiguous {shape} {dtype} on {dev}")
+    else:
+        dist1 = torch.empty((b, n), dtype=torch.float32, device=dev)
+        idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+        dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
+        idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        grad1 = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
+        grad2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
     with on_device_of(xyz1) as stream:
         nbytes = lib.hp_chamfer_workspace_bytes(b, n, m)
         ws = zeroed_workspace(dev, stream, nbytes, "chamfer")

@@ -54,7 +54,10 @@ def _capture(fn, device, warmup: int = 3):
 class ChamferStepGraph:
     """Chamfer forward (both directions + loss) and backward (both gradients, upstream grad 1) as one graph."""
 
-    def __init__(self, batch: int, n: int, m: int, device, with_host_io: bool = False):
+    def __init__(self, batch: int, n: int, m: int, device, with_host_io: bool = False, split_host_io=None):
+        """``split_host_io`` (only with ``with_host_io``): run ``run_from_host_loss_only`` as consecutive part-batch steps so that
+        the next part's host->device copies fly under the current part's kernels (default: one part; see ``_host_io_bounds``
+        for the measurement that made it an opt-in)."""
         self.device = torch.device(device)
         with torch.cuda.device(self.device):
             self.xyz1 = torch.zeros(batch, n, 3, device=self.device)
@@ -104,8 +107,76 @@ class ChamferStepGraph:
                     self.loss_host.copy_(loss, non_blocking=True)
                     return loss, g1, g2
 
-                self.host_graph_loss, self._host_loss_outs, _ = _capture(host_step_loss_only, self.device)
+                self.host_io_parts = self._host_io_bounds(batch, n, m, split_host_io)  # [0, b1, ..., batch]
+                self.host_io_split = len(self.host_io_parts) > 2
+                if self.host_io_split:
+                    # The step is PCIe-bound from the host (C2: 1.5 MB in = 45-60 us before a 58 us step).  Clouds are independent
+                    # and the loss is a sum over clouds, so the batch runs as consecutive part-batch steps: the copies of part k+1
+                    # are a parallel branch of the graph (own stream during capture) that flies under the kernels of part k.
+                    # Results land in batch slices of full-size buffers; the loss is the sum of the parts' losses (each part in
+                    # the library's fixed order, then one fp32 reduction over the parts).
+                    dev, bounds = self.device, self.host_io_parts
+                    nparts = len(bounds) - 1
+                    self._s_loss = torch.empty(nparts, 1, device=dev)
+                    self._s_loss_sum = torch.empty(1, device=dev)
+                    self._s_d1, self._s_i1 = torch.empty(batch, n, device=dev), torch.empty(batch, n, dtype=torch.int32, device=dev)
+                    self._s_d2, self._s_i2 = torch.empty(batch, m, device=dev), torch.empty(batch, m, dtype=torch.int32, device=dev)
+                    self._s_g1, self._s_g2 = torch.empty(batch, n, 3, device=dev), torch.empty(batch, m, 3, device=dev)
+                    self._copy_stream = torch.cuda.Stream(device=dev)
+
+                    def copy_in(lo, hi):
+                        self.xyz1[lo:hi].copy_(self.xyz1_host[lo:hi], non_blocking=True)
+                        self.xyz2[lo:hi].copy_(self.xyz2_host[lo:hi], non_blocking=True)
+
+                    def part(k):
+                        lo, hi = bounds[k], bounds[k + 1]
+                        outs = (self._s_loss[k], self._s_d1[lo:hi], self._s_i1[lo:hi], self._s_d2[lo:hi], self._s_i2[lo:hi],
+                                self._s_g1[lo:hi], self._s_g2[lo:hi])
+                        chamfer_step(self.xyz1[lo:hi], self.xyz2[lo:hi], self._one, out=outs)
+
+                    def host_step_loss_only_split():
+                        main = torch.cuda.current_stream(dev)
+                        copy_in(bounds[0], bounds[1])
+                        arrived = [torch.cuda.Event() for _ in range(nparts)]
+                        arrived[0].record(main)
+                        with torch.cuda.stream(self._copy_stream):  # later parts: behind the first part's copies, beside its kernels
+                            self._copy_stream.wait_event(arrived[0])
+                            for k in range(1, nparts):
+                                copy_in(bounds[k], bounds[k + 1])
+                                arrived[k].record(self._copy_stream)
+                        part(0)
+                        for k in range(1, nparts):
+                            main.wait_event(arrived[k])
+                            part(k)
+                        main.wait_stream(self._copy_stream)
+                        torch.sum(self._s_loss, dim=0, out=self._s_loss_sum)
+                        self.loss_host.copy_(self._s_loss_sum, non_blocking=True)
+                        return self._s_loss_sum, self._s_g1, self._s_g2
+
+                    self.host_graph_loss, self._host_loss_outs, _ = _capture(host_step_loss_only_split, self.device)
+                else:
+                    self.host_graph_loss, self._host_loss_outs, _ = _capture(host_step_loss_only, self.device)
                 self.d2h_bytes_loss_only = 4
+
+    def _host_io_bounds(self, batch: int, n: int, m: int, split):
+        """Batch boundaries of the parts ``run_from_host_loss_only`` runs one after the other.  ``split``: None / False / 0 / 1 = one
+        part (the default); True = two halves; an int P = P near-equal parts; a sequence = explicit boundaries.  Every part must be
+        a shape of the fused step.  Measured at C2 on a B200 (``tools/time_host_split.py``, ``profiles/r02_host_split.txt``): the two
+        copies take 41 us, the step 58 us, one part 100 us at best; two halves 109 us, three parts 120 us -- every extra part costs
+        8-10 us (two more launches on grids of less than a wave, the cross-branch dependencies of the graph) and the copies do not
+        hide fully, so the split is an opt-in, not the default."""
+        if split is None:
+            split = 1
+        if isinstance(split, (list, tuple)):
+            bounds = [int(v) for v in split]
+            if bounds[0] != 0 or bounds[-1] != batch or any(b1 <= b0 for b0, b1 in zip(bounds, bounds[1:])):
+                raise ValueError(f"split_host_io boundaries must ascend from 0 to {batch}: {bounds}")
+        else:
+            parts = max(1, min(int(split), batch))
+            bounds = [(batch * k) // parts for k in range(parts + 1)]
+        if len(bounds) > 2 and not all(chamfer_step_supported(b1 - b0, n, m) for b0, b1 in zip(bounds, bounds[1:])):
+            bounds = [0, batch]
+        return bounds
 
     def replay(self):
         """Inputs: self.xyz1 / self.xyz2 (device).  Outputs refreshed in place: loss [1], dist*, idx*, grad_xyz*."""
@@ -126,7 +197,8 @@ class ChamferStepGraph:
 
     def run_from_host_loss_only(self):
         """Pinned-host inputs (``xyz1_host`` / ``xyz2_host``) -> ``loss_host``; the gradients stay on the device
-        (``grad_outputs_on_device()``).  One graph: two H2D copies, ring kernel, tail kernel, one 4-byte D2H copy."""
+        (``grad_outputs_on_device()``).  One graph: H2D copies, ring kernel, tail kernel, one 4-byte D2H copy -- as two half-batch
+        steps with the second half's copies under the first half's kernels when ``host_io_split``."""
         if self.host_graph is None:
             raise RuntimeError("construct ChamferStepGraph(with_host_io=True) to use run_from_host_loss_only")
         self.host_graph_loss.replay()

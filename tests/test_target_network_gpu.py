@@ -259,6 +259,58 @@ def test_graph_capture_matches_eager(hp):
     assert torch.equal(lh.reshape(()), ref.detach().cpu()) and torch.equal(g1h, ad.grad.cpu()) and torch.equal(g2h, cd.grad.cpu())
 
 
+@pytest.mark.parametrize("b,split", [(5, True), (4, True), (4, False), (4, None)])
+def test_host_graph_loss_only_split_matches_eager(hp, b, split):
+    """ChamferStepGraph.run_from_host_loss_only, also as two half-batch steps whose second-half copies fly under the first half's
+    kernels (split_host_io): per-cloud results (distances, indices, both gradients) are bit-identical to the eager step -- a cloud's
+    numbers do not depend on which launch carried it -- and the loss is the sum of the halves' losses; replays with new inputs
+    (zero-restored workspace shared by the two halves) stay exact."""
+    n, m = 700, 900
+    cg = hp.ChamferStepGraph(b, n, m, DEV, with_host_io=True, split_host_io=split)
+    assert cg.host_io_split == bool(split)  # opt-in: None means one part
+    g = torch.Generator().manual_seed(31 + b)
+    one = torch.ones((), device=DEV)
+    for rep in range(3):
+        a, c = torch.rand(b, n, 3, generator=g) - 0.5, torch.rand(b, m, 3, generator=g) - 0.5
+        if rep == 2:
+            c = c * 0.02  # skewed assignment: the tail's general path
+        cg.xyz1_host.copy_(a)
+        cg.xyz2_host.copy_(c)
+        lh = cg.run_from_host_loss_only()
+        torch.cuda.synchronize()
+        g1, g2 = cg.grad_outputs_on_device()
+        loss, _d1, _i1, _d2, _i2, e1, e2 = hp.chamfer_step(a.to(DEV), c.to(DEV), one)
+        assert torch.equal(g1, e1) and torch.equal(g2, e2)
+        if cg.host_io_split:
+            h = b // 2
+            la = hp.chamfer_step(a[:h].to(DEV), c[:h].to(DEV), one)[0]
+            lb = hp.chamfer_step(a[h:].to(DEV), c[h:].to(DEV), one)[0]
+            assert torch.equal(lh, (la + lb).cpu())
+            assert torch.equal(cg._s_d1, _d1) and torch.equal(cg._s_i1, _i1) and torch.equal(cg._s_d2, _d2) and torch.equal(cg._s_i2, _i2)
+            torch.testing.assert_close(lh, loss.cpu(), rtol=2e-6, atol=0)
+        else:
+            assert torch.equal(lh, loss.cpu())
+
+
+def test_chamfer_step_out_buffers(hp):
+    b, n, m = 3, 300, 257
+    g = torch.Generator().manual_seed(4)
+    a, c = (torch.rand(b, n, 3, generator=g) - 0.5).to(DEV), (torch.rand(b, m, 3, generator=g) - 0.5).to(DEV)
+    one = torch.ones((), device=DEV)
+    ref = hp.chamfer_step(a, c, one)
+    big = [torch.zeros(2, 1, device=DEV), torch.zeros(b + 2, n, device=DEV), torch.zeros(b + 2, n, dtype=torch.int32, device=DEV),
+           torch.zeros(b + 2, m, device=DEV), torch.zeros(b + 2, m, dtype=torch.int32, device=DEV), torch.zeros(b + 2, n, 3, device=DEV),
+           torch.zeros(b + 2, m, 3, device=DEV)]
+    out = tuple([big[0][1]] + [t[1:1 + b] for t in big[1:]])
+    got = hp.chamfer_step(a, c, one, out=out)
+    for r, o, t in zip(ref, got, big):
+        assert torch.equal(r, o)
+    for t in big[1:]:
+        assert not bool(t[0].any()) and not bool(t[-1].any())  # nothing outside the slices was touched
+    with pytest.raises(RuntimeError):
+        hp.chamfer_step(a, c, one, out=tuple([big[0][1]] + [t[:b + 1] for t in big[1:]]))
+
+
 def test_host_pipeline_matches_eager(hp):
     """ChamferHostPipeline overlaps H2D / compute / D2H over several buffer sets: every ticket's results must equal the
     eager module on the same inputs, also when slots are reused."""
