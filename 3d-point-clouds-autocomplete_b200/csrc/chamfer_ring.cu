@@ -673,6 +673,8 @@ __global__ void __launch_bounds__(RF_MERGE_THREADS) nn_ring_unpack_kernel(const 
     u64 *src = (dir2 ? a.colkey : a.rowkey) + (size_t)cloud * cnt;
     float *dist = (dir2 ? a.dist2 : a.dist1) + (size_t)cloud * cnt;
     int *idx = (dir2 ? a.idx2 : a.idx1) + (size_t)cloud * cnt;
+    // launched programmatically dependent on the ring kernel: resident while that drains, running once its keys are complete
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (!dir2 && tid == 0 && a.tickets) a.ticket[cloud] = 0u;  // the ring kernel's arrivals are not needed on this path
     // Phase 1 only READS the keys: the device-scope fence of the loss ticket below then has no stores of this SM to
     // drain (a fence issued after the 3 stores per element costs ~10 us).  Phase 2 (unpack_store) writes the outputs.
@@ -1185,6 +1187,24 @@ bool nn_ring_step_supported(int n, int m) { return n > 0 && m > 0 && rf_tail_sme
 
 enum RingMode { RING_UNPACK = 0, RING_STEP = 1, RING_ONLY = 2 };
 
+// The unpack kernel follows the ring kernel programmatically dependent (its CTAs become resident while the ring grid drains and
+// start from griddepcontrol.wait the moment it completes).
+static cudaError_t launch_unpack(void (*kern)(const RingNNArgs), unsigned grid, size_t smem, cudaStream_t stream, const RingNNArgs &a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(RF_MERGE_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs, cfg.numAttrs = 1;
+#ifdef HP_BENCH_BUILD
+    {
+        const char *e = getenv("HP_NO_PDL");
+        if (e && atoi(e)) cfg.numAttrs = 0;
+    }
+#endif
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
                                int *idx2, float *loss, int *inv1, int *inv2, const float *step_g, float *step_grad1,
                                float *step_grad2, void *workspace, cudaStream_t stream, RingMode mode);
@@ -1314,9 +1334,9 @@ static int nn_ring_launch_impl(int b, int n, const float *xyz1, int m, const flo
                                        : (size_t)a.sort_n * sizeof(unsigned int);
         static SmemAttrCache attr;
         if (smem > 40 * 1024) HP_CUDA(ensure_dynamic_smem(nn_ring_unpack_kernel<true>, smem, attr));
-        nn_ring_unpack_kernel<true><<<(unsigned)ugrid, RF_MERGE_THREADS, smem, stream>>>(a);
+        HP_CUDA(launch_unpack(nn_ring_unpack_kernel<true>, (unsigned)ugrid, smem, stream, a));
     } else {
-        nn_ring_unpack_kernel<false><<<(unsigned)ugrid, RF_MERGE_THREADS, 0, stream>>>(a);
+        HP_CUDA(launch_unpack(nn_ring_unpack_kernel<false>, (unsigned)ugrid, 0, stream, a));
     }
     HP_LAUNCH_CHECK("nn_ring_unpack_kernel / nn_ring_tail_kernel");
     return HP_OK;
