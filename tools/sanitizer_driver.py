@@ -34,6 +34,8 @@ hp.MatchCost(p, q, match)
 hp.MatchCostGrad(p, q, match)
 hp.emd_cost_pairs(p, p.flip(0))
 hp.emd_cost_pairs(p, p.flip(0), fast=True)                                      # fused P3 + P1 sweep
+ia = (torch.arange(640, dtype=torch.int32) % 2).to(dev)                           # 640 pairs: the passes fill the GPU, so the auction's
+hp.emd_cost_pairs(p, q, ia, (1 - ia).contiguous())                                # chain of kernels launches programmatically dependent
 hp.batch_pairwise_dist(p, q)                                                     # a2: the expansion-form matrix
 s1 = (torch.rand(6, 128, 3, generator=g) - 0.5).to(dev)
 s2 = (torch.rand(5, 128, 3, generator=g) - 0.5).to(dev)
