@@ -165,8 +165,10 @@ class ChamferStepGraph:
         copies take 41 us, the step 58 us, one part 100 us at best; two halves 109 us, three parts 120 us -- every extra part costs
         8-10 us (two more launches on grids of less than a wave, the cross-branch dependencies of the graph) and the copies do not
         hide fully, so the split is an opt-in, not the default."""
-        if split is None:
+        if split is None or split is False:
             split = 1
+        elif split is True:
+            split = 2
         if isinstance(split, (list, tuple)):
             bounds = [int(v) for v in split]
             if bounds[0] != 0 or bounds[-1] != batch or any(b1 <= b0 for b0, b1 in zip(bounds, bounds[1:])):
