@@ -60,8 +60,12 @@ class ChamferStepGraph:
         for the measurement that made it an opt-in)."""
         self.device = torch.device(device)
         with torch.cuda.device(self.device):
-            self.xyz1 = torch.zeros(batch, n, 3, device=self.device)
-            self.xyz2 = torch.zeros(batch, m, 3, device=self.device)
+            # both inputs live in ONE allocation (second cloud set 16-byte aligned behind the first): with host I/O the pinned
+            # staging buffer has the same layout and a step's inputs arrive with a single host->device copy
+            off2 = (batch * n * 3 + 3) & ~3
+            self._xyz_both = torch.zeros(off2 + batch * m * 3, device=self.device)
+            self.xyz1 = self._xyz_both[:batch * n * 3].view(batch, n, 3)
+            self.xyz2 = self._xyz_both[off2:].view(batch, m, 3)
             # any finite placeholder works for capture; callers overwrite xyz1 / xyz2 before replaying
             self.xyz1.uniform_(-0.5, 0.5)
             self.xyz2.uniform_(-0.5, 0.5)
@@ -77,8 +81,9 @@ class ChamferStepGraph:
 
             self.host_graph = None
             if with_host_io:
-                self.xyz1_host = torch.empty(batch, n, 3).pin_memory()
-                self.xyz2_host = torch.empty(batch, m, 3).pin_memory()
+                self._xyz_both_host = torch.zeros(self._xyz_both.numel()).pin_memory()
+                self.xyz1_host = self._xyz_both_host[:batch * n * 3].view(batch, n, 3)
+                self.xyz2_host = self._xyz_both_host[off2:].view(batch, m, 3)
                 self.loss_host = torch.empty(1).pin_memory()
                 self.grad_xyz1_host = torch.empty(batch, n, 3).pin_memory()
                 self.grad_xyz2_host = torch.empty(batch, m, 3).pin_memory()
@@ -86,8 +91,7 @@ class ChamferStepGraph:
                 self.xyz2_host.copy_(self.xyz2)
 
                 def host_step():
-                    self.xyz1.copy_(self.xyz1_host, non_blocking=True)
-                    self.xyz2.copy_(self.xyz2_host, non_blocking=True)
+                    self._xyz_both.copy_(self._xyz_both_host, non_blocking=True)
                     loss, _d1, _i1, _d2, _i2, g1, g2 = chamfer_step(self.xyz1, self.xyz2, self._one)
                     self.loss_host.copy_(loss, non_blocking=True)
                     self.grad_xyz1_host.copy_(g1, non_blocking=True)
@@ -101,8 +105,7 @@ class ChamferStepGraph:
                 def host_step_loss_only():
                     # what a trainer's step moves: inputs in, the loss value out; the gradients stay on the device for the
                     # TargetNetwork backward (core/epoch_loops.py:19-39 reads only .item() of the losses)
-                    self.xyz1.copy_(self.xyz1_host, non_blocking=True)
-                    self.xyz2.copy_(self.xyz2_host, non_blocking=True)
+                    self._xyz_both.copy_(self._xyz_both_host, non_blocking=True)
                     loss, _d1, _i1, _d2, _i2, g1, g2 = chamfer_step(self.xyz1, self.xyz2, self._one)
                     self.loss_host.copy_(loss, non_blocking=True)
                     return loss, g1, g2
@@ -199,8 +202,8 @@ class ChamferStepGraph:
 
     def run_from_host_loss_only(self):
         """Pinned-host inputs (``xyz1_host`` / ``xyz2_host``) -> ``loss_host``; the gradients stay on the device
-        (``grad_outputs_on_device()``).  One graph: H2D copies, ring kernel, tail kernel, one 4-byte D2H copy -- as two half-batch
-        steps with the second half's copies under the first half's kernels when ``host_io_split``."""
+        (``grad_outputs_on_device()``).  One graph: ONE H2D copy of both cloud sets, ring kernel, tail kernel, one 4-byte D2H
+        copy -- or part-batch steps with the next part's copies under the current part's kernels when ``host_io_split``."""
         if self.host_graph is None:
             raise RuntimeError("construct ChamferStepGraph(with_host_io=True) to use run_from_host_loss_only")
         self.host_graph_loss.replay()
