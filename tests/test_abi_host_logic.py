@@ -69,3 +69,20 @@ def test_target_network_mode_switch_validates(hp, lib):
     assert lib.hp_target_network_set_mode(0) == hp._native.HP_OK   # back to the default (3xTF32: tcgen05 forward, mma.sync backward)
     with pytest.raises(ValueError):
         hp.target_network_set_mode("bf16")
+
+
+def test_host_io_split_boundaries(hp):
+    """ChamferStepGraph._host_io_bounds: which batch slices run_from_host_loss_only runs one after the other (host logic only)."""
+    G = hp.graphs.ChamferStepGraph
+    obj = object.__new__(G)
+    bounds = lambda split, batch=5: G._host_io_bounds(obj, batch, 700, 900, split)  # noqa: E731
+    assert bounds(None) == bounds(False) == bounds(0) == bounds(1) == [0, 5]        # the default: one part
+    assert bounds(True) == bounds(2) == [0, 2, 5]
+    assert bounds(3) == [0, 1, 3, 5] and bounds(9) == [0, 1, 2, 3, 4, 5]            # never more parts than clouds
+    assert bounds([0, 4, 5]) == [0, 4, 5] and bounds((0, 5)) == [0, 5]
+    for bad in ([1, 5], [0, 3, 3, 5], [0, 4]):
+        with pytest.raises(ValueError):
+            bounds(bad)
+    assert bounds(2, batch=8) == [0, 4, 8]
+    # a part the fused step cannot take (clouds above 4096 points) falls back to one part
+    assert G._host_io_bounds(obj, 4, 5000, 5000, 2) == [0, 4]
