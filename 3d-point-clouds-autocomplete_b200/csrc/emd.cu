@@ -60,6 +60,9 @@ struct EmdArgs {
     int first_level;              // P3: match = w instead of match += w
     int cp_stride;
     int pdl;                      // host side: launch the chain's kernels programmatically dependent (see pdl_trigger)
+    // Exhausted points of the second cloud (remainR == 0) drop out of every later pass, see emd_compact_kernel:
+    int *active;                  // [pairs][m] indices l with remainR[l] > 0, ascending (nullptr: every point, no compaction)
+    int *active_cnt;              // [pairs]
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -122,6 +125,10 @@ __global__ void __launch_bounds__(THREADS) emd_pass_kernel(const EmdArgs a) {
     const float *__restrict__ C = (MODE == 2) ? X1 : X2;
     float *st = a.state + (size_t)pair * 2 * (n + m);
     const float *colw = (MODE == 1) ? st + n : (MODE == 2) ? st + n + m : st + n + m + n;  // remainR | ratioL | ratioR
+    // compaction (never with MATCH: that path writes match in place and keeps every column): the points of the second cloud
+    // that still have mass, ascending -- the COLUMNS of passes 1 and 3, the ROWS of pass 2
+    const bool compact = !MATCH && a.active != nullptr;
+    const int *__restrict__ alist = compact ? a.active + (size_t)pair * m : nullptr;
     const float level = -powf(4.0f, (float)a.j);  // approxmatch.cu:56, evaluated on the device like the reference
     // The reference evaluates __expf(level*d) as ex2((d*level)*log2e) with two roundings.  level is a power of two, so
     // d*level is exact and (d*level)*log2e == d*(level*log2e) bit for bit (level*log2e is exact as well): ONE multiply.
@@ -131,9 +138,23 @@ __global__ void __launch_bounds__(THREADS) emd_pass_kernel(const EmdArgs a) {
     f32x2 qx[RQ], qy[RQ], qz[RQ];
     float acc[RQ], rl[RQ], cost[RQ];
     int row[RQ];
+    int nc_act = nc;  // columns this pass sweeps: all of them, or the compacted list (passes 1 and 3)
+    if (MODE == 2 && compact) {
+        // rows = the second cloud's points that still have mass; the list is a result of the chain, so nothing is read ahead
+        pdl_wait();
+        const int cnt = a.active_cnt[pair];
+        if (rt * (THREADS * RQ) >= cnt) return;  // block-uniform: nothing left for this row tile (its rows keep remainR = ratioR = 0)
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+            const int pos = rt * (THREADS * RQ) + q * THREADS + tid;
+            row[q] = pos < cnt ? alist[pos] : nr;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) row[q] = rt * (THREADS * RQ) + q * THREADS + tid;
+    }
 #pragma unroll
     for (int q = 0; q < RQ; ++q) {
-        row[q] = rt * (THREADS * RQ) + q * THREADS + tid;
         float x = 0.f, y = 0.f, z = 0.f;
         rl[q] = 0.f;
         if (row[q] < nr) x = __ldg(R + (size_t)row[q] * 3 + 0), y = __ldg(R + (size_t)row[q] * 3 + 1), z = __ldg(R + (size_t)row[q] * 3 + 2);
@@ -141,19 +162,25 @@ __global__ void __launch_bounds__(THREADS) emd_pass_kernel(const EmdArgs a) {
         acc[q] = (MODE == 1 && s == 0) ? 1e-9f : 0.f;  // approxmatch.cu:68 (P1) / :117,169 (P2, P3)
         cost[q] = 0.f;
     }
-    pdl_wait();  // the previous pass (or its combine) is complete: state readable, partial / costpart / match writable
+    if (!(MODE == 2 && compact)) pdl_wait();  // the previous pass (or its combine) is complete: state readable, partial / costpart / match writable
     if (MODE == 3) {
 #pragma unroll
         for (int q = 0; q < RQ; ++q)
             if (row[q] < nr) rl[q] = st[n + m + row[q]];  // ratioL[k]
     }
+    if (MODE != 2 && compact) nc_act = a.active_cnt[pair];
 
-    const int c_begin = s * a.span, c_end = min(nc, c_begin + a.span);
+    // A column with zero weight adds exactly nothing to any sum (fma(e, 0, acc) == acc), so sweeping the compacted list in its
+    // ascending order gives the bits of the full sweep.  Column slices (SPLIT) partition the LIST.
+    const int c_begin = s * a.span, c_end = min(nc_act, c_begin + a.span);
     for (int c0 = c_begin; c0 < c_end; c0 += EMD_CC) {
         for (int i = tid; i < EMD_CC; i += THREADS) {
-            const int c = c0 + i;
+            const int p = c0 + i;
             float x = 0.f, y = 0.f, z = 0.f, w = 0.f;  // zero weight: padded columns add exactly nothing
-            if (c < c_end) x = __ldg(C + (size_t)c * 3 + 0), y = __ldg(C + (size_t)c * 3 + 1), z = __ldg(C + (size_t)c * 3 + 2), w = colw[c];
+            if (p < c_end) {
+                const int c = (MODE != 2 && compact) ? alist[p] : p;
+                x = __ldg(C + (size_t)c * 3 + 0), y = __ldg(C + (size_t)c * 3 + 1), z = __ldg(C + (size_t)c * 3 + 2), w = colw[c];
+            }
             xs[i] = x, ys[i] = y, zs[i] = z, ws[i] = w;
         }
         __syncthreads();
@@ -371,12 +398,58 @@ __global__ void emd_combine_kernel(const EmdArgs a) {
     const size_t total = (size_t)a.pairs * nr;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int pair = (int)(i / nr), r = (int)(i % nr);
+        // compaction: pass 2 left no partial sums for exhausted rows (remainR == 0); their remainR / ratioR stay 0
+        if (MODE == 2 && a.active != nullptr && a.state[(size_t)pair * 2 * (a.n + a.m) + a.n + r] <= 0.f) continue;
         const float *p = a.partial + (size_t)pair * a.S * a.rstride + r;
         float acc = p[0];
         for (int s = 1; s < a.S; ++s) acc += p[(size_t)s * a.rstride];
         emd_row_epilogue<MODE>(acc, a.state + (size_t)pair * 2 * (a.n + a.m), a.n, a.m, r,
                                a.hist ? a.hist + ((size_t)pair * 9 + a.level_index) * (a.n + a.m) : nullptr);
     }
+}
+
+// Compaction, once per level before pass 1.  A point l of the second cloud whose remainR has reached 0 (the clamp of
+// approxmatch.cu:140 hits exactly 0 whenever the point is over-subscribed -- measured on uniform clouds of 2048 points: 10 % of
+// the points after the first level, 43 / 65 / 78 / 87 / 93 / 98 / 99 % after the following ones) takes no further part in the
+// auction: as a column of pass 1 its weight remainR is 0, as a row of pass 2 its results do not depend on the sum
+// (sumr = acc * 0, ratioR = 0, remainR stays 0, :137-140), as a column of pass 3 its weight ratioR is 0.  fma(e, 0, acc) == acc,
+// so leaving these points out changes no bit of any sum as long as the others keep their ascending order.  This kernel writes
+// the stable list of the points with remainR > 0 per cloud pair and zeroes ratioR (and the recorded per-level ratioR) of the
+// others, which pass 2 no longer visits.  One CTA per pair.
+constexpr int CP_THREADS = 256;
+__global__ void __launch_bounds__(CP_THREADS) emd_compact_kernel(const EmdArgs a) {
+    __shared__ int wsum[CP_THREADS / 32];
+    pdl_trigger();
+    pdl_wait();
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = a.n, m = a.m;
+    float *st = a.state + (size_t)pair * 2 * (n + m);
+    const float *remainR = st + n;
+    float *ratioR = st + n + m + n;
+    float *hist_level = a.hist ? a.hist + ((size_t)pair * 9 + a.level_index) * (n + m) : nullptr;
+    int *list = a.active + (size_t)pair * m;
+    int base = 0;
+    for (int c0 = 0; c0 < m; c0 += CP_THREADS) {  // block-uniform trip count
+        const int c = c0 + tid;
+        const bool act = c < m && remainR[c] > 0.f;
+        if (c < m && !act) {
+            ratioR[c] = 0.f;
+            if (hist_level) hist_level[n + c] = 0.f;
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) wsum[warp] = __popc(ball);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < CP_THREADS / 32; ++w) {
+            before += (w < warp) ? wsum[w] : 0;
+            total += wsum[w];
+        }
+        if (act) list[base + before + __popc(ball & ((1u << lane) - 1u))] = c;
+        base += total;
+        __syncthreads();  // wsum reusable
+    }
+    if (tid == 0) a.active_cnt[pair] = base;
 }
 
 // remainL = multiL, remainR = multiR with the reference's INTEGER division (approxmatch.cu:36-43,49-52)
@@ -658,6 +731,7 @@ static int run_auction(EmdArgs a, cudaStream_t stream) {
         a.level_index = li;
         a.first_level = (li == 0);
         int rc;
+        if (!MATCH && a.active != nullptr) HP_CUDA(launch_chain(a.pdl != 0, emd_compact_kernel, (unsigned)a.pairs, CP_THREADS, stream, a));
         a.span = span_rows_m;
         if ((rc = launch_pass_auto<1, SPLIT, false, false>(a, stream)) != HP_OK) return rc;
         if (SPLIT) {
@@ -782,7 +856,8 @@ extern "C" int hp_approxmatch(int b, int n, int m, const float *xyz1, const floa
 
 extern "C" size_t hp_approxmatch_workspace_bytes(int b, int n, int m) {
     if (b <= 0 || n <= 0 || m <= 0) return 16;
-    return (size_t)b * 9 * ((size_t)n + m) * sizeof(float) + 64;  // per-level ratioL | ratioR
+    // per-level ratioL | ratioR, then the compaction list of every batch element and its length
+    return ((size_t)b * 9 * ((size_t)n + m) + (size_t)b * ((size_t)m + 1)) * sizeof(float) + 64;
 }
 
 extern "C" int hp_approxmatch_ws(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *temp,
@@ -805,6 +880,8 @@ extern "C" int hp_approxmatch_ws(int b, int n, int m, const float *xyz1, const f
     // the 1e-5 bar; the match-free metrics path (hp_emd_cost_pairs) may split because the COST stays within 1e-6.
     a.partial = nullptr;
     a.hist = reinterpret_cast<float *>(workspace);
+    a.active = reinterpret_cast<int *>(a.hist + (size_t)b * 9 * ((size_t)n + m));
+    a.active_cnt = a.active + (size_t)b * m;
     a.match = match, a.costpart = nullptr;
     a.n = n, a.m = m, a.pairs = b, a.S = 1, a.rstride = 0, a.cp_stride = 0;
     int rc = run_auction<false, false, false>(a, stream);
@@ -833,7 +910,8 @@ extern "C" size_t hp_emd_cost_workspace_bytes(int pairs, int n, int m) {
     const size_t partial = S > 1 ? (size_t)2 * pairs * S * big : 0;  // two sums in the fused P3 + P1 sweep
     const int rt_max = (n + 127) / 128;  // upper bound: the smallest row tile is 64 threads x 2 rows
     const size_t costpart = (size_t)pairs * 9 * rt_max * S;
-    return (state + partial + costpart) * sizeof(float) + 64;
+    const size_t active = (size_t)pairs * ((size_t)m + 1);  // compaction list and its length per pair (ints)
+    return (state + partial + costpart + active) * sizeof(float) + 64;
 }
 
 static int emd_cost_pairs_impl(int pairs, int n, int m, const float *first, const int *ia, const float *second, const int *ib,
@@ -860,6 +938,11 @@ static int emd_cost_pairs_impl(int pairs, int n, int m, const float *first, cons
     a.partial2 = S > 1 ? ws : nullptr;
     ws += S > 1 ? (size_t)pairs * S * big : 0;
     a.costpart = ws;
+    ws += (size_t)pairs * 9 * ((n + 127) / 128) * S;  // the bound hp_emd_cost_workspace_bytes reserves
+    if (!fused) {  // the opt-in fused sweep keeps every column (its two sums want different lists)
+        a.active = reinterpret_cast<int *>(ws);
+        a.active_cnt = a.active + (size_t)pairs * m;
+    }
     a.match = nullptr;
     a.n = n, a.m = m, a.pairs = pairs, a.S = S, a.rstride = (int)big;
     const int rt3 = row_tiles_auto(pairs, n, S);  // the row tiling P3 will use (same rule as launch_pass_auto<3>)
