@@ -187,7 +187,10 @@ HP_API int hp_matchcostgrad(int b, int n, int m, const float *xyz1, const float 
 /* Fused, match-free EMD cost for the metrics path (utils/metrics.py:71-76,147: match_cost is
  * only ever used forward-only there): cost[p] = match_cost(first[ia[p]], second[ib[p]]) for
  * `pairs` cloud pairs addressed through index lists (ia/ib may be NULL = identity).
- *   first [na, npts, 3], second [nb, npts, 3].  workspace: hp_emd_cost_workspace_bytes(). */
+ *   first [na, npts, 3], second [nb, npts, 3].  workspace: hp_emd_cost_workspace_bytes().
+ * Points of the second cloud whose mass is exhausted (remainR == 0 after the clamp of approxmatch.cu:140) are left
+ * out of every later pass: their terms are exact zeros, so no sum changes (csrc/emd.cu: emd_compact_kernel); the
+ * running time therefore depends on the data, the result does not. */
 HP_API size_t hp_emd_cost_workspace_bytes(int pairs, int n, int m);
 HP_API int hp_emd_cost_pairs(int pairs, int n, int m, const float *first, const int *ia,
                       const float *second, const int *ib, float *cost, void *workspace,
