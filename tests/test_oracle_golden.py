@@ -173,3 +173,21 @@ def test_jsd_restatement_matches_reference(oracle, golden_cpu):
         assert np.array_equal(oracle.occupancy_counts(g["jsd_smp"], res), g[f"jsd_cnt_r{res}"].astype(np.float64))
         got = oracle.jsd_between_point_cloud_sets(g["jsd_smp"], g["jsd_ref"], res)
         assert abs(got - float(g[f"jsd_r{res}"])) <= 1e-9 * abs(float(g[f"jsd_r{res}"]))
+
+
+def test_emd_exhausted_points_premise_of_the_compaction(oracle):
+    """The premise of emd_compact_kernel, checked on the CPU restatement of approxmatch.cu: the clamp of
+    approxmatch.cu:140 leaves most points of the second cloud with remainR == 0 EXACTLY (not merely small), so their later terms
+    are exact zeros; and a point whose remainR is 0 receives nothing more (its column of `match` stops growing), which is what
+    allows the kernels to leave it out."""
+    rng = np.random.default_rng(11)
+    n = 512
+    a = (rng.random((2, n, 3), dtype=np.float32) - 0.5)
+    b = (rng.random((2, n, 3), dtype=np.float32) - 0.5)
+    match, temp = oracle.approx_match(a, b)
+    remain_l, remain_r = temp[:, :n], temp[:, n:2 * n]
+    assert (remain_r >= 0).all() and (remain_l >= 0).all()
+    assert (remain_r == 0).mean() > 0.9            # exhausted exactly, the common case
+    received = match.sum(axis=2)                    # mass point l of the second cloud received, match is [B, m, n]
+    assert (received[remain_r == 0] > 0.99).all()   # exhausted points are full (multiR = 1 for n == m) ...
+    assert (received <= 1.0 + 1e-4).all()           # ... and nobody is over-full
