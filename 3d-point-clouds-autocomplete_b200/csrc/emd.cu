@@ -24,7 +24,9 @@
 // hp_emd_cost_pairs_fast is an opt-in shortcut: P3 of level j and P1 of level j-1 sweep the same (row, column) pairs and P1's sum
 // needs nothing of P3 but the row scalar remainL[k], so they run as ONE sweep (emd_fused31_kernel) with ONE ex2 for both -- the
 // next level's e' = ex2(d * scale') is evaluated and the current level's e = e'^4 follows by two multiplies (level' = level / 4):
-// 3 instead of 4 MUFU operations per pair and level, 19 launches instead of 27, 1.2x faster at B=32, 2048^2 (1.16 vs 1.43 ms).
+// 3 instead of 4 MUFU operations per pair and level, 19 launches instead of 27, 1.2x faster at B=32, 2048^2 (1.16 vs 1.43 ms)
+// when both swept every point.  Since the exact path leaves exhausted points out (emd_compact_kernel) it is the faster one
+// (1.18 vs 1.25 ms): the fused sweep keeps every column because its two sums want the lists of two different levels.
 // e'^4 deviates from ex2.approx(d * scale) by ~1e-6 relative, P3 then no longer sends exactly what P2 accepted, and the
 // nine-level feedback amplifies that to up to 2.1e-5 on the cost (same test) -- above the 1e-5 parity bar, hence not the default.
 // (Giving P2 the same e'^4, so that P2 and P3 agree with each other but not with P1, measured WORSE: 1.6e-4.)

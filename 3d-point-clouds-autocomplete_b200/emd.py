@@ -92,7 +92,8 @@ def emd_cost_pairs(first: torch.Tensor, second: torch.Tensor, ia: Optional[torch
 
     No [pairs, M, N] matrix is ever written: the auction's per-level weights are folded into the cost
     inside pass 3 (utils/metrics.py only ever uses match_cost under no_grad).  ``fast=True`` takes hp_emd_cost_pairs_fast
-    (one ex2 shared between two passes: 1.2x faster, but up to 2.1e-5 off the reference's cost -- outside the 1e-5 bar)."""
+    (one ex2 shared between two passes, but up to 2.1e-5 off the reference's cost -- outside the 1e-5 bar -- and, since the exact
+    path leaves exhausted points out, no longer faster either: a measured variant, not a recommendation)."""
     check_points(first, "first")
     check_points(second, "second")
     check_same_device(first, second)
