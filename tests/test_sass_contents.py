@@ -1,7 +1,9 @@
 """The shipped library is sm_100a machine code of the kinds DESIGN.md claims (no GPU needed: cuobjdump reads the cubin).
   * Chamfer / EMD / metrics: packed fp32 (FFMA2 / FADD2), bulk-TMA staging (UBLKCP), MUFU.EX2 -- K = 3 stays on the CUDA cores;
   * TargetNetwork forward: tcgen05 (UTCHMMA) with tensor-memory loads / stores (LDTM / STTM);
-  * TargetNetwork backward: legacy tensor path (HMMA.1688.F32.TF32) with the running gradient in tensor memory."""
+  * TargetNetwork backward: legacy tensor path (HMMA.1688.F32.TF32) with the running gradient in tensor memory;
+  * programmatic dependent launches: griddepcontrol.launch_dependents / .wait (PREEXIT / ACQBULK) in the Chamfer ring -> tail / unpack
+    pair and along the EMD auction's chain of kernels, incl. its compaction kernel."""
 import collections
 import re
 import shutil
@@ -28,3 +30,16 @@ def test_library_sass_matches_the_design(hp):
     for needle in ("nn_ring_kernel", "nn_ring_tail_kernel", "tn_tc5_forward_kernel", "tn_mma_backward_kernel", "tn_mma_forward_kernel",
                    "tn_forward_kernel", "tn_backward_kernel", "emd_pass_kernel", "pairwise_cd_kernel", "batch_pairwise_dist_kernel"):
         assert any(needle in f for f in functions), needle
+    assert any("emd_compact_kernel" in f for f in functions)
+    # per function: the opcodes between its "Function :" line and the next
+    per = {}
+    for chunk in re.split(r"^\s*Function : ", out, flags=re.M)[1:]:
+        name, _, body = chunk.partition("\n")
+        per[name.strip()] = set(re.findall(r"\b(PREEXIT|ACQBULK)\b", body))
+    def has(needle, op):
+        hits = [ops_ for f, ops_ in per.items() if needle in f]
+        return bool(hits) and all(op in ops_ for ops_ in hits)
+    assert has("nn_ring_kernel", "PREEXIT")                                                 # lets the tail / unpack kernel in early
+    assert has("nn_ring_unpack_kernel", "ACQBULK") and has("nn_ring_tail_kernel", "ACQBULK")
+    for k in ("emd_pass_kernel", "emd_combine_kernel", "emd_compact_kernel", "emd_init_kernel", "emd_cost_finish_kernel"):
+        assert has(k, "PREEXIT") and has(k, "ACQBULK"), k                                   # every link of the auction's chain
